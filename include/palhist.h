@@ -1,0 +1,202 @@
+/*
+ * palhist.h — C ABI of the B200-native colour kernels (libpalhist.so).
+ *
+ * Drop-in boundary for the per-pixel colour path of fegemo/palette-and-histo-gan.  The reference
+ * has no FFI of its own: its boundary is a set of Python callables over TensorFlow ops.  Each entry
+ * point below names the reference callable (file:line under /root/reference) whose arithmetic it
+ * replaces; the Python host in `palette-and-histo-gan_b200/` keeps those callables' signatures and
+ * forwards to these functions through ctypes (see INTEGRATION.md for the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `const T*` / `T*` is a DEVICE pointer unless the
+ *     parameter name ends in `_host`;
+ *   - all tensors are caller-owned, dense, row-major (C-contiguous) in the layouts stated;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); kernels are
+ *     enqueued on it and the call returns without synchronising unless stated otherwise;
+ *   - return value: PH_OK (0) or a negative PH_ERR_* code; `ph_last_error()` returns a
+ *     thread-local message for the last failing call on this host thread;
+ *   - re-entrant: no global mutable state; scratch memory is passed in by the caller
+ *     (`workspace`, size from the matching `*_workspace_bytes`).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     PH_ERR_CUDA.
+ */
+#ifndef PALHIST_H_
+#define PALHIST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PH_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PH_API __attribute__((visibility("default")))
+#else
+#define PH_API
+#endif
+
+enum ph_status {
+  PH_OK = 0,
+  PH_ERR_INVALID = -1,     /* bad argument (shape, enum, NULL pointer, workspace too small) */
+  PH_ERR_CUDA = -2,        /* CUDA runtime / launch failure (message has cudaGetErrorString) */
+  PH_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve (e.g. tensor-core path, bins not multiple of 64) */
+};
+
+/* histogram.py:22-27 — the two bin kernels the reference implements. */
+enum ph_method { PH_METHOD_INVERSE_QUADRATIC = 0, PH_METHOD_RBF = 1 };
+
+/* io_utils.py:44-58 — deterministic palette orderings ("shuffled" is a host-side permutation). */
+enum ph_ordering { PH_ORDER_TOP2BOTTOM = 0, PH_ORDER_BOTTOM2TOP = 1, PH_ORDER_GRAYNESS = 2 };
+
+/* rgba_to_indexed flavour: the reference's exact-match scatter-add (io_utils.py:84-91) or
+ * nearest colour (first arg-min of squared RGBA distance; equal to the former whenever every
+ * pixel colour occurs exactly once in the palette). */
+enum ph_index_mode { PH_INDEX_EXACT_SUM = 0, PH_INDEX_NEAREST = 1 };
+
+/* Contraction engine for the histogram GEMMs. */
+enum ph_impl {
+  PH_IMPL_AUTO = 0, /* tensor cores when the shape allows, else SIMT */
+  PH_IMPL_SIMT = 1, /* fp32 CUDA-core contraction (any bin count) */
+  PH_IMPL_TC = 2,   /* tcgen05 3xTF32 contraction, accumulators in TMEM */
+};
+
+/* per-image status written by ph_extract_palette into ncolors[]: >=0 colour count (may exceed 256 =
+ * overflow, palette undefined — the reference raises there, io_utils.py:62); PH_PALETTE_BAD_VALUE
+ * when a channel value lies outside [0,255]. */
+#define PH_PALETTE_BAD_VALUE (-1)
+#define PH_MAX_PALETTE_SIZE 256 /* configuration.py:31 */
+
+PH_API int ph_abi_version(void);
+PH_API const char* ph_last_error(void);
+/* Number of kernel launches issued through this library by this process (all threads) since the
+ * last reset (bench.py's `gpu_launches`). */
+PH_API int64_t ph_launch_count(void);
+PH_API void ph_reset_launch_count(void);
+/* sm_count / compute capability of `device`; PH_ERR_CUDA without a usable GPU. */
+PH_API int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * RGB-uv histogram  (histogram.py:36-81 `calculate_rgbuv_histogram`)
+ * ------------------------------------------------------------------------------------------
+ * image        (batch, npix, channels) float32 in [-1,1], channels = 3 or 4 (alpha ignored, :61)
+ * bin_centers  (bins) float32 — the `tf.linspace(-3,3,size)` tensor of :55 passed as data
+ * hist         (batch, bins, bins, 3) float32, each image sums to 1 (:78-79)
+ * denom        (batch) float32 — the per-image normaliser of :78 (needed by the backward)
+ */
+PH_API size_t ph_hist_workspace_bytes(int64_t batch, int64_t npix, int bins, int impl);
+
+PH_API int ph_hist_forward(const float* image, int64_t batch, int64_t npix, int channels,
+                    const float* bin_centers, int bins, int method, float sigma_sqr, float epsilon,
+                    float* hist, float* denom, void* workspace, size_t workspace_bytes, int impl,
+                    void* stream);
+
+/* histogram.py:5-32 `calculate_component_histogram`: un-normalised (batch,bins,bins) histogram of one
+ * component against two projections, intensities (batch,npix) given. */
+PH_API int ph_component_histogram(const float* component, const float* projection1, const float* projection2,
+                           const float* color_intensities, int64_t batch, int64_t npix,
+                           const float* bin_centers, int bins, int method, float sigma_sqr,
+                           float epsilon, float* hist_raw, void* stream);
+
+/* Backward of ph_hist_forward (TF autodiff in the reference, pix2pix_model.py:78).  Exactly one of
+ * the two upstream forms is used:
+ *   (a) grad_hist != NULL: dL/dhist, (batch,bins,bins,3) float32;
+ *   (b) grad_hist == NULL: the Hellinger loss of histogram.py:84-89 is differentiated in the
+ *       prologue from hist_true, *ssum (device double, whole-batch sum of squares — after the
+ *       all-reduce when the batch is sharded), global_batch and the upstream scalar *loss_scale (device float; NULL = 1).
+ * grad_image (batch, npix, channels) float32; the alpha channel (if any) is written as 0. */
+PH_API int ph_hist_backward(const float* image, int64_t batch, int64_t npix, int channels,
+                     const float* bin_centers, int bins, int method, float sigma_sqr, float epsilon,
+                     const float* hist_pred, const float* denom_pred, const float* grad_hist,
+                     const float* hist_true, const double* ssum, int64_t global_batch,
+                     const float* loss_scale, float* grad_image, void* workspace, size_t workspace_bytes,
+                     int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hellinger / L1 / L2 histogram losses  (histogram.py:84-97)
+ * ------------------------------------------------------------------------------------------ */
+/* *ssum (device double) = sum over n elements of (sqrt(pred)-sqrt(true))^2; overwritten. */
+PH_API int ph_hellinger_ssum(const float* hist_true, const float* hist_pred, int64_t n, double* ssum,
+                      void* stream);
+/* *loss (device float) = (1/sqrt 2) * sqrt(*ssum) / global_batch. */
+PH_API int ph_hellinger_finish(const double* ssum, int64_t global_batch, float* loss, void* stream);
+/* Backward of the Hellinger loss: d loss / d hist for either argument (NULL = not wanted), n elements,
+ * scaled by the upstream scalar *loss_scale (device float; NULL = 1); *ssum is the whole-batch sum
+ * of squares. */
+PH_API int ph_hellinger_backward(const float* hist_true, const float* hist_pred, int64_t n, const double* ssum,
+                          int64_t global_batch, const float* loss_scale, float* grad_true, float* grad_pred,
+                          void* stream);
+/* *out (device float) = mean |a-b| (kind 1) or mean (a-b)^2 (kind 2) over n elements. */
+PH_API int ph_mean_abs_or_sq_diff(const float* a, const float* b, int64_t n, int kind, float* out,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Palette helpers  (io_utils.py:25-103, pix2pix_model.py:300-301, dataset_utils.py:131-151)
+ * ------------------------------------------------------------------------------------------ */
+/* io_utils.py:25-65 `extract_palette`, batched.  image (batch, rows, 4) int32 with values in
+ * [0,255]; rows are the pixels in reshape(-1,4) order.  palette (batch,256,4) int32 padded with
+ * INVALID_INDEX_COLOR (configuration.py:32); ncolors (batch) int32, see PH_PALETTE_BAD_VALUE. */
+PH_API int ph_extract_palette(const int32_t* image, int64_t batch, int64_t rows, int ordering,
+                       int32_t* palette, int32_t* ncolors, void* stream);
+
+/* io_utils.py:78-93 `rgba_to_indexed`, batched, optionally fused with the one-hot of
+ * pix2pix_model.py:300-301.  image (batch,npix,4) int32; palette (palette_batch,256,4) int32 with
+ * palette_batch == batch or 1 (shared); indexed (batch,npix) int32; one_hot NULL or
+ * (batch,npix,depth) float32 (index outside [0,depth) -> all-zero row, TF semantics). */
+PH_API int ph_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,
+                       int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
+                       void* stream);
+
+/* pix2pix_model.py:300-301 `tf.one_hot(idx, depth)`: indexed (n) int32 -> one_hot (n,depth) float32. */
+PH_API int ph_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, void* stream);
+
+/* io_utils.py:96-103 `indexed_to_rgba`: out[b,n,:] = palette[b or 0, indexed[b,n], :]; an index
+ * outside [0,palette_rows) is a PH_ERR_INVALID-free no-op row of zeros (TF's GPU gather semantics). */
+PH_API int ph_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npix, const int32_t* palette,
+                       int64_t palette_batch, int palette_rows, int channels, int32_t* out,
+                       void* stream);
+
+/* dataset_utils.py:138-151 glue, batched: shared palette of source||target (rows interleaved
+ * src px0, tgt px0, src px1, ... as the channel-axis concat + reshape(-1,4) produces), then both
+ * index images.  source/target (batch,npix,4) int32. */
+PH_API int ph_load_indexed_images(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
+                           int ordering, int32_t* source_indexed, int32_t* target_indexed,
+                           int32_t* palette, int32_t* ncolors, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer convenience (the call a CPU-side caller such as a tf.data worker binds):
+ * pinned or pageable HOST pointers in and out; device staging, chunked H2D/compute/D2H overlap and
+ * one final stream synchronise happen inside.  `ctx` from ph_host_ctx_create (one per host thread).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ph_host_ctx ph_host_ctx;
+PH_API int ph_host_ctx_create(int device, ph_host_ctx** ctx);
+PH_API void ph_host_ctx_destroy(ph_host_ctx* ctx);
+
+/* pix2pix_model.py:243-245 + :78 in one call: loss and d loss / d fake for host images.
+ * real_host / fake_host / grad_fake_host (batch,npix,channels) float32; loss_host 1 float. */
+PH_API int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
+                      int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
+                      float sigma_sqr, float epsilon, int impl, float* loss_host,
+                      float* grad_fake_host);
+
+/* The same in two phases for a batch sharded over processes: `begin` uploads, runs both forward
+ * passes and returns this shard's sum of squares (host double); the caller all-reduces it; `finish`
+ * takes the whole-batch sum and batch size, returns the loss and this shard's gradient. */
+PH_API int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
+                       int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
+                       float sigma_sqr, float epsilon, int impl, double* ssum_local_host);
+PH_API int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
+                        float* grad_fake_host);
+
+/* dataset_utils.py:138-151 for host images (+ optional one-hot of the target indices). */
+PH_API int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,
+                                int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
+                                int32_t* target_indexed_host, int32_t* palette_host,
+                                int32_t* ncolors_host, float* target_one_hot_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PALHIST_H_ */

@@ -1,0 +1,265 @@
+// extern "C" surface of libpalhist.so — argument validation and engine dispatch only.
+// See include/palhist.h for the contract and the reference file:line each entry point replaces.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+#include "hist_internal.cuh"
+
+namespace ph {
+
+static thread_local char g_error[512] = "";
+static std::atomic<int64_t> g_launches{0};  // process-wide: autograd runs backward on its own thread
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int cached_sm_count() {
+  static int counts[64];
+  static std::once_flag once;
+  std::call_once(once, [] { memset(counts, 0, sizeof(counts)); });
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (counts[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    counts[dev] = n;
+  }
+  return counts[dev];
+}
+
+static int resolve_impl(int impl, int64_t npix, int bins, int method) {
+  if (impl == PH_IMPL_AUTO) return tc_supported(npix, bins, method) ? PH_IMPL_TC : PH_IMPL_SIMT;
+  return impl;
+}
+
+static int check_hist_args(const void* image, int64_t batch, int64_t npix, int channels,
+                           const void* dom, int bins, int method, float sigma_sqr) {
+  PH_CHECK_ARG(image != nullptr && dom != nullptr, "image / bin_centers must not be NULL");
+  PH_CHECK_ARG(batch >= 0 && npix > 0, "bad shape: batch=%lld npix=%lld", (long long)batch, (long long)npix);
+  PH_CHECK_ARG(channels == 3 || channels == 4, "channels must be 3 or 4 (got %d)", channels);
+  PH_CHECK_ARG(bins >= 1 && bins <= 1024, "bins must be in [1,1024] (got %d)", bins);
+  PH_CHECK_ARG(method == PH_METHOD_INVERSE_QUADRATIC || method == PH_METHOD_RBF,
+               "unknown histogram method %d (the reference silently mis-computes here, histogram.py:22-27)", method);
+  PH_CHECK_ARG(sigma_sqr > 0.f, "sigma_sqr must be positive");
+  PH_CHECK_ARG(channels != 4 || (reinterpret_cast<uintptr_t>(image) & 15) == 0,
+               "RGBA image pointer must be 16-byte aligned");
+  return PH_OK;
+}
+
+}  // namespace ph
+
+using namespace ph;
+
+extern "C" {
+
+int ph_abi_version(void) { return PH_ABI_VERSION; }
+const char* ph_last_error(void) { return g_error; }
+int64_t ph_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void ph_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  cudaDeviceProp prop;
+  PH_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return PH_OK;
+}
+
+size_t ph_hist_workspace_bytes(int64_t batch, int64_t npix, int bins, int impl) {
+  if (batch <= 0 || npix <= 0 || bins <= 0) return 256;
+  size_t s = simt_workspace_bytes(batch, npix, bins);
+  if (impl != PH_IMPL_SIMT) {
+    const size_t t = tc_workspace_bytes(batch, npix, bins);
+    if (t > s) s = t;
+  }
+  return s;
+}
+
+int ph_hist_forward(const float* image, int64_t batch, int64_t npix, int channels,
+                    const float* bin_centers, int bins, int method, float sigma_sqr, float epsilon,
+                    float* hist, float* denom, void* workspace, size_t workspace_bytes, int impl,
+                    void* stream) {
+  int rc = check_hist_args(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr);
+  if (rc != PH_OK) return rc;
+  PH_CHECK_ARG(hist != nullptr && denom != nullptr, "hist / denom must not be NULL");
+  PH_CHECK_ARG(impl >= PH_IMPL_AUTO && impl <= PH_IMPL_TC, "bad impl %d", impl);
+  if (batch == 0) return PH_OK;
+  const int eng = resolve_impl(impl, npix, bins, method);
+  PH_CHECK_ARG(workspace != nullptr && workspace_bytes >= ph_hist_workspace_bytes(batch, npix, bins, eng),
+               "workspace too small: %zu < %zu", workspace_bytes, ph_hist_workspace_bytes(batch, npix, bins, eng));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (eng == PH_IMPL_TC) {
+    if (!tc_supported(npix, bins, method)) {
+      set_error("tensor-core engine does not cover npix=%lld bins=%d method=%d", (long long)npix, bins, method);
+      return PH_ERR_UNSUPPORTED;
+    }
+    return tc_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist,
+                           denom, workspace, st);
+  }
+  return simt_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist,
+                           denom, workspace, st);
+}
+
+int ph_component_histogram(const float* component, const float* projection1, const float* projection2,
+                           const float* color_intensities, int64_t batch, int64_t npix,
+                           const float* bin_centers, int bins, int method, float sigma_sqr,
+                           float epsilon, float* hist_raw, void* stream) {
+  PH_CHECK_ARG(component && projection1 && projection2 && color_intensities && bin_centers && hist_raw,
+               "NULL pointer argument");
+  PH_CHECK_ARG(batch >= 0 && npix > 0, "bad shape");
+  PH_CHECK_ARG(bins >= 1 && bins <= 1024, "bins must be in [1,1024] (got %d)", bins);
+  PH_CHECK_ARG(method == PH_METHOD_INVERSE_QUADRATIC || method == PH_METHOD_RBF, "unknown histogram method %d", method);
+  PH_CHECK_ARG(sigma_sqr > 0.f, "sigma_sqr must be positive");
+  if (batch == 0) return PH_OK;
+  return simt_component_histogram(component, projection1, projection2, color_intensities, batch, npix,
+                                  bin_centers, bins, method, sigma_sqr, epsilon, hist_raw,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int ph_hist_backward(const float* image, int64_t batch, int64_t npix, int channels,
+                     const float* bin_centers, int bins, int method, float sigma_sqr, float epsilon,
+                     const float* hist_pred, const float* denom_pred, const float* grad_hist,
+                     const float* hist_true, const double* ssum, int64_t global_batch,
+                     const float* loss_scale, float* grad_image, void* workspace, size_t workspace_bytes,
+                     int impl, void* stream) {
+  int rc = check_hist_args(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr);
+  if (rc != PH_OK) return rc;
+  PH_CHECK_ARG(hist_pred && denom_pred && grad_image, "hist_pred / denom_pred / grad_image must not be NULL");
+  PH_CHECK_ARG(grad_hist != nullptr || (hist_true != nullptr && ssum != nullptr && global_batch > 0),
+               "either grad_hist or (hist_true, ssum, global_batch>0) must be given");
+  PH_CHECK_ARG(impl >= PH_IMPL_AUTO && impl <= PH_IMPL_TC, "bad impl %d", impl);
+  PH_CHECK_ARG(channels != 4 || (reinterpret_cast<uintptr_t>(grad_image) & 15) == 0,
+               "RGBA gradient pointer must be 16-byte aligned");
+  if (batch == 0) return PH_OK;
+  const int eng = resolve_impl(impl, npix, bins, method);
+  PH_CHECK_ARG(workspace != nullptr && workspace_bytes >= ph_hist_workspace_bytes(batch, npix, bins, eng),
+               "workspace too small: %zu < %zu", workspace_bytes, ph_hist_workspace_bytes(batch, npix, bins, eng));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (eng == PH_IMPL_TC) {
+    if (!tc_supported(npix, bins, method)) {
+      set_error("tensor-core engine does not cover npix=%lld bins=%d method=%d", (long long)npix, bins, method);
+      return PH_ERR_UNSUPPORTED;
+    }
+    return tc_hist_backward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon,
+                            hist_pred, denom_pred, grad_hist, hist_true, ssum, global_batch, loss_scale,
+                            grad_image, workspace, st);
+  }
+  return simt_hist_backward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon,
+                            hist_pred, denom_pred, grad_hist, hist_true, ssum, global_batch, loss_scale,
+                            grad_image, workspace, st);
+}
+
+int ph_hellinger_ssum(const float* hist_true, const float* hist_pred, int64_t n, double* ssum, void* stream) {
+  PH_CHECK_ARG(hist_true && hist_pred && ssum && n >= 0, "bad argument");
+  return launch_hellinger_ssum(hist_true, hist_pred, n, ssum, static_cast<cudaStream_t>(stream));
+}
+
+int ph_hellinger_finish(const double* ssum, int64_t global_batch, float* loss, void* stream) {
+  PH_CHECK_ARG(ssum && loss && global_batch > 0, "bad argument");
+  return launch_hellinger_finish(ssum, global_batch, loss, static_cast<cudaStream_t>(stream));
+}
+
+int ph_hellinger_backward(const float* hist_true, const float* hist_pred, int64_t n, const double* ssum,
+                          int64_t global_batch, const float* loss_scale, float* grad_true, float* grad_pred,
+                          void* stream) {
+  PH_CHECK_ARG(hist_true && hist_pred && ssum && n >= 0 && global_batch > 0, "bad argument");
+  PH_CHECK_ARG(grad_true || grad_pred, "at least one gradient output is required");
+  return launch_hellinger_backward(hist_true, hist_pred, n, ssum, global_batch, loss_scale, grad_true, grad_pred,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int ph_mean_abs_or_sq_diff(const float* a, const float* b, int64_t n, int kind, float* out, void* stream) {
+  PH_CHECK_ARG(a && b && out && n > 0, "bad argument");
+  PH_CHECK_ARG(kind == 1 || kind == 2, "kind must be 1 (L1) or 2 (L2)");
+  return launch_diff_reduce(a, b, n, kind, out, static_cast<cudaStream_t>(stream));
+}
+
+int ph_extract_palette(const int32_t* image, int64_t batch, int64_t rows, int ordering,
+                       int32_t* palette, int32_t* ncolors, void* stream) {
+  PH_CHECK_ARG(image && palette && ncolors, "NULL pointer argument");
+  PH_CHECK_ARG(batch >= 0 && rows > 0, "bad shape");
+  PH_CHECK_ARG(ordering >= PH_ORDER_TOP2BOTTOM && ordering <= PH_ORDER_GRAYNESS, "bad ordering %d", ordering);
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0 && (reinterpret_cast<uintptr_t>(palette) & 15) == 0,
+               "image / palette must be 16-byte aligned");
+  return launch_extract_palette(image, nullptr, batch, rows, ordering, palette, ncolors,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int ph_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,
+                       int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
+                       void* stream) {
+  PH_CHECK_ARG(image && palette && indexed, "NULL pointer argument");
+  PH_CHECK_ARG(batch >= 0 && npix >= 0, "bad shape");
+  PH_CHECK_ARG(palette_batch == 1 || palette_batch == batch, "palette_batch must be 1 or batch");
+  PH_CHECK_ARG(mode == PH_INDEX_EXACT_SUM || mode == PH_INDEX_NEAREST, "bad index mode %d", mode);
+  PH_CHECK_ARG(one_hot == nullptr || depth > 0, "one-hot depth must be positive");
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0 && (reinterpret_cast<uintptr_t>(palette) & 15) == 0,
+               "image / palette must be 16-byte aligned");
+  PH_CHECK_ARG(one_hot == nullptr || (reinterpret_cast<uintptr_t>(one_hot) & 15) == 0, "one_hot must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // gridDim.y limit: split very large batches
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    int rc = launch_rgba_to_indexed(image + b0 * npix * 4, nb, npix,
+                                    palette + (palette_batch == 1 ? 0 : b0 * PH_MAX_PALETTE_SIZE * 4),
+                                    palette_batch == 1 ? 1 : nb, mode, indexed + b0 * npix,
+                                    one_hot ? one_hot + b0 * npix * depth : nullptr, depth, st);
+    if (rc != PH_OK) return rc;
+  }
+  return PH_OK;
+}
+
+int ph_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, void* stream) {
+  PH_CHECK_ARG(indexed && one_hot && n >= 0 && depth > 0, "bad argument");
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(one_hot) & 15) == 0, "one_hot must be 16-byte aligned");
+  return launch_one_hot(indexed, n, depth, one_hot, static_cast<cudaStream_t>(stream));
+}
+
+int ph_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npix, const int32_t* palette,
+                       int64_t palette_batch, int palette_rows, int channels, int32_t* out, void* stream) {
+  PH_CHECK_ARG(indexed && palette && out, "NULL pointer argument");
+  PH_CHECK_ARG(batch >= 0 && npix >= 0 && palette_rows > 0 && channels > 0, "bad shape");
+  PH_CHECK_ARG(palette_batch == 1 || palette_batch == batch, "palette_batch must be 1 or batch");
+  PH_CHECK_ARG(channels != 4 || ((reinterpret_cast<uintptr_t>(palette) & 15) == 0 &&
+                                 (reinterpret_cast<uintptr_t>(out) & 15) == 0),
+               "RGBA palette / out must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+    const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    int rc = launch_indexed_to_rgba(indexed + b0 * npix, nb, npix,
+                                    palette + (palette_batch == 1 ? 0 : b0 * (int64_t)palette_rows * channels),
+                                    palette_batch == 1 ? 1 : nb, palette_rows, channels,
+                                    out + b0 * npix * channels, st);
+    if (rc != PH_OK) return rc;
+  }
+  return PH_OK;
+}
+
+int ph_load_indexed_images(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
+                           int ordering, int32_t* source_indexed, int32_t* target_indexed,
+                           int32_t* palette, int32_t* ncolors, void* stream) {
+  PH_CHECK_ARG(source && target && source_indexed && target_indexed && palette && ncolors, "NULL pointer argument");
+  PH_CHECK_ARG(batch >= 0 && npix > 0, "bad shape");
+  PH_CHECK_ARG(ordering >= PH_ORDER_TOP2BOTTOM && ordering <= PH_ORDER_GRAYNESS, "bad ordering %d", ordering);
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(source) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(palette) & 15) == 0,
+               "source / target / palette must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = launch_extract_palette(source, target, batch, 2 * npix, ordering, palette, ncolors, st);
+  if (rc != PH_OK) return rc;
+  rc = ph_rgba_to_indexed(source, batch, npix, palette, batch, PH_INDEX_EXACT_SUM, source_indexed, nullptr, 0, stream);
+  if (rc != PH_OK) return rc;
+  return ph_rgba_to_indexed(target, batch, npix, palette, batch, PH_INDEX_EXACT_SUM, target_indexed, nullptr, 0, stream);
+}
+
+}  // extern "C"

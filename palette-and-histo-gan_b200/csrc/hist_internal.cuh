@@ -1,0 +1,59 @@
+// Internal launcher prototypes shared between the translation units of libpalhist.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace ph {
+
+int cached_sm_count();  // SM count of the current device (148 on B200), cached per device
+
+// ---- hist_simt.cu ---------------------------------------------------------------------------
+int simt_fwd_splits(int64_t batch, int64_t npix, int bins);
+size_t simt_workspace_bytes(int64_t batch, int64_t npix, int bins);
+int simt_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
+                      int bins, int method, float sigma_sqr, float eps, float* hist, float* denom,
+                      void* workspace, cudaStream_t st);
+int simt_component_histogram(const float* comp, const float* proj1, const float* proj2,
+                             const float* inten, int64_t batch, int64_t npix, const float* dom, int bins,
+                             int method, float sigma_sqr, float eps, float* hist_raw, cudaStream_t st);
+int launch_bwd_prep(const float* hist_pred, const float* denom, const float* grad_hist,
+                    const float* hist_true, const double* ssum, int64_t global_batch, const float* loss_scale,
+                    int64_t batch, int bins, float* ghat, cudaStream_t st);
+int simt_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
+                       int bins, int method, float sigma_sqr, float eps, const float* hist_pred,
+                       const float* denom, const float* grad_hist, const float* hist_true,
+                       const double* ssum, int64_t global_batch, const float* loss_scale, float* grad_image,
+                       void* workspace, cudaStream_t st);
+int launch_hellinger_ssum(const float* ht, const float* hp, int64_t n, double* ssum, cudaStream_t st);
+int launch_hellinger_finish(const double* ssum, int64_t global_batch, float* loss, cudaStream_t st);
+int launch_hellinger_backward(const float* ht, const float* hp, int64_t n, const double* ssum,
+                              int64_t global_batch, const float* loss_scale, float* grad_true, float* grad_pred,
+                              cudaStream_t st);
+int launch_diff_reduce(const float* a, const float* b, int64_t n, int kind, float* out, cudaStream_t st);
+
+// ---- hist_tc.cu (tcgen05 engine) --------------------------------------------------------------
+bool tc_supported(int64_t npix, int bins, int method);
+size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins);
+int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
+                    int bins, int method, float sigma_sqr, float eps, float* hist, float* denom,
+                    void* workspace, cudaStream_t st);
+int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
+                     int bins, int method, float sigma_sqr, float eps, const float* hist_pred,
+                     const float* denom, const float* grad_hist, const float* hist_true,
+                     const double* ssum, int64_t global_batch, const float* loss_scale, float* grad_image,
+                     void* workspace, cudaStream_t st);
+
+// ---- palette.cu -------------------------------------------------------------------------------
+int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows,
+                           int ordering, int32_t* palette, int32_t* ncolors, cudaStream_t st);
+int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,
+                           int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
+                           cudaStream_t st);
+int launch_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, cudaStream_t st);
+int launch_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npix, const int32_t* palette,
+                           int64_t palette_batch, int palette_rows, int channels, int32_t* out,
+                           cudaStream_t st);
+
+}  // namespace ph

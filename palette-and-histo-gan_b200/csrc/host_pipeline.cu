@@ -1,0 +1,277 @@
+// Host-buffer entry points: the calls a CPU-side caller (a tf.data worker, a cgo/JNI-style binding)
+// makes with plain host arrays.  Device staging is owned by an opaque per-thread context; batches
+// are cut into chunks so the H2D copy of chunk k+1 overlaps the forward kernels of chunk k, and the
+// D2H copy of gradient chunk k overlaps the backward kernels of chunk k+1.  The Hellinger loss
+// couples all images through one scalar (histogram.py:88-89), hence the two phases.
+#include <new>
+
+#include "common.cuh"
+#include "hist_internal.cuh"
+
+struct ph_host_ctx {
+  int device = 0;
+  cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+  // grow-only device arena
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+  static constexpr int kMaxChunks = 64;
+  cudaEvent_t ev_in[kMaxChunks];
+  cudaEvent_t ev_done[kMaxChunks];
+  cudaEvent_t ev_free[2];
+  bool events_ready = false;
+  // state carried from ph_host_hist_begin to ph_host_hist_finish
+  struct Job {
+    float *d_fake, *d_real[2], *d_hreal, *d_hfake, *d_denom_r, *d_denom_f, *d_grad[2], *d_dom, *d_loss;
+    double* d_ssum;
+    char* d_ws;
+    size_t ws_bytes;
+    int64_t batch, npix, chunk;
+    int channels, bins, method, impl, nchunks;
+    float sigma_sqr, epsilon;
+  } job;
+  bool job_valid = false;
+};
+
+namespace ph {
+
+static int ensure_arena(ph_host_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->arena_bytes) return PH_OK;
+  if (ctx->arena) {
+    PH_CUDA_OK(cudaDeviceSynchronize());
+    PH_CUDA_OK(cudaFree(ctx->arena));
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+  }
+  PH_CUDA_OK(cudaMalloc(&ctx->arena, bytes));
+  ctx->arena_bytes = bytes;
+  return PH_OK;
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace ph
+
+using namespace ph;
+
+extern "C" {
+
+int ph_host_ctx_create(int device, ph_host_ctx** out) {
+  PH_CHECK_ARG(out != nullptr, "ctx output pointer is NULL");
+  PH_CUDA_OK(cudaSetDevice(device));
+  ph_host_ctx* ctx = new (std::nothrow) ph_host_ctx();
+  PH_CHECK_ARG(ctx != nullptr, "out of host memory");
+  ctx->device = device;
+  PH_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+  PH_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+  PH_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+  for (int i = 0; i < ph_host_ctx::kMaxChunks; ++i) {
+    PH_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+    PH_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 2; ++i) PH_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+  ctx->events_ready = true;
+  *out = ctx;
+  return PH_OK;
+}
+
+void ph_host_ctx_destroy(ph_host_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->events_ready) {
+    for (int i = 0; i < ph_host_ctx::kMaxChunks; ++i) {
+      cudaEventDestroy(ctx->ev_in[i]);
+      cudaEventDestroy(ctx->ev_done[i]);
+    }
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->ev_free[i]);
+  }
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+  if (ctx->arena) cudaFree(ctx->arena);
+  delete ctx;
+}
+
+// Two-phase form (ph_host_hist_begin / ph_host_hist_finish): the caller may all-reduce the local sum
+// of squares over ranks between the phases; ph_host_hist_loss is the single-process composition.
+int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
+                       int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
+                       float sigma_sqr, float epsilon, int impl, double* ssum_local_host) {
+  PH_CHECK_ARG(ctx && real_host && fake_host && bin_centers_host && ssum_local_host, "NULL pointer argument");
+  PH_CHECK_ARG(batch > 0 && npix > 0 && (channels == 3 || channels == 4), "bad shape");
+  PH_CHECK_ARG(bins >= 1 && bins <= 1024, "bins must be in [1,1024]");
+  PH_CUDA_OK(cudaSetDevice(ctx->device));
+  ctx->job_valid = false;
+
+  // chunking: at least 8 MiB per copy, at most kMaxChunks chunks
+  const size_t img_bytes = (size_t)npix * channels * sizeof(float);
+  int64_t chunk = (int64_t)((8u << 20) / img_bytes);
+  if (chunk < 1) chunk = 1;
+  if (ceil_div(batch, chunk) > ph_host_ctx::kMaxChunks) chunk = ceil_div(batch, ph_host_ctx::kMaxChunks);
+  const int nchunks = (int)ceil_div(batch, chunk);
+  const size_t hist_elems = (size_t)bins * bins * 3;
+  const size_t ws_bytes = ph_hist_workspace_bytes(chunk, npix, bins, impl);
+
+  ph_host_ctx::Job& J = ctx->job;
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass == 0 ? nullptr : ctx->arena);
+    J.d_fake = cv.take<float>((size_t)batch * npix * channels);
+    J.d_real[0] = cv.take<float>((size_t)chunk * npix * channels);
+    J.d_real[1] = cv.take<float>((size_t)chunk * npix * channels);
+    J.d_hreal = cv.take<float>((size_t)batch * hist_elems);
+    J.d_hfake = cv.take<float>((size_t)batch * hist_elems);
+    J.d_denom_r = cv.take<float>((size_t)batch);
+    J.d_denom_f = cv.take<float>((size_t)batch);
+    J.d_grad[0] = cv.take<float>((size_t)chunk * npix * channels);
+    J.d_grad[1] = cv.take<float>((size_t)chunk * npix * channels);
+    J.d_dom = cv.take<float>((size_t)bins);
+    J.d_ssum = cv.take<double>(1);
+    J.d_loss = cv.take<float>(1);
+    J.d_ws = cv.take<char>(ws_bytes);
+    if (pass == 0) {
+      int rc = ensure_arena(ctx, align_up(cv.off, 256) + 256);
+      if (rc != PH_OK) return rc;
+    }
+  }
+  J.batch = batch; J.npix = npix; J.channels = channels; J.bins = bins; J.method = method;
+  J.sigma_sqr = sigma_sqr; J.epsilon = epsilon; J.impl = impl; J.chunk = chunk; J.nchunks = nchunks;
+  J.ws_bytes = ws_bytes;
+
+  PH_CUDA_OK(cudaMemcpyAsync(J.d_dom, bin_centers_host, sizeof(float) * bins, cudaMemcpyHostToDevice, ctx->s_in));
+  // ---- phase A: upload + forward, chunk by chunk ----
+  for (int k = 0; k < nchunks; ++k) {
+    const int64_t b0 = (int64_t)k * chunk;
+    const int64_t nb = batch - b0 < chunk ? batch - b0 : chunk;
+    const size_t n = (size_t)nb * npix * channels;
+    const int slot = k & 1;
+    if (k >= 2) PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_free[slot], 0));
+    PH_CUDA_OK(cudaMemcpyAsync(J.d_real[slot], real_host + (size_t)b0 * npix * channels, n * sizeof(float),
+                               cudaMemcpyHostToDevice, ctx->s_in));
+    PH_CUDA_OK(cudaMemcpyAsync(J.d_fake + (size_t)b0 * npix * channels, fake_host + (size_t)b0 * npix * channels,
+                               n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_in));
+    PH_CUDA_OK(cudaEventRecord(ctx->ev_in[k], ctx->s_in));
+    PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[k], 0));
+    int rc = ph_hist_forward(J.d_real[slot], nb, npix, channels, J.d_dom, bins, method, sigma_sqr, epsilon,
+                             J.d_hreal + (size_t)b0 * hist_elems, J.d_denom_r + b0, J.d_ws, ws_bytes, impl,
+                             ctx->s_compute);
+    if (rc != PH_OK) return rc;
+    PH_CUDA_OK(cudaEventRecord(ctx->ev_free[slot], ctx->s_compute));
+    rc = ph_hist_forward(J.d_fake + (size_t)b0 * npix * channels, nb, npix, channels, J.d_dom, bins, method,
+                         sigma_sqr, epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0, J.d_ws, ws_bytes,
+                         impl, ctx->s_compute);
+    if (rc != PH_OK) return rc;
+  }
+  // ---- the one coupling scalar ----
+  int rc = ph_hellinger_ssum(J.d_hreal, J.d_hfake, (int64_t)(batch * hist_elems), J.d_ssum, ctx->s_compute);
+  if (rc != PH_OK) return rc;
+  PH_CUDA_OK(cudaMemcpyAsync(ssum_local_host, J.d_ssum, sizeof(double), cudaMemcpyDeviceToHost, ctx->s_compute));
+  PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+  ctx->job_valid = true;
+  return PH_OK;
+}
+
+int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
+                        float* grad_fake_host) {
+  PH_CHECK_ARG(ctx && loss_host, "NULL pointer argument");
+  PH_CHECK_ARG(ctx->job_valid, "ph_host_hist_finish without a preceding successful ph_host_hist_begin");
+  PH_CHECK_ARG(global_batch > 0, "global_batch must be positive");
+  PH_CUDA_OK(cudaSetDevice(ctx->device));
+  ctx->job_valid = false;
+  const ph_host_ctx::Job& J = ctx->job;
+  const size_t hist_elems = (size_t)J.bins * J.bins * 3;
+  PH_CUDA_OK(cudaMemcpyAsync(J.d_ssum, &ssum_global, sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
+  int rc = ph_hellinger_finish(J.d_ssum, global_batch, J.d_loss, ctx->s_compute);
+  if (rc != PH_OK) return rc;
+  PH_CUDA_OK(cudaMemcpyAsync(loss_host, J.d_loss, sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
+  // ---- phase B: backward + download, chunk by chunk ----
+  if (grad_fake_host) {
+    for (int k = 0; k < J.nchunks; ++k) {
+      const int64_t b0 = (int64_t)k * J.chunk;
+      const int64_t nb = J.batch - b0 < J.chunk ? J.batch - b0 : J.chunk;
+      const size_t n = (size_t)nb * J.npix * J.channels;
+      const int slot = k & 1;
+      if (k >= 2) PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[k - 2], 0));  // grad slot drained
+      rc = ph_hist_backward(J.d_fake + (size_t)b0 * J.npix * J.channels, nb, J.npix, J.channels, J.d_dom, J.bins,
+                            J.method, J.sigma_sqr, J.epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0,
+                            nullptr, J.d_hreal + (size_t)b0 * hist_elems, J.d_ssum, global_batch, nullptr,
+                            J.d_grad[slot], J.d_ws, J.ws_bytes, J.impl, ctx->s_compute);
+      if (rc != PH_OK) return rc;
+      PH_CUDA_OK(cudaEventRecord(ctx->ev_done[k], ctx->s_compute));
+      PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[k], 0));
+      PH_CUDA_OK(cudaMemcpyAsync(grad_fake_host + (size_t)b0 * J.npix * J.channels, J.d_grad[slot], n * sizeof(float),
+                                 cudaMemcpyDeviceToHost, ctx->s_out));
+      PH_CUDA_OK(cudaEventRecord(ctx->ev_in[k], ctx->s_out));  // reuse ev_in[k] as "slot drained"
+    }
+  }
+  PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+  PH_CUDA_OK(cudaStreamSynchronize(ctx->s_out));
+  return PH_OK;
+}
+
+int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
+                      int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
+                      float sigma_sqr, float epsilon, int impl, float* loss_host, float* grad_fake_host) {
+  double ssum = 0.0;
+  int rc = ph_host_hist_begin(ctx, real_host, fake_host, batch, npix, channels, bin_centers_host, bins, method,
+                              sigma_sqr, epsilon, impl, &ssum);
+  if (rc != PH_OK) return rc;
+  return ph_host_hist_finish(ctx, ssum, batch, loss_host, grad_fake_host);
+}
+
+int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,
+                                int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
+                                int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
+                                float* target_one_hot_host) {
+  PH_CHECK_ARG(ctx && source_host && target_host && source_indexed_host && target_indexed_host && palette_host &&
+                   ncolors_host,
+               "NULL pointer argument");
+  PH_CHECK_ARG(batch > 0 && npix > 0, "bad shape");
+  PH_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t img = (size_t)batch * npix * 4;
+  const int depth = PH_MAX_PALETTE_SIZE;
+  for (int pass = 0; pass < 2; ++pass) {
+    Carver cv(pass == 0 ? nullptr : ctx->arena);
+    int32_t* d_src = cv.take<int32_t>(img);
+    int32_t* d_tgt = cv.take<int32_t>(img);
+    int32_t* d_sidx = cv.take<int32_t>((size_t)batch * npix);
+    int32_t* d_tidx = cv.take<int32_t>((size_t)batch * npix);
+    int32_t* d_pal = cv.take<int32_t>((size_t)batch * depth * 4);
+    int32_t* d_nc = cv.take<int32_t>((size_t)batch);
+    float* d_oh = target_one_hot_host ? cv.take<float>((size_t)batch * npix * depth) : nullptr;
+    if (pass == 0) {
+      int rc = ensure_arena(ctx, align_up(cv.off, 256) + 256);
+      if (rc != PH_OK) return rc;
+      continue;
+    }
+    cudaStream_t st = ctx->s_compute;
+    PH_CUDA_OK(cudaMemcpyAsync(d_src, source_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PH_CUDA_OK(cudaMemcpyAsync(d_tgt, target_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int rc = ph_load_indexed_images(d_src, d_tgt, batch, npix, ordering, d_sidx, d_tidx, d_pal, d_nc, st);
+    if (rc != PH_OK) return rc;
+    if (d_oh) {
+      rc = ph_one_hot(d_tidx, batch * npix, depth, d_oh, st);
+      if (rc != PH_OK) return rc;
+    }
+    PH_CUDA_OK(cudaMemcpyAsync(source_indexed_host, d_sidx, (size_t)batch * npix * 4, cudaMemcpyDeviceToHost, st));
+    PH_CUDA_OK(cudaMemcpyAsync(target_indexed_host, d_tidx, (size_t)batch * npix * 4, cudaMemcpyDeviceToHost, st));
+    PH_CUDA_OK(cudaMemcpyAsync(palette_host, d_pal, (size_t)batch * depth * 16, cudaMemcpyDeviceToHost, st));
+    PH_CUDA_OK(cudaMemcpyAsync(ncolors_host, d_nc, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    if (d_oh)
+      PH_CUDA_OK(cudaMemcpyAsync(target_one_hot_host, d_oh, (size_t)batch * npix * depth * 4, cudaMemcpyDeviceToHost, st));
+    PH_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return PH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+// Palette kernels: unique-colour extraction, colour -> index, one-hot, index -> colour.
+// Integer/byte work bound by HBM bandwidth: 128-bit loads/stores, one CTA-resident hash table per
+// image, warp-level match/ballot de-duplication in front of the shared-memory atomics.
+//
+// Reference semantics: io_utils.py:25-65 (extract_palette), :78-93 (rgba_to_indexed), :96-103
+// (indexed_to_rgba), pix2pix_model.py:300-301 (one-hot), dataset_utils.py:138-151 (call site).
+#include "common.cuh"
+#include "hist_internal.cuh"
+
+namespace ph {
+
+constexpr unsigned long long SLOT_EMPTY = ~0ull;
+
+__device__ __forceinline__ bool in_byte_range(const int4& c) {
+  return ((unsigned)c.x | (unsigned)c.y | (unsigned)c.z | (unsigned)c.w) < 256u;
+}
+__device__ __forceinline__ unsigned pack_rgba(const int4& c) {
+  return (unsigned)c.x | ((unsigned)c.y << 8) | ((unsigned)c.z << 16) | ((unsigned)c.w << 24);
+}
+__device__ __forceinline__ int4 unpack_rgba(unsigned k) {
+  return make_int4((int)(k & 255u), (int)((k >> 8) & 255u), (int)((k >> 16) & 255u), (int)(k >> 24));
+}
+template <int BITS>
+__device__ __forceinline__ unsigned hash_slot(unsigned key) {
+  return (key * 2654435761u) >> (32 - BITS);
+}
+
+// =============================================================================================
+// extract_palette: one CTA per image.
+//   1. every row (pixel) is packed to a 32-bit key; lanes holding the same key elect the lane with
+//      the earliest row (warp match) and only that lane touches the hash table;
+//   2. the table keeps (key, earliest row) per colour  -> first-occurrence order of
+//      UniqueWithCountsV2 (io_utils.py:46-57);
+//   3. entries are ranked by earliest row, and for "grayness" re-ranked by the float32 key
+//      ((r*0.2989+g*0.5870)+b*0.1140)+a*0 with ties broken by first occurrence = stable argsort
+//      (io_utils.py:51-55);
+//   4. rows n..255 are INVALID_INDEX_COLOR (io_utils.py:61-63, configuration.py:32).
+// =============================================================================================
+constexpr int PAL_THREADS = 256;
+constexpr int PAL_HASH_BITS = 11;
+constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;
+constexpr int PAL_MAX = PH_MAX_PALETTE_SIZE;
+
+__global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
+    const int4* __restrict__ image, const int4* __restrict__ image2, int64_t rows, int ordering,
+    int4* __restrict__ palette, int* __restrict__ ncolors) {
+  __shared__ unsigned long long table[PAL_HASH_SIZE];
+  __shared__ unsigned long long entries[PAL_MAX];
+  __shared__ unsigned first_order[PAL_MAX];  // keys in first-occurrence order
+  __shared__ float gray[PAL_MAX];
+  __shared__ int s_count, s_bad, s_n;
+
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < PAL_HASH_SIZE; i += PAL_THREADS) table[i] = SLOT_EMPTY;
+  if (tid == 0) { s_count = 0; s_bad = 0; s_n = 0; }
+  __syncthreads();
+
+  // image2 != nullptr: rows interleave source/target pixels (dataset_utils.py:142-145)
+  const int64_t per_image = image2 ? rows / 2 : rows;
+  const int4* src0 = image + b * per_image;
+  const int4* src1 = image2 ? image2 + b * per_image : nullptr;
+  const bool reversed = ordering == PH_ORDER_BOTTOM2TOP;
+
+  const int64_t rows_padded = (rows + 31) / 32 * 32;
+  for (int64_t r = tid; r < rows_padded; r += PAL_THREADS) {
+    const bool active = r < rows;
+    unsigned key = 0;
+    unsigned pos = 0xffffffffu;
+    if (active) {
+      int4 c;
+      if (src1) c = __ldg(((r & 1) ? src1 : src0) + (r >> 1));
+      else c = __ldg(src0 + r);
+      if (!in_byte_range(c)) s_bad = 1;
+      key = pack_rgba(c);
+      pos = (unsigned)(reversed ? rows - 1 - r : r);
+    }
+    // warp de-duplication: among lanes with the same colour keep the one with the earliest row
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    if (!active) continue;
+    const unsigned peers = __match_any_sync(amask, key);
+    const int leader = reversed ? 31 - __clz(peers) : __ffs(peers) - 1;
+    if (lane != leader) continue;
+    if (*(volatile int*)&s_count > PAL_MAX) continue;  // already overflowed: result is "too many"
+
+    const unsigned long long word = ((unsigned long long)key << 32) | pos;
+    unsigned h = hash_slot<PAL_HASH_BITS>(key);
+    for (int probe = 0; probe < PAL_HASH_SIZE; ++probe) {
+      unsigned long long cur = *(volatile unsigned long long*)&table[h];
+      if (cur == SLOT_EMPTY) {
+        cur = atomicCAS(&table[h], SLOT_EMPTY, word);
+        if (cur == SLOT_EMPTY) { atomicAdd(&s_count, 1); break; }
+      }
+      if ((unsigned)(cur >> 32) == key) {
+        if ((unsigned)cur > pos) atomicMin(&table[h], word);
+        break;
+      }
+      h = (h + 1) & (PAL_HASH_SIZE - 1);
+    }
+  }
+  __syncthreads();
+
+  const int count = s_count;
+  if (s_bad || count > PAL_MAX) {
+    if (tid == 0) ncolors[b] = s_bad ? PH_PALETTE_BAD_VALUE : count;
+    const int4 filler = make_int4(255, 0, 220, 255);
+    for (int k = tid; k < PAL_MAX; k += PAL_THREADS) palette[b * PAL_MAX + k] = filler;
+    return;
+  }
+
+  // compact occupied slots
+  for (int i = tid; i < PAL_HASH_SIZE; i += PAL_THREADS) {
+    const unsigned long long w = table[i];
+    if (w != SLOT_EMPTY) entries[atomicAdd(&s_n, 1)] = w;
+  }
+  __syncthreads();
+  const int n = s_n;  // == count
+
+  // rank by earliest row -> first-occurrence order
+  if (tid < n) {
+    const unsigned long long me = entries[tid];
+    const unsigned mypos = (unsigned)me;
+    int rank = 0;
+    for (int e = 0; e < n; ++e) rank += ((unsigned)entries[e] < mypos) ? 1 : 0;
+    const unsigned key = (unsigned)(me >> 32);
+    first_order[rank] = key;
+    const int4 c = unpack_rgba(key);
+    // float32, non-fused, left to right: the (n,4)x(4,1) product of io_utils.py:51-52
+    float g = __fmul_rn((float)c.x, 0.2989f);
+    g = __fadd_rn(g, __fmul_rn((float)c.y, 0.5870f));
+    g = __fadd_rn(g, __fmul_rn((float)c.z, 0.1140f));
+    g = __fadd_rn(g, __fmul_rn((float)c.w, 0.0f));
+    gray[rank] = g;
+  }
+  __syncthreads();
+
+  const int4 filler = make_int4(255, 0, 220, 255);
+  int4* out = palette + b * PAL_MAX;
+  if (ordering == PH_ORDER_GRAYNESS && n > 1) {
+    if (tid < n) {
+      const float mine = gray[tid];
+      int rank = 0;
+      for (int e = 0; e < n; ++e) {
+        const float other = gray[e];
+        rank += (other < mine || (other == mine && e < tid)) ? 1 : 0;
+      }
+      out[rank] = unpack_rgba(first_order[tid]);
+    }
+  } else {
+    if (tid < n) out[tid] = unpack_rgba(first_order[tid]);
+  }
+  for (int k = n + tid; k < PAL_MAX; k += PAL_THREADS) out[k] = filler;
+  if (tid == 0) ncolors[b] = n;
+}
+
+// =============================================================================================
+// rgba_to_indexed (+ optional fused one-hot).
+// The palette is hashed once per CTA: slot = (key, sum of the row indices carrying that colour)
+// for the reference's scatter-add semantics (duplicates — e.g. a pixel equal to the filler colour —
+// add up, io_utils.py:84-91; no match -> 0), or (key, lowest row index) for nearest-colour mode
+// where an exact hit short-cuts the arg-min scan.  Values outside [0,255] take an exact
+// 4x int32 comparison scan, so any int32 input follows the reference.
+// =============================================================================================
+constexpr int IDX_THREADS = 256;
+constexpr int IDX_PX_PER_THREAD = 4;
+constexpr int IDX_HASH_BITS = 10;
+constexpr int IDX_HASH_SIZE = 1 << IDX_HASH_BITS;
+
+__device__ __forceinline__ void write_one_hot_rows(float* __restrict__ one_hot, int64_t first_px,
+                                                   int64_t npix_total, int idx, int depth, int lane) {
+  // the warp writes the `depth` floats of each of its 32 pixels; 16 B per lane per store
+  for (int p = 0; p < 32; ++p) {
+    const int hot = __shfl_sync(0xffffffffu, idx, p);
+    const int64_t px = first_px + p;
+    if (px >= npix_total) break;  // warp-uniform
+    float* row = one_hot + px * depth;
+    if ((depth & 3) == 0) {
+      for (int c4 = lane * 4; c4 < depth; c4 += 128) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int d = hot - c4;
+        if (d == 0) v.x = 1.f; else if (d == 1) v.y = 1.f; else if (d == 2) v.z = 1.f; else if (d == 3) v.w = 1.f;
+        __stcs(reinterpret_cast<float4*>(row + c4), v);
+      }
+    } else {
+      for (int c = lane; c < depth; c += 32) __stcs(row + c, c == hot ? 1.f : 0.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(IDX_THREADS) rgba_to_indexed_kernel(
+    const int4* __restrict__ image, int64_t npix, const int4* __restrict__ palette,
+    int64_t palette_batch, int mode, int* __restrict__ indexed, float* __restrict__ one_hot, int depth) {
+  __shared__ unsigned long long table[IDX_HASH_SIZE];
+  __shared__ int4 pal[PAL_MAX];
+  __shared__ int s_wide;  // some palette row has a channel outside [0,255]
+
+  const int64_t b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int4* psrc = palette + (palette_batch == 1 ? 0 : b) * PAL_MAX;
+  for (int i = tid; i < IDX_HASH_SIZE; i += IDX_THREADS) table[i] = SLOT_EMPTY;
+  if (tid == 0) s_wide = 0;
+  __syncthreads();
+  if (tid < PAL_MAX) {
+    const int4 c = __ldg(psrc + tid);
+    pal[tid] = c;
+    if (in_byte_range(c)) {
+      const unsigned key = pack_rgba(c);
+      const unsigned long long word = ((unsigned long long)key << 32) | (unsigned)tid;
+      unsigned h = hash_slot<IDX_HASH_BITS>(key);
+      for (int probe = 0; probe < IDX_HASH_SIZE; ++probe) {
+        unsigned long long cur = atomicCAS(&table[h], SLOT_EMPTY, word);
+        if (cur == SLOT_EMPTY) break;
+        if ((unsigned)(cur >> 32) == key) {
+          if (mode == PH_INDEX_EXACT_SUM) atomicAdd(&table[h], (unsigned long long)tid);
+          else atomicMin(&table[h], word);
+          break;
+        }
+        h = (h + 1) & (IDX_HASH_SIZE - 1);
+      }
+    } else {
+      s_wide = 1;
+    }
+  }
+  __syncthreads();
+  const bool wide_palette = s_wide != 0;
+
+  const int4* img = image + b * npix;
+  int* idx_out = indexed + b * npix;
+  float* oh = one_hot ? one_hot + b * npix * (int64_t)depth : nullptr;
+  const int64_t cta_first = (int64_t)blockIdx.x * (IDX_THREADS * IDX_PX_PER_THREAD);
+
+#pragma unroll
+  for (int it = 0; it < IDX_PX_PER_THREAD; ++it) {
+    const int64_t px = cta_first + it * IDX_THREADS + tid;
+    int idx = 0;
+    if (px < npix) {
+      const int4 c = __ldg(img + px);
+      bool hit = false;
+      if (in_byte_range(c)) {
+        const unsigned key = pack_rgba(c);
+        unsigned h = hash_slot<IDX_HASH_BITS>(key);
+        for (int probe = 0; probe < IDX_HASH_SIZE; ++probe) {
+          const unsigned long long w = table[h];
+          if (w == SLOT_EMPTY) break;
+          if ((unsigned)(w >> 32) == key) { idx = (int)(unsigned)w; hit = true; break; }
+          h = (h + 1) & (IDX_HASH_SIZE - 1);
+        }
+      } else if (wide_palette || mode == PH_INDEX_NEAREST) {
+        // exact 128-bit comparison against every row (values that do not pack into a byte key)
+        int sum = 0, first = -1;
+        for (int k = 0; k < PAL_MAX; ++k) {
+          const int4 q = pal[k];
+          if (q.x == c.x && q.y == c.y && q.z == c.z && q.w == c.w) { sum += k; if (first < 0) first = k; }
+        }
+        if (first >= 0) { idx = mode == PH_INDEX_EXACT_SUM ? sum : first; hit = true; }
+      }
+      if (!hit && mode == PH_INDEX_NEAREST) {
+        long long best = 0x7fffffffffffffffll;
+        for (int k = 0; k < PAL_MAX; ++k) {
+          const int4 q = pal[k];
+          const long long dx = (long long)q.x - c.x, dy = (long long)q.y - c.y;
+          const long long dz = (long long)q.z - c.z, dw = (long long)q.w - c.w;
+          const long long d = dx * dx + dy * dy + dz * dz + dw * dw;
+          if (d < best) { best = d; idx = k; }
+        }
+      }
+      idx_out[px] = idx;
+    }
+    if (oh) {
+      const int64_t warp_first = cta_first + it * IDX_THREADS + (tid & ~31);
+      if (warp_first < npix) write_one_hot_rows(oh, warp_first, npix, idx, depth, lane);
+    }
+  }
+}
+
+// =============================================================================================
+// one-hot (pix2pix_model.py:300-301) and indexed_to_rgba (io_utils.py:96-103)
+// =============================================================================================
+__global__ void __launch_bounds__(256) one_hot_kernel(const int* __restrict__ indexed, int64_t n,
+                                                      int depth, float* __restrict__ one_hot) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nblk = (n + 31) / 32;
+  for (int64_t blk = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); blk < nblk; blk += warps) {
+    const int64_t px = blk * 32 + lane;
+    const int idx = px < n ? __ldg(indexed + px) : -1;
+    write_one_hot_rows(one_hot, blk * 32, n, idx, depth, lane);
+  }
+}
+
+__global__ void __launch_bounds__(256) indexed_to_rgba_kernel(
+    const int* __restrict__ indexed, int64_t npix, const int* __restrict__ palette, int64_t palette_batch,
+    int palette_rows, int channels, int* __restrict__ out) {
+  const int64_t b = blockIdx.y;
+  const int* pal = palette + (palette_batch == 1 ? 0 : b) * (int64_t)palette_rows * channels;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t px = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; px < npix; px += stride) {
+    const int idx = __ldg(indexed + b * npix + px);
+    const bool ok = idx >= 0 && idx < palette_rows;
+    int* dst = out + (b * npix + px) * channels;
+    if (channels == 4) {
+      const int4 c = ok ? __ldg(reinterpret_cast<const int4*>(pal) + idx) : make_int4(0, 0, 0, 0);
+      *reinterpret_cast<int4*>(dst) = c;
+    } else {
+      for (int ch = 0; ch < channels; ++ch) dst[ch] = ok ? __ldg(pal + (int64_t)idx * channels + ch) : 0;
+    }
+  }
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows,
+                           int ordering, int32_t* palette, int32_t* ncolors, cudaStream_t st) {
+  PH_CHECK_ARG(batch < (1ll << 31), "batch too large");
+  PH_CHECK_ARG(rows < (1ll << 31), "too many rows per image (%lld)", (long long)rows);
+  if (batch == 0) return PH_OK;
+  extract_palette_kernel<<<(unsigned)batch, PAL_THREADS, 0, st>>>(
+      reinterpret_cast<const int4*>(image), reinterpret_cast<const int4*>(image2), rows, ordering,
+      reinterpret_cast<int4*>(palette), ncolors);
+  PH_LAUNCH_OK("extract_palette_kernel");
+  return PH_OK;
+}
+
+int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,
+                           int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
+                           cudaStream_t st) {
+  PH_CHECK_ARG(batch <= 65535, "rgba_to_indexed: batch %lld > 65535 per call", (long long)batch);
+  if (batch == 0 || npix == 0) return PH_OK;
+  const dim3 grid((unsigned)ceil_div(npix, IDX_THREADS * IDX_PX_PER_THREAD), (unsigned)batch);
+  rgba_to_indexed_kernel<<<grid, IDX_THREADS, 0, st>>>(
+      reinterpret_cast<const int4*>(image), npix, reinterpret_cast<const int4*>(palette), palette_batch,
+      mode, indexed, one_hot, depth);
+  PH_LAUNCH_OK("rgba_to_indexed_kernel");
+  return PH_OK;
+}
+
+int launch_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, cudaStream_t st) {
+  if (n == 0) return PH_OK;
+  int64_t grid = ceil_div(n, 256);
+  const int64_t cap = (int64_t)cached_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  one_hot_kernel<<<(unsigned)grid, 256, 0, st>>>(indexed, n, depth, one_hot);
+  PH_LAUNCH_OK("one_hot_kernel");
+  return PH_OK;
+}
+
+int launch_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npix, const int32_t* palette,
+                           int64_t palette_batch, int palette_rows, int channels, int32_t* out,
+                           cudaStream_t st) {
+  PH_CHECK_ARG(batch <= 65535, "indexed_to_rgba: batch %lld > 65535 per call", (long long)batch);
+  if (batch == 0 || npix == 0) return PH_OK;
+  int64_t gx = ceil_div(npix, 256);
+  if (gx > 1024) gx = 1024;
+  indexed_to_rgba_kernel<<<dim3((unsigned)gx, (unsigned)batch), 256, 0, st>>>(
+      indexed, npix, palette, palette_batch, palette_rows, channels, out);
+  PH_LAUNCH_OK("indexed_to_rgba_kernel");
+  return PH_OK;
+}
+
+}  // namespace ph

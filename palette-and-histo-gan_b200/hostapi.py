@@ -1,0 +1,140 @@
+"""Host-buffer calls: numpy arrays (or pinned CPU torch tensors) in, numpy arrays out, GPU in between.
+
+These bind the `ph_host_*` entry points of libpalhist — the functions a CPU-side caller of the
+reference (a `tf.data` map worker, `dataset_utils.py:236-244`; an eager `generator_loss`,
+`pix2pix_model.py:242-250`) would call with host memory.  Host<->device copies, chunked and overlapped
+with the kernels, happen inside the call.  This is the path bench.py times as `e2e`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from .histogram import EPSILON, _method_id, _sigma_sqr, tf_linspace
+
+_tls = threading.local()
+
+
+class HostContext:
+    """Per-thread device staging (streams, events, grow-only arena). Not shareable across threads."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _lib.call("ph_host_ctx_create", int(device), C.byref(self._h))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            _lib.load().ph_host_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def default_context(device: int = 0) -> HostContext:
+    ctxs = getattr(_tls, "ctxs", None)
+    if ctxs is None:
+        ctxs = _tls.ctxs = {}
+    if device not in ctxs:
+        ctxs[device] = HostContext(device)
+    return ctxs[device]
+
+
+def _np(x, dtype, name):
+    if hasattr(x, "numpy") and not isinstance(x, np.ndarray):  # CPU torch tensor (possibly pinned)
+        x = x.numpy()
+    a = np.asarray(x)
+    if a.dtype != dtype:
+        raise TypeError(f"{name} must be {np.dtype(dtype).name}, got {a.dtype}")
+    if not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",
+                   want_grad=True, out_grad=None, ctx=None, device=0):
+    """Loss and d loss/d fake of pix2pix_model.py:243-245 for host images (B,H,W,3|4) float32.
+    Returns (loss: float, grad: np.ndarray | None)."""
+    real = _np(real_image, np.float32, "real_image")
+    fake = _np(fake_image, np.float32, "fake_image")
+    if real.shape != fake.shape or real.ndim != 4 or real.shape[-1] not in (3, 4):
+        raise ValueError("real_image and fake_image must both be (B,H,W,3|4)")
+    b, h, w, ch = real.shape
+    dom = tf_linspace(-3.0, 3.0, int(size))
+    loss = np.zeros((1,), np.float32)
+    grad = None
+    if want_grad:
+        grad = out_grad if out_grad is not None else np.empty_like(fake)
+        grad = _np(grad, np.float32, "out_grad")
+    ctx = ctx or default_context(device)
+    _lib.call("ph_host_hist_loss", ctx._h, real.ctypes.data, fake.ctypes.data, b, h * w, ch, dom.ctypes.data,
+              int(size), _method_id(method), _sigma_sqr(sigma), EPSILON, _lib.IMPLS[impl], loss.ctypes.data,
+              grad.ctypes.data if grad is not None else None)
+    return float(loss[0]), grad
+
+
+def histogram_loss_begin(real_image, fake_image, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",
+                         ctx=None, device=0) -> float:
+    """Phase 1 of a sharded evaluation: upload + both forward passes; returns this shard's sum of squares
+    (all-reduce it over ranks, then call `histogram_loss_finish`)."""
+    real = _np(real_image, np.float32, "real_image")
+    fake = _np(fake_image, np.float32, "fake_image")
+    if real.shape != fake.shape or real.ndim != 4 or real.shape[-1] not in (3, 4):
+        raise ValueError("real_image and fake_image must both be (B,H,W,3|4)")
+    b, h, w, ch = real.shape
+    dom = tf_linspace(-3.0, 3.0, int(size))
+    ssum = C.c_double(0.0)
+    ctx = ctx or default_context(device)
+    _lib.call("ph_host_hist_begin", ctx._h, real.ctypes.data, fake.ctypes.data, b, h * w, ch, dom.ctypes.data,
+              int(size), _method_id(method), _sigma_sqr(sigma), EPSILON, _lib.IMPLS[impl], C.byref(ssum))
+    return float(ssum.value)
+
+
+def histogram_loss_finish(ssum_global: float, global_batch: int, out_grad, *, ctx=None, device=0):
+    """Phase 2: loss of the whole batch and the gradient of this shard into `out_grad` (host float32
+    array shaped like the shard's fake images, or None)."""
+    loss = np.zeros((1,), np.float32)
+    grad = _np(out_grad, np.float32, "out_grad") if out_grad is not None else None
+    ctx = ctx or default_context(device)
+    _lib.call("ph_host_hist_finish", ctx._h, float(ssum_global), int(global_batch), loss.ctypes.data,
+              grad.ctypes.data if grad is not None else None)
+    return float(loss[0]), grad
+
+
+def load_indexed_images(source_image, target_image, palette_ordering="grayness", *, with_one_hot=False,
+                        ctx=None, device=0):
+    """dataset_utils.py:138-151 for host images (B,H,W,4) int32 (values 0..255).
+    Returns (source_indexed, target_indexed, palette[, target_one_hot]) as numpy arrays."""
+    from .io_utils import PaletteOverflowError, _ordering_id
+    from .configuration import MAX_PALETTE_SIZE
+
+    if palette_ordering == "shuffled":
+        raise ValueError("'shuffled' is nondeterministic; use the tensor API (dataset_utils.load_indexed_images)")
+    src = _np(source_image, np.int32, "source_image")
+    tgt = _np(target_image, np.int32, "target_image")
+    if src.shape != tgt.shape or src.ndim != 4 or src.shape[-1] != 4:
+        raise ValueError("source_image and target_image must both be (B,H,W,4)")
+    b, h, w, _ = src.shape
+    s_idx = np.empty((b, h, w, 1), np.int32)
+    t_idx = np.empty((b, h, w, 1), np.int32)
+    pal = np.empty((b, MAX_PALETTE_SIZE, 4), np.int32)
+    nc = np.empty((b,), np.int32)
+    oh = np.empty((b, h, w, MAX_PALETTE_SIZE), np.float32) if with_one_hot else None
+    ctx = ctx or default_context(device)
+    _lib.call("ph_host_load_indexed_images", ctx._h, src.ctypes.data, tgt.ctypes.data, b, h * w,
+              _ordering_id(palette_ordering), s_idx.ctypes.data, t_idx.ctypes.data, pal.ctypes.data,
+              nc.ctypes.data, oh.ctypes.data if oh is not None else None)
+    if (nc == _lib.PALETTE_BAD_VALUE).any():
+        raise ValueError("colour values must lie in [0, 255]")
+    if (nc > MAX_PALETTE_SIZE).any():
+        raise PaletteOverflowError(f"more than {MAX_PALETTE_SIZE} unique colours")
+    if with_one_hot:
+        return s_idx, t_idx, pal, oh
+    return s_idx, t_idx, pal

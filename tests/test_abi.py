@@ -1,0 +1,122 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/palhist.h declares,
+the ctypes prototypes cover exactly that set, and the host layer validates arguments and refuses to
+compute without a GPU (no compute calls are made here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "palhist.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return sorted(set(re.findall(r"PH_API[^;(]*?\b(ph_\w+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+
+    if not os.path.exists(os.path.join(ROOT, "palette-and-histo-gan_b200", "libpalhist.so")):
+        g.build()
+    import palette_and_histo_gan_b200 as p
+
+    return p
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    for name in ("ph_hist_forward", "ph_hist_backward", "ph_hellinger_ssum", "ph_extract_palette",
+                 "ph_rgba_to_indexed", "ph_one_hot", "ph_indexed_to_rgba", "ph_load_indexed_images",
+                 "ph_host_hist_loss", "ph_host_load_indexed_images"):
+        assert name in syms
+    # every entry point cites the reference code it replaces
+    text = open(HEADER).read()
+    for ref in ("histogram.py:36-81", "histogram.py:5-32", "histogram.py:84-89", "io_utils.py:25-65",
+                "io_utils.py:78-93", "io_utils.py:96-103", "pix2pix_model.py:300-301",
+                "dataset_utils.py:138-151"):
+        assert ref in text, ref
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(pkg._lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in palhist.h but not exported"
+    assert lib.ph_abi_version() == 1
+
+
+def test_ctypes_prototypes_match_header(pkg):
+    assert sorted(pkg._lib.PROTOTYPES) == declared_symbols()
+    # argument counts agree with the header's parameter lists
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in pkg._lib.PROTOTYPES.items():
+        m = re.search(r"\b%s\s*\(([^)]*)\)" % name, text)
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), (name, n, len(args))
+
+
+def test_no_cpu_fallback(pkg):
+    """CPU tensors are rejected; nothing in the product package imports the oracle."""
+    x = torch.zeros((1, 4, 4, 4), dtype=torch.float32)
+    with pytest.raises(ValueError, match="CUDA"):
+        pkg.histogram.calculate_rgbuv_histogram(x)
+    with pytest.raises(ValueError, match="CUDA"):
+        pkg.io_utils.extract_palette(torch.zeros((4, 4, 4), dtype=torch.int32), "grayness")
+    out = subprocess.run(["grep", "-rIl", "--include=*.py", "--include=*.cu", "--include=*.cuh", "-E",
+                          r"^\s*(from|import)\s+oracle|oracle/", os.path.join(ROOT, "palette-and-histo-gan_b200")],
+                         capture_output=True, text=True)
+    assert out.stdout.strip() == "", f"product package references the oracle: {out.stdout}"
+
+
+def test_host_argument_validation(pkg):
+    h = pkg.histogram
+    with pytest.raises(ValueError):
+        h._method_id("thresholding")
+    with pytest.raises(ValueError):
+        pkg.io_utils._ordering_id("by-count")
+    assert h._sigma_sqr(0.02) == float(np.float32(4e-4))
+    with pytest.raises(TypeError):
+        pkg._tensor.from_any([1, 2, 3])
+    with pytest.raises(ValueError):
+        pkg.io_utils.extract_palette(torch.zeros((4, 4, 3), dtype=torch.int32), "grayness", channels=3)
+
+
+def test_linspace_matches_oracle(pkg):
+    from oracle.histogram_oracle import tf_linspace_f32
+
+    for n in (1, 2, 16, 64, 256):
+        assert np.array_equal(pkg.histogram.tf_linspace(-3.0, 3.0, n), tf_linspace_f32(-3.0, 3.0, n))
+
+
+def test_dlpack_ingestion_is_zero_copy(pkg):
+    class Foreign:  # any object speaking the DLPack protocol
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, **kw):
+            return self.t.__dlpack__(**kw)
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    t = torch.arange(12, dtype=torch.float32)
+    v = pkg._tensor.from_any(Foreign(t))
+    assert v.data_ptr() == t.data_ptr()
+    cap = torch.utils.dlpack.to_dlpack(t)
+    assert pkg._tensor.from_any(cap).data_ptr() == t.data_ptr()
+
+
+def test_compute_entry_point_fails_loudly_without_gpu(pkg):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    sm = ctypes.c_int()
+    rc = pkg._lib.load().ph_device_info(0, ctypes.byref(sm), None, None)
+    assert rc == pkg._lib.PH_ERR_CUDA
+    assert "failed" in pkg._lib.last_error()

@@ -1,0 +1,171 @@
+"""GPU parity tests of the palette half, through the C ABI.  Integer work: every comparison is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import palette_oracle as po
+from tests.conftest import sprite_like_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import palette_and_histo_gan_b200 as pkg
+
+    return pkg
+
+
+def dev_i32(a, cuda):
+    return torch.from_numpy(np.ascontiguousarray(a).astype(np.int32)).to(cuda)
+
+
+@pytest.mark.parametrize("ordering", ["grayness", "top2bottom", "bottom2top"])
+def test_all_sprite_pairs_match_golden(P, cuda, sprites, palette_golden, ordering):
+    src, tgt = dev_i32(sprites["front"], cuda), dev_i32(sprites["right"], cuda)
+    s_idx, t_idx, pal = P.dataset_utils.load_indexed_images(src, tgt, ordering)
+    assert pal.dtype == torch.int32 and tuple(pal.shape) == (108, 256, 4)
+    assert np.array_equal(pal.cpu().numpy(), palette_golden[f"palette_{ordering}"].astype(np.int32))
+    assert np.array_equal(s_idx.cpu().numpy()[..., 0], palette_golden[f"src_idx_{ordering}"][..., 0].astype(np.int32))
+    assert np.array_equal(t_idx.cpu().numpy()[..., 0], palette_golden[f"tgt_idx_{ordering}"][..., 0].astype(np.int32))
+    # round trip (how pix2pix_model.py:446-447 reconstructs targets)
+    back = P.io_utils.indexed_to_rgba(t_idx, pal)
+    assert torch.equal(back, tgt)
+    # the separate calls of dataset_utils.py:142-149 give the same result as the fused glue
+    cat = torch.cat([src, tgt], dim=-1)
+    pal2, ncol = P.io_utils.extract_palette(cat, ordering, return_counts=True)
+    assert torch.equal(pal2, pal)
+    assert np.array_equal(ncol.cpu().numpy(), palette_golden[f"ncolors_{ordering}"])
+    assert torch.equal(P.io_utils.rgba_to_indexed(src, pal2), s_idx)
+
+
+def test_single_image_signatures(P, cuda, sprites):
+    """Un-batched calls with the reference's exact signatures and shapes."""
+    s, t = sprites["front"][3].astype(np.int32), sprites["right"][3].astype(np.int32)
+    cat = dev_i32(np.concatenate([s, t], -1), cuda)  # (64,64,8) as dataset_utils.py:142 builds it
+    pal = P.io_utils.extract_palette(cat, "grayness")
+    epal, _ = po.extract_palette(np.concatenate([s, t], -1), "grayness")
+    assert tuple(pal.shape) == (256, 4) and np.array_equal(pal.cpu().numpy(), epal)
+    idx = P.io_utils.rgba_to_indexed(dev_i32(s, cuda), pal)
+    assert tuple(idx.shape) == (64, 64, 1) and np.array_equal(idx.cpu().numpy(), po.rgba_to_indexed(s, epal))
+    rgba = P.io_utils.indexed_to_rgba(idx, pal)
+    assert tuple(rgba.shape) == (64, 64, 4) and np.array_equal(rgba.cpu().numpy(), s)
+
+
+def test_grayness_ties_and_stable_sort(P, cuda):
+    # alpha-only ties and the RGB tie d(r,g,b) = (10,-35,154) from SURVEY.md §4
+    base = np.array([100, 100, 50, 255])
+    tie = base + np.array([10, -35, 154, 0])
+    imgs = []
+    for order in ([base, tie], [tie, base]):
+        px = [[0, 0, 0, 255], order[0], [0, 0, 0, 0], order[1], [0, 0, 0, 7], [255, 255, 255, 255]]
+        imgs.append(np.array(px, np.int32).reshape(1, 6, 4))
+    batch = np.stack(imgs)
+    for ordering in ("grayness", "top2bottom", "bottom2top"):
+        pal = P.io_utils.extract_palette(dev_i32(batch, cuda), ordering).cpu().numpy()
+        for i in range(2):
+            assert np.array_equal(pal[i], po.extract_palette(batch[i], ordering)[0]), ordering
+
+
+def test_random_images_many_colours(P, cuda):
+    rng = np.random.default_rng(5)
+    # exactly 256 colours (full palette), 255, 1, and a ragged row count not divisible by the block size
+    cases = []
+    for ncol, npx in ((256, 64 * 64), (255, 50 * 30), (1, 17), (37, 1000), (200, 8191)):
+        cols = rng.integers(0, 256, size=(ncol, 4))
+        cols = np.unique(cols, axis=0)
+        while cols.shape[0] < ncol:
+            cols = np.unique(np.concatenate([cols, rng.integers(0, 256, size=(ncol - cols.shape[0], 4))]), axis=0)
+        rng.shuffle(cols)
+        px = np.concatenate([cols, cols[rng.integers(0, ncol, size=npx - ncol)]]) if npx > ncol else cols[:npx]
+        rng.shuffle(px)
+        cases.append(px.astype(np.int32).reshape(1, -1, 4))
+    for img in cases:
+        for ordering in ("grayness", "top2bottom", "bottom2top"):
+            pal, n = P.io_utils.extract_palette(dev_i32(img, cuda), ordering, return_counts=True)
+            epal, en = po.extract_palette(img, ordering)
+            assert int(n) == en and np.array_equal(pal.cpu().numpy(), epal)
+            idx = P.io_utils.rgba_to_indexed(dev_i32(img, cuda), pal)
+            assert np.array_equal(idx.cpu().numpy(), po.rgba_to_indexed(img, epal))
+
+
+def test_overflow_and_bad_values_raise(P, cuda):
+    k = np.arange(300)
+    many = np.stack([k % 256, k // 256, np.zeros(300), np.full(300, 255)], -1).astype(np.int32).reshape(1, 300, 4)
+    with pytest.raises(P.io_utils.PaletteOverflowError):
+        P.io_utils.extract_palette(dev_i32(many, cuda), "grayness")
+    noise = np.random.default_rng(0).integers(0, 256, size=(2, 64, 64, 4)).astype(np.int32)
+    with pytest.raises(P.io_utils.PaletteOverflowError):
+        P.io_utils.extract_palette(dev_i32(noise, cuda), "top2bottom")
+    bad = np.array([[[0, 0, 0, 255], [0, 300, 0, 255]]], np.int32)
+    with pytest.raises(ValueError):
+        P.io_utils.extract_palette(dev_i32(bad, cuda), "grayness")
+
+
+def test_scatter_add_edge_cases(P, cuda):
+    """io_utils.py:84-91: duplicates add up, no match gives 0; out-of-range index one-hot is all zero."""
+    pal, _ = po.extract_palette(np.array([[[1, 2, 3, 255], [4, 5, 6, 255]]], np.int32), "top2bottom")
+    img = np.array([[[255, 0, 220, 255], [4, 5, 6, 255], [7, 7, 7, 7], [1, 2, 3, 255], [-5, 2, 3, 255], [1, 2, 3, 256]]], np.int32)
+    idx, oh = P.io_utils.rgba_to_indexed(dev_i32(img, cuda), dev_i32(pal, cuda), with_one_hot=True)
+    exp = po.rgba_to_indexed(img, pal)
+    assert np.array_equal(idx.cpu().numpy(), exp)
+    assert exp.reshape(-1).tolist() == [sum(range(2, 256)), 1, 0, 0, 0, 0]
+    assert np.array_equal(oh.cpu().numpy(), po.one_hot(exp))
+    # palette rows outside the byte range still match exactly (any int32 follows the reference)
+    wide = pal.copy()
+    wide[5] = [1000, -3, 70000, 255]
+    img2 = np.array([[[1000, -3, 70000, 255], [4, 5, 6, 255]]], np.int32)
+    idx2 = P.io_utils.rgba_to_indexed(dev_i32(img2, cuda), dev_i32(wide, cuda))
+    assert np.array_equal(idx2.cpu().numpy(), po.rgba_to_indexed(img2, wide))
+    # nearest mode: equals exact mode on the reference's domain, differs by design off it
+    near = P.io_utils.rgba_to_indexed(dev_i32(img, cuda), dev_i32(pal, cuda), mode="nearest")
+    assert np.array_equal(near.cpu().numpy(), po.rgba_to_nearest(img, pal))
+
+
+def test_one_hot_shapes(P, cuda):
+    rng = np.random.default_rng(6)
+    idx = rng.integers(-3, 260, size=(2, 9, 7, 1)).astype(np.int32)
+    out = P.io_utils.one_hot(dev_i32(idx, cuda))
+    assert tuple(out.shape) == (2, 9, 7, 256) and out.dtype == torch.float32
+    assert np.array_equal(out.cpu().numpy(), po.one_hot(idx))
+    out10 = P.io_utils.one_hot(dev_i32(idx % 10, cuda), depth=10)  # depth not a multiple of 4
+    assert np.array_equal(out10.cpu().numpy(), po.one_hot(idx % 10, 10))
+
+
+def test_cfgB_full_size_properties(P, cuda):
+    """cfgB: batch 256 of 64x64 pairs.  Bit-exact against the oracle on 16 spot images, plus the
+    round-trip / one-hot-sum properties on all of them."""
+    rng = np.random.default_rng(47)
+    src = sprite_like_batch(rng, 256).astype(np.int32)
+    tgt = src.copy()
+    tgt[:, :, ::2] = src[:, :, 1::2]  # target shares most colours with the source, like a real pair
+    s_idx, t_idx, pal = P.dataset_utils.load_indexed_images(dev_i32(src, cuda), dev_i32(tgt, cuda), "grayness")
+    assert torch.equal(P.io_utils.indexed_to_rgba(s_idx, pal), dev_i32(src, cuda))
+    assert torch.equal(P.io_utils.indexed_to_rgba(t_idx, pal), dev_i32(tgt, cuda))
+    idx2, oh = P.io_utils.rgba_to_indexed(dev_i32(tgt, cuda), pal, with_one_hot=True)
+    assert torch.equal(idx2, t_idx)
+    assert float(oh.sum()) == 256 * 64 * 64
+    assert torch.equal(oh.argmax(-1, keepdim=True).to(torch.int32), t_idx)
+    for i in range(0, 256, 16):
+        es, et, ep = po.load_indexed_images(src[i], tgt[i], "grayness")
+        assert np.array_equal(pal[i].cpu().numpy(), ep) and np.array_equal(s_idx[i].cpu().numpy(), es)
+        assert np.array_equal(t_idx[i].cpu().numpy(), et)
+
+
+def test_shuffled_ordering_is_a_permutation(P, cuda, sprites):
+    s, t = sprites["front"][:4].astype(np.int32), sprites["right"][:4].astype(np.int32)
+    s_idx, t_idx, pal = P.dataset_utils.load_indexed_images(dev_i32(s, cuda), dev_i32(t, cuda), "shuffled")
+    for i in range(4):
+        ep, n = po.extract_palette(np.concatenate([s[i], t[i]], -1), "top2bottom")
+        got = pal[i].cpu().numpy()
+        assert sorted(map(tuple, got[:n])) == sorted(map(tuple, ep[:n])) and (got[n:] == ep[n:]).all()
+    assert torch.equal(P.io_utils.indexed_to_rgba(s_idx, pal), dev_i32(s, cuda))
+
+
+def test_host_api_matches_device_api(P, cuda, sprites):
+    s, t = sprites["front"][:8].astype(np.int32), sprites["right"][:8].astype(np.int32)
+    hs, ht, hp, oh = P.hostapi.load_indexed_images(s, t, "grayness", with_one_hot=True)
+    for i in range(8):
+        es, et, ep = po.load_indexed_images(s[i], t[i], "grayness")
+        assert np.array_equal(hs[i], es) and np.array_equal(ht[i], et) and np.array_equal(hp[i], ep)
+        assert np.array_equal(oh[i], po.one_hot(et))

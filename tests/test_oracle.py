@@ -1,0 +1,159 @@
+"""CPU tests pinning the oracle itself (no GPU): known-answer values from SURVEY.md §4, the committed
+golden fixtures, torch autograd, finite differences, and the identities the reference's call sites rely on.
+PARITY UNPINNED: TensorFlow is not installable in this image, so these are the strongest pins available."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import histogram_oracle as ho
+from oracle import palette_oracle as po
+from oracle import torch_port as tp
+
+
+def test_linspace_matches_tf_formula():
+    dom = ho.tf_linspace_f32(-3.0, 3.0, 64)
+    assert dom.dtype == np.float32 and dom.shape == (64,)
+    assert dom[0] == np.float32(-3.0) and dom[-1] == np.float32(3.0)
+    delta = np.float32(np.float32(6.0) / np.float32(63.0))
+    assert dom[17] == np.float32(np.float32(-3.0) + delta * np.float32(17.0))
+    # TF's linspace is not exactly symmetric
+    asym = np.abs(dom + dom[::-1]).max()
+    assert 0 < asym < 1e-6
+    assert ho.sigma_sqr_f32(0.02) == np.float32(4e-4)
+
+
+def test_palette_known_answers(sprites, palette_golden):
+    """SURVEY.md §4 known-answer values for train/2-front/0 || train/3-right/0, grayness ordering."""
+    src, tgt = sprites["front"][0], sprites["right"][0]
+    s_idx, t_idx, pal = po.load_indexed_images(src, tgt, "grayness")
+    n = int((pal != np.array(po.INVALID_INDEX_COLOR)).any(-1).sum())
+    assert n == 50
+    assert pal[:4].tolist() == [[0, 0, 0, 0], [30, 30, 30, 255], [106, 14, 14, 255], [81, 32, 30, 255]]
+    assert pal[48:50].tolist() == [[255, 255, 235, 255], [255, 255, 243, 255]]
+    assert (pal[50:] == np.array([255, 0, 220, 255])).all()
+    assert int((s_idx == 0).sum()) == 3406 and int(s_idx.max()) == 49
+    assert np.array_equal(po.indexed_to_rgba(s_idx, pal), src.astype(np.int32))
+    assert np.array_equal(pal, palette_golden["palette_grayness"][0].astype(np.int32))
+
+
+def test_palette_golden_fixtures_reproduce(sprites, palette_golden):
+    for ordering in ("grayness", "top2bottom", "bottom2top"):
+        for i in (1, 7, 63, 64, 107):
+            s, t = sprites["front"][i], sprites["right"][i]
+            s_idx, t_idx, pal = po.load_indexed_images(s, t, ordering)
+            assert np.array_equal(pal, palette_golden[f"palette_{ordering}"][i])
+            assert np.array_equal(s_idx, palette_golden[f"src_idx_{ordering}"][i].astype(np.int32))
+            assert np.array_equal(t_idx, palette_golden[f"tgt_idx_{ordering}"][i].astype(np.int32))
+            assert np.array_equal(po.indexed_to_rgba(t_idx, pal), t.astype(np.int32))
+
+
+def test_palette_orderings_and_ties():
+    # alpha has weight 0: (0,0,0,0) and (0,0,0,255) tie and keep first-occurrence order (stable sort)
+    img = np.array([[[0, 0, 0, 255], [9, 9, 9, 255], [0, 0, 0, 0], [1, 1, 1, 255]]], np.int32)
+    pal, n = po.extract_palette(img, "grayness")
+    assert n == 4 and pal[:4].tolist() == [[0, 0, 0, 255], [0, 0, 0, 0], [1, 1, 1, 255], [9, 9, 9, 255]]
+    pal, _ = po.extract_palette(img, "top2bottom")
+    assert pal[:4].tolist() == [[0, 0, 0, 255], [9, 9, 9, 255], [0, 0, 0, 0], [1, 1, 1, 255]]
+    pal, _ = po.extract_palette(img, "bottom2top")
+    assert pal[:4].tolist() == [[1, 1, 1, 255], [0, 0, 0, 0], [9, 9, 9, 255], [0, 0, 0, 255]]
+    # single colour: defined as identity
+    pal, n = po.extract_palette(np.full((2, 2, 4), 7, np.int32), "grayness")
+    assert n == 1 and pal[0].tolist() == [7, 7, 7, 7]
+    with pytest.raises(po.PaletteOverflow):
+        many = np.stack([np.arange(257) % 256, np.arange(257) // 256, np.zeros(257), np.full(257, 255)], -1)
+        po.extract_palette(many.astype(np.int32).reshape(257, 1, 4), "grayness")
+
+
+def test_rgba_to_indexed_scatter_add_semantics():
+    pal, _ = po.extract_palette(np.array([[[1, 2, 3, 255], [4, 5, 6, 255]]], np.int32), "top2bottom")
+    # pixel equal to the filler colour while the palette is not full: indices 2..255 add up
+    img = np.array([[[255, 0, 220, 255], [4, 5, 6, 255], [7, 7, 7, 7]]], np.int32)
+    idx = po.rgba_to_indexed(img, pal)
+    assert idx.reshape(-1).tolist() == [sum(range(2, 256)), 1, 0]
+    oh = po.one_hot(idx)
+    assert oh.shape == (1, 3, 256) and oh[0, 0].sum() == 0 and oh[0, 1, 1] == 1 and oh[0, 2, 0] == 1
+    assert po.rgba_to_nearest(img, pal).reshape(-1).tolist()[1] == 1
+
+
+def test_histogram_identities(hist_golden):
+    real = hist_golden["real"][:2]
+    h, d = ho.rgbuv_histogram_f64(real)
+    assert np.allclose(h.sum(axis=(1, 2, 3)), 1.0, atol=1e-12)
+    assert ho.hellinger_loss_f64(h, h) == 0.0
+    # alpha is ignored (histogram.py:61)
+    changed = real.copy()
+    changed[..., 3] = 0.123
+    assert np.array_equal(ho.rgbuv_histogram_f64(changed)[0], h)
+    # an all-black image: u = v = 0 for every pixel -> every channel is the same rank-1 outer product
+    hb, _ = ho.rgbuv_histogram_f64(np.full((1, 8, 8, 4), -1.0, np.float32))
+    k0 = 1.0 / (1.0 + ho.tf_linspace_f32(-3, 3, 64).astype(np.float64) ** 2 / float(ho.sigma_sqr_f32()))
+    outer = np.outer(k0, k0)
+    assert np.allclose(hb[0, :, :, 0], outer / (3 * outer.sum()), rtol=1e-12)
+    assert np.allclose(hb[0, :, :, 1], hb[0, :, :, 0]) and np.allclose(hb[0, :, :, 2], hb[0, :, :, 0])
+
+
+def test_f32_restatement_close_to_f64(hist_golden):
+    """the reference's own float32 arithmetic is 2-5e-6 norm-relative from float64."""
+    assert ho.rel_l2(hist_golden["hist_fake_f32"], hist_golden["hist_fake"]) < 1e-5
+    assert ho.rel_max(hist_golden["hist_real_f32"], hist_golden["hist_real"]) < 1e-5
+    l32 = ho.hellinger_loss_f32(hist_golden["hist_real_f32"], hist_golden["hist_fake_f32"])
+    assert abs(float(l32) - float(hist_golden["loss"])) / float(hist_golden["loss"]) < 1e-5
+
+
+def test_golden_loss_and_grad_reproduce(hist_golden):
+    res = ho.hist_loss_and_grad_f64(hist_golden["real"][:2], hist_golden["fake"][:2], global_batch=8,
+                                    global_ssum=float(hist_golden["ssum"]))
+    assert np.allclose(res["grad"], hist_golden["grad"][:2], rtol=1e-10, atol=1e-14)
+    assert abs(res["loss"] - float(hist_golden["loss"])) < 1e-14
+
+
+def test_analytic_gradient_vs_torch_autograd(hist_golden):
+    real = hist_golden["real"][:1, ::2, ::2]
+    fake = hist_golden["fake"][:1, ::2, ::2]
+    res = ho.hist_loss_and_grad_f64(real, fake)
+    loss, grad = tp.hist_loss_fwd_bwd(torch.from_numpy(real).double(), torch.from_numpy(fake).double())
+    assert abs(float(loss) - res["loss"]) < 1e-13
+    assert ho.rel_l2(res["grad"], grad.numpy()) < 1e-12
+    assert np.abs(res["grad"][..., 3]).max() == 0.0
+
+
+def test_analytic_gradient_vs_finite_differences():
+    rng = np.random.default_rng(3)
+    real = np.tanh(rng.standard_normal((2, 6, 6, 4))).astype(np.float32)
+    fake = np.tanh(rng.standard_normal((2, 6, 6, 4))).astype(np.float32)
+    res = ho.hist_loss_and_grad_f64(real, fake, size=16)
+    h = 2.0 ** -17  # exactly representable in float32, so the perturbed images are exact
+    for (b, y, x, c) in [(0, 1, 2, 0), (1, 3, 3, 1), (0, 5, 0, 2), (1, 0, 4, 0)]:
+        up, dn = fake.copy(), fake.copy()
+        up[b, y, x, c] += np.float32(h)
+        dn[b, y, x, c] -= np.float32(h)
+        lu = ho.hellinger_loss_f64(ho.rgbuv_histogram_f64(real, 16)[0], ho.rgbuv_histogram_f64(up, 16)[0])
+        ld = ho.hellinger_loss_f64(ho.rgbuv_histogram_f64(real, 16)[0], ho.rgbuv_histogram_f64(dn, 16)[0])
+        fd = (lu - ld) / (float(up[b, y, x, c]) - float(dn[b, y, x, c]))
+        assert abs(fd - res["grad"][b, y, x, c]) < 2e-4 * max(abs(fd), 1e-6) + 1e-9
+
+
+def test_sharded_loss_equals_whole_batch(hist_golden):
+    """shards are coupled only through S and the global batch size."""
+    real, fake = hist_golden["real"][:4, ::2, ::2], hist_golden["fake"][:4, ::2, ::2]
+    whole = ho.hist_loss_and_grad_f64(real, fake, size=32)
+    parts = [ho.hist_loss_and_grad_f64(real[i:i + 2], fake[i:i + 2], size=32) for i in (0, 2)]
+    ssum = sum(p["ssum"] for p in parts)
+    assert abs(ssum - whole["ssum"]) < 1e-12
+    for k, i in enumerate((0, 2)):
+        sh = ho.hist_loss_and_grad_f64(real[i:i + 2], fake[i:i + 2], size=32, global_batch=4, global_ssum=ssum)
+        assert abs(sh["loss"] - whole["loss"]) < 1e-14
+        assert np.allclose(sh["grad"], whole["grad"][i:i + 2], rtol=1e-10, atol=1e-16)
+
+
+def test_rbf_method_and_unknown_method():
+    rng = np.random.default_rng(5)
+    img = np.tanh(rng.standard_normal((1, 8, 8, 3))).astype(np.float32)
+    h, _ = ho.rgbuv_histogram_f64(img, 16, method="RBF")
+    assert np.isclose(h.sum(), 1.0)
+    # sigma large enough that exp(-t) never underflows to 0 (sqrt'(0) = inf gives NaN in TF as well)
+    loss, grad = tp.hist_loss_fwd_bwd(torch.from_numpy(img).double(), torch.from_numpy(img * 0.5).double(), 16, "RBF", 0.5)
+    res = ho.hist_loss_and_grad_f64(img, img * 0.5, 16, "RBF", 0.5)
+    assert ho.rel_l2(res["grad"], grad.numpy()) < 1e-10
+    with pytest.raises(ValueError):
+        ho.rgbuv_histogram_f64(img, 16, method="thresholding")
