@@ -44,11 +44,11 @@ PROTOTYPES = {
     "ph_hist_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "ph_hist_forward": (_int, [_p, _i64, _i64, _int, _p, _int, _int, _f, _f, _p, _p, _p, _sz, _int, _p]),
     "ph_component_histogram": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _int, _int, _f, _f, _p, _p]),
-    "ph_hist_backward": (_int, [_p, _i64, _i64, _int, _p, _int, _int, _f, _f, _p, _p, _p, _p, _p, _i64, _f,
+    "ph_hist_backward": (_int, [_p, _i64, _i64, _int, _p, _int, _int, _f, _f, _p, _p, _p, _p, _p, _i64, _p,
                                 _p, _p, _sz, _int, _p]),
     "ph_hellinger_ssum": (_int, [_p, _p, _i64, _p, _p]),
     "ph_hellinger_finish": (_int, [_p, _i64, _p, _p]),
-    "ph_hellinger_backward": (_int, [_p, _p, _i64, _p, _i64, _f, _p, _p, _p]),
+    "ph_hellinger_backward": (_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _p]),
     "ph_mean_abs_or_sq_diff": (_int, [_p, _p, _i64, _int, _p, _p]),
     "ph_extract_palette": (_int, [_p, _i64, _i64, _int, _p, _p, _p]),
     "ph_rgba_to_indexed": (_int, [_p, _i64, _i64, _p, _i64, _int, _p, _p, _int, _p]),

@@ -48,10 +48,21 @@ static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; 
 // The three log-chroma differences generate all six (u,v) coordinates of the three channel
 // histograms (histogram.py:72-74):  R:(d_rg,d_rb)  G:(-d_rg,d_gb)  B:(-d_rb,-d_gb).
 struct PixelTerms {
-  float x0, x1, x2;        // image*0.5+0.5
-  float iy;                // sqrt(x0^2+x1^2+x2^2+eps)
-  float d_rg, d_rb, d_gb;  // log(x_a+eps)-log(x_b+eps), evaluated as log of the ratio
+  float x0, x1, x2;  // image*0.5+0.5
+  float iy;          // sqrt(x0^2+x1^2+x2^2+eps)
+  // log(x_a+eps)-log(x_b+eps) for (a,b) = (r,g), (r,b), (g,b), each as an unevaluated float pair
+  // hi+lo.  The bin kernel is 1/(1+(u-c)^2/sigma^2) with sigma = 0.02: an absolute error of 1e-7 in
+  // u (what float32 logs give, and what the reference's own arithmetic has) is a 1e-5 relative
+  // error in dK/du near the bin centre.  The three logs are therefore taken in float64 (3 per pixel
+  // against >= 384 bin weights per pixel) and the residual is carried into every (u-c).
+  float d_rg, d_rb, d_gb;
+  float l_rg, l_rb, l_gb;
 };
+
+__device__ __forceinline__ void split_double(double v, float& hi, float& lo) {
+  hi = (float)v;
+  lo = (float)(v - (double)hi);
+}
 
 __device__ __forceinline__ PixelTerms pixel_terms(float r, float g, float b, float eps) {
   PixelTerms t;
@@ -59,20 +70,21 @@ __device__ __forceinline__ PixelTerms pixel_terms(float r, float g, float b, flo
   t.x1 = fmaf(g, 0.5f, 0.5f);
   t.x2 = fmaf(b, 0.5f, 0.5f);
   t.iy = sqrtf(t.x0 * t.x0 + t.x1 * t.x1 + t.x2 * t.x2 + eps);
-  const float e0 = t.x0 + eps, e1 = t.x1 + eps, e2 = t.x2 + eps;
-  // log(a)-log(b) computed as log(a/b): one rounding of the ratio (6e-8 relative) and one of the
-  // result instead of two roundings at magnitude up to 13.8 (ulp 9.5e-7); exact 0 when a == b.
-  t.d_rg = logf(e0 / e1);
-  t.d_rb = logf(e0 / e2);
-  t.d_gb = logf(e1 / e2);
+  const double e = (double)eps;
+  const double l0 = log(fma((double)r, 0.5, 0.5) + e);
+  const double l1 = log(fma((double)g, 0.5, 0.5) + e);
+  const double l2 = log(fma((double)b, 0.5, 0.5) + e);
+  split_double(l0 - l1, t.d_rg, t.l_rg);
+  split_double(l0 - l2, t.d_rb, t.l_rb);
+  split_double(l1 - l2, t.d_gb, t.l_gb);
   return t;
 }
 
-// (u,v) of output channel c (0=R,1=G,2=B) — histogram.py:72-74.
-__device__ __forceinline__ void channel_uv(const PixelTerms& t, int c, float& u, float& v) {
-  if (c == 0) { u = t.d_rg; v = t.d_rb; }
-  else if (c == 1) { u = -t.d_rg; v = t.d_gb; }
-  else { u = -t.d_rb; v = -t.d_gb; }
+// (u,v) of output channel c (0=R,1=G,2=B) as hi+lo pairs — histogram.py:72-74.
+__device__ __forceinline__ void channel_uv(const PixelTerms& t, int c, float& u, float& ul, float& v, float& vl) {
+  if (c == 0) { u = t.d_rg; ul = t.l_rg; v = t.d_rb; vl = t.l_rb; }
+  else if (c == 1) { u = -t.d_rg; ul = -t.l_rg; v = t.d_gb; vl = t.l_gb; }
+  else { u = -t.d_rb; ul = -t.l_rb; v = -t.d_gb; vl = -t.l_gb; }
 }
 
 // Bin kernel (histogram.py:20-27): t = (x-c)^2/sigma^2; IQ: 1/(1+t); RBF: exp(-t).

@@ -71,15 +71,15 @@ __global__ void __launch_bounds__(FWD_THREADS) hist_fwd_simt_kernel(FwdParams p)
 
   for (int64_t base = px_begin; base < px_end; base += FWD_TP) {
     // ---- lanes 0..7 of each warp fetch one pixel each and derive (u, v, iy) ----
-    float u_l = 0.f, v_l = 0.f, iy_l = 0.f;
+    float u_l = 0.f, v_l = 0.f, iy_l = 0.f, ul_l = 0.f, vl_l = 0.f;
     if (lane < 8) {
       const int64_t px = base + warp * 8 + lane;
       if (px < px_end) {
         if (p.comp != nullptr) {
           const int64_t o = b * p.npix + px;
-          const float ec = p.comp[o] + p.eps;
-          u_l = logf(ec / (p.proj1[o] + p.eps));
-          v_l = logf(ec / (p.proj2[o] + p.eps));
+          const double lc = log((double)p.comp[o] + (double)p.eps);
+          split_double(lc - log((double)p.proj1[o] + (double)p.eps), u_l, ul_l);
+          split_double(lc - log((double)p.proj2[o] + (double)p.eps), v_l, vl_l);
           iy_l = p.inten[o];
         } else {
           const float* src = p.image + (b * p.npix + px) * p.channels;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(FWD_THREADS) hist_fwd_simt_kernel(FwdParams p)
             r = __ldg(src); g = __ldg(src + 1); bl = __ldg(src + 2);
           }
           const PixelTerms t = pixel_terms(r, g, bl, p.eps);
-          channel_uv(t, c, u_l, v_l);
+          channel_uv(t, c, u_l, ul_l, v_l, vl_l);
           iy_l = t.iy;
         }
       }
@@ -100,13 +100,15 @@ __global__ void __launch_bounds__(FWD_THREADS) hist_fwd_simt_kernel(FwdParams p)
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const float u = __shfl_sync(0xffffffffu, u_l, kk);
+      const float ul = __shfl_sync(0xffffffffu, ul_l, kk);
       const float v = __shfl_sync(0xffffffffu, v_l, kk);
+      const float vl = __shfl_sync(0xffffffffu, vl_l, kk);
       const float iy = __shfl_sync(0xffffffffu, iy_l, kk);
       const int k = warp * 8 + kk;
-      As[k][lane] = mu0 * iy * bin_weight<METHOD>(u - du0, p.inv_sigma_sqr);
-      As[k][lane + 32] = mu1 * iy * bin_weight<METHOD>(u - du1, p.inv_sigma_sqr);
-      Bs[k][lane] = mv0 * bin_weight<METHOD>(v - dv0, p.inv_sigma_sqr);
-      Bs[k][lane + 32] = mv1 * bin_weight<METHOD>(v - dv1, p.inv_sigma_sqr);
+      As[k][lane] = mu0 * iy * bin_weight<METHOD>((u - du0) + ul, p.inv_sigma_sqr);
+      As[k][lane + 32] = mu1 * iy * bin_weight<METHOD>((u - du1) + ul, p.inv_sigma_sqr);
+      Bs[k][lane] = mv0 * bin_weight<METHOD>((v - dv0) + vl, p.inv_sigma_sqr);
+      Bs[k][lane + 32] = mv1 * bin_weight<METHOD>((v - dv1) + vl, p.inv_sigma_sqr);
     }
     __syncthreads();
 #pragma unroll 8
@@ -348,9 +350,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) hist_bwd_simt_kernel(BwdParams
   const int64_t plane = (int64_t)p.bins * p.bins;
 
   for (int c = 0; c < 3; ++c) {
-    float u[2], v[2];
-    channel_uv(t[0], c, u[0], v[0]);
-    channel_uv(t[1], c, u[1], v[1]);
+    float u[2], v[2], ul[2], vl[2];
+    channel_uv(t[0], c, u[0], ul[0], v[0], vl[0]);
+    channel_uv(t[1], c, u[1], ul[1], v[1], vl[1]);
     float gu[2] = {0.f, 0.f}, gv[2] = {0.f, 0.f};
     for (int ti = 0; ti < p.tiles; ++ti) {
       for (int tj = 0; tj < p.tiles; ++tj) {
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) hist_bwd_simt_kernel(BwdParams
           float kv[2], dkv[2];
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const float d = v[s] - cj;
+            const float d = (v[s] - cj) + vl[s];
             kv[s] = bin_weight<METHOD>(d, p.inv_sigma_sqr);
             dkv[s] = bin_weight_grad<METHOD>(d, kv[s], p.inv_sigma_sqr);
           }
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) hist_bwd_simt_kernel(BwdParams
           const float ci = domS[ti * 64 + q * 16 + i];
 #pragma unroll
           for (int s = 0; s < 2; ++s) {
-            const float d = u[s] - ci;
+            const float d = (u[s] - ci) + ul[s];
             const float ku = bin_weight<METHOD>(d, p.inv_sigma_sqr);
             const float dku = bin_weight_grad<METHOD>(d, ku, p.inv_sigma_sqr);
             g_iy[s] = fmaf(ku, P[s][i], g_iy[s]);

@@ -53,13 +53,23 @@ def test_library_exports_every_declared_symbol(pkg):
 
 def test_ctypes_prototypes_match_header(pkg):
     assert sorted(pkg._lib.PROTOTYPES) == declared_symbols()
-    # argument counts agree with the header's parameter lists
+    # argument counts AND kinds agree with the header's parameter lists
     text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+
+    def kind(ctype):
+        if ctype in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ctype, "contents"):
+            return "ptr"
+        return {ctypes.c_int64: "int64_t", ctypes.c_int: "int", ctypes.c_float: "float",
+                ctypes.c_double: "double", ctypes.c_size_t: "size_t"}[ctype]
+
     for name, (_, args) in pkg._lib.PROTOTYPES.items():
         m = re.search(r"\b%s\s*\(([^)]*)\)" % name, text)
         params = m.group(1).strip()
-        n = 0 if params in ("", "void") else params.count(",") + 1
-        assert n == len(args), (name, n, len(args))
+        plist = [] if params in ("", "void") else [x.strip() for x in params.split(",")]
+        assert len(plist) == len(args), (name, plist, args)
+        for decl, ctype in zip(plist, args):
+            expected = "ptr" if "*" in decl else decl.replace("const ", "").split()[0]
+            assert kind(ctype) == expected, (name, decl, ctype)
 
 
 def test_no_cpu_fallback(pkg):

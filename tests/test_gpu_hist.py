@@ -176,7 +176,8 @@ def test_full_size_properties(H, cuda, impl):
                      h2.detach(), H._forward(f2.detach(), H.histogram_domain(64, cuda), 0, H._sigma_sqr(0.02),
                                              0 if impl == "auto" else 1)[1],
                      hist_true=hr[256:].contiguous(), ssum=ssum, global_batch=b)
-    assert ho.rel_l2(g2.cpu().numpy(), fake.grad[256:].cpu().numpy()) < 1e-6
+    # the two evaluations split the pixel axis differently (batch-dependent grid), so they differ by fp32 rounding
+    assert ho.rel_l2(g2.cpu().numpy(), fake.grad[256:].cpu().numpy()) < 1e-5
 
 
 def test_simt_and_auto_engines_agree(H, cuda):
