@@ -511,6 +511,11 @@ int simt_hist_forward(const float* image, int64_t batch, int64_t npix, int chann
   return PH_OK;
 }
 
+void launch_finalize(const float* partial, int splits, int nch, int bins, int normalise, float* hist,
+                     float* denom, int64_t batch, cudaStream_t st) {
+  hist_finalize_kernel<<<(unsigned)batch, 256, 0, st>>>(partial, splits, nch, bins, normalise, hist, denom);
+}
+
 int simt_component_histogram(const float* comp, const float* proj1, const float* proj2,
                              const float* inten, int64_t batch, int64_t npix, const float* dom, int bins,
                              int method, float sigma_sqr, float eps, float* hist_raw, cudaStream_t st) {
