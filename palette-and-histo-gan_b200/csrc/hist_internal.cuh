@@ -20,7 +20,7 @@ int simt_component_histogram(const float* comp, const float* proj1, const float*
                              int method, float sigma_sqr, float eps, float* hist_raw, cudaStream_t st);
 int launch_bwd_prep(const float* hist_pred, const float* denom, const float* grad_hist,
                     const float* hist_true, const double* ssum, int64_t global_batch, const float* loss_scale,
-                    int64_t batch, int bins, float* ghat, cudaStream_t st);
+                    int64_t batch, int bins, int transposed, float* ghat, cudaStream_t st);
 int simt_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                        int bins, int method, float sigma_sqr, float eps, const float* hist_pred,
                        const float* denom, const float* grad_hist, const float* hist_true,

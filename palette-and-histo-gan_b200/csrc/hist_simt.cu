@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) hist_bwd_prep_kernel(
     const float* __restrict__ hist_pred, const float* __restrict__ denom,
     const float* __restrict__ grad_hist, const float* __restrict__ hist_true,
     const double* __restrict__ ssum, double global_batch, const float* loss_scale, int bins,
-    float* __restrict__ ghat) {
+    int transposed, float* __restrict__ ghat) {
   __shared__ double scratch[32];
   const int64_t b = blockIdx.x;
   const int64_t plane = (int64_t)bins * bins, per_image = plane * 3;
@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(256) hist_bwd_prep_kernel(
     const int64_t ij = e / 3;
     const int c = (int)(e % 3);
     const int64_t i = ij / bins, j = ij % bins;
-    out[c * plane + j * bins + i] = (g - fdot) * inv_d;
+    // transposed: [c][j][i] (CUDA-core kernel); else [c][i][j] (K-major B operand of the tensor-core kernel)
+    out[c * plane + (transposed ? j * bins + i : i * bins + j)] = (g - fdot) * inv_d;
   }
 }
 
@@ -546,9 +547,9 @@ int simt_component_histogram(const float* comp, const float* proj1, const float*
 
 int launch_bwd_prep(const float* hist_pred, const float* denom, const float* grad_hist,
                     const float* hist_true, const double* ssum, int64_t global_batch, const float* loss_scale,
-                    int64_t batch, int bins, float* ghat, cudaStream_t st) {
+                    int64_t batch, int bins, int transposed, float* ghat, cudaStream_t st) {
   hist_bwd_prep_kernel<<<(unsigned)batch, 256, 0, st>>>(hist_pred, denom, grad_hist, hist_true, ssum,
-                                                        (double)global_batch, loss_scale, bins, ghat);
+                                                        (double)global_batch, loss_scale, bins, transposed, ghat);
   PH_LAUNCH_OK("hist_bwd_prep_kernel");
   return PH_OK;
 }
@@ -561,7 +562,7 @@ int simt_hist_backward(const float* image, int64_t batch, int64_t npix, int chan
   PH_CHECK_ARG(bins <= 1024, "SIMT backward supports at most 1024 bins (got %d)", bins);
   float* ghat = static_cast<float*>(workspace);
   int rc = launch_bwd_prep(hist_pred, denom, grad_hist, hist_true, ssum, global_batch, loss_scale, batch,
-                           bins, ghat, st);
+                           bins, 1, ghat, st);
   if (rc != PH_OK) return rc;
   BwdParams p{};
   p.image = image;

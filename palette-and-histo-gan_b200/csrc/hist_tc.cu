@@ -2,14 +2,15 @@
 // (histogram.py:29-30) as kind::tf32 MMAs with fp32 emulation by operand splitting
 // (w = hi + lo, both tf32; hi.hi + hi.lo + lo.hi + lo.lo accumulated in fp32 in TMEM).
 //
-// Forward, 64 bins, one persistent CTA per SM, 13 warps:
-//   warps 9-12  pixel terms: RGBA load, float64 log-chroma (hi+lo), intensity -> smem ring
+// Forward, 64 bins, one persistent CTA per SM, 21 warps:
+//   warps 17-20 pixel terms: RGBA load, float64 log-chroma (hi+lo), intensity -> smem ring
 //               (round-robin over 32-pixel rounds)
-//   warps 0-3   A operand (u side, Iy-weighted) written straight into TMEM: lane = bin, the two
+//   warps 0-7   A operand (u side, Iy-weighted) written straight into TMEM: lane = bin, the two
 //               half-warps of a TMEM sub-partition hold the hi and the lo rows of the same 16 bins,
-//               so M = 128 = 64 bins x {hi, lo};   also the epilogue (TMEM -> global) warps
-//   warps 4-7   B operand (v side) hi|lo into shared memory, K-major no-swizzle core matrices
-//   warp 8      one thread issues tcgen05.mma (M=128, N=64, K=8) twice per k-step: B_hi and B_lo,
+//               so M = 128 = 64 bins x {hi, lo}; warps w and w+4 share a sub-partition and take 16 of
+//               the 32 pixels of a stage each;   also the epilogue (TMEM -> global) warps
+//   warps 8-15  B operand (v side) hi|lo into shared memory, K-major no-swizzle core matrices
+//   warp 16     one thread issues tcgen05.mma (M=128, N=64, K=8) twice per k-step: B_hi and B_lo,
 //               accumulating all four cross terms into the same 64 TMEM columns per channel
 // The operands never exist in global memory: they are generated from 16 B per pixel.
 #include "common.cuh"
@@ -25,9 +26,11 @@ namespace fwdtc {
 constexpr int BINS = 64;
 constexpr int KB = 32;        // pixels per pipeline stage
 constexpr int NS = 3;         // A/B operand stages
-constexpr int PXW = 4;        // pixel-term warps
+constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 4;
+constexpr int MMA_WARP = A_WARPS + B_WARPS;  // 16
+constexpr int PX_WARP0 = MMA_WARP + 1;       // 17
 constexpr int PR = 8;         // pixel-term ring slots
-constexpr int THREADS = (9 + PXW) * 32;  // 13 warps
+constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 21 warps
 constexpr int TMEM_COLS = 512;
 constexpr int D_COLS = 64;                 // per channel
 constexpr int A_COL0 = 3 * D_COLS;         // 192
@@ -78,14 +81,14 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 32); mbar_init(&S.px_empty[i], 256); }
-    for (int i = 0; i < NS; ++i) { mbar_init(&S.ab_full[i], 256); mbar_init(&S.ab_empty[i], 1); }
+    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 32); mbar_init(&S.px_empty[i], (A_WARPS + B_WARPS) * 32); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&S.ab_full[i], (A_WARPS + B_WARPS) * 32); mbar_init(&S.ab_empty[i], 1); }
     mbar_init(&S.d_full, 1);
-    mbar_init(&S.d_empty, 128);
+    mbar_init(&S.d_empty, A_WARPS * 32);
     fence_mbar_init();
   }
   if (tid < BINS) S.dom[tid] = p.dom[tid];
-  if (warp == 8) tmem_alloc(&S.tmem_base, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -93,9 +96,9 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
 
   const int64_t first = blockIdx.x, step = gridDim.x;
 
-  if (warp >= 9) {
+  if (warp >= PX_WARP0) {
     // ===================== pixel terms (PXW warps, round-robin over rounds) =====================
-    const int me = warp - 9;
+    const int me = warp - PX_WARP0;
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const int64_t b = w / p.splits, split = w % p.splits;
@@ -129,12 +132,15 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         mbar_arrive(&S.px_full[slot]);
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < A_WARPS) {
     // ===================== A operand (TMEM) + epilogue =====================
+    const int quad = warp & 3;                  // TMEM sub-partition of this warp
+    const int sub = warp >> 2;                  // which 16 of the 32 pixels of a stage
     const int half = lane >> 4;                 // 0: hi rows, 1: lo rows
-    const int bin = warp * 16 + (lane & 15);
+    const int bin = quad * 16 + (lane & 15);
     const float c_bin = S.dom[bin];
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int px_own = sub * 16 + half * 8;     // the 8 pixels this thread evaluates
     uint32_t it = 0, item_idx = 0;
     for (int64_t w = first; w < p.items; w += step, ++item_idx) {
       const int64_t b = w / p.splits, split = w % p.splits;
@@ -148,64 +154,63 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         const PxSlot& in = S.px[slot];
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
-          float wv[16];
+          uint32_t out[16];
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 uh = *reinterpret_cast<const float4*>(&in.u_hi[c][half * 16 + i4 * 4]);
-            const float4 ul = *reinterpret_cast<const float4*>(&in.u_lo[c][half * 16 + i4 * 4]);
-            const float4 iy = *reinterpret_cast<const float4*>(&in.iy[half * 16 + i4 * 4]);
-            wv[i4 * 4 + 0] = iy.x * weight<METHOD>((uh.x - c_bin) + ul.x, p.inv_sigma_sqr);
-            wv[i4 * 4 + 1] = iy.y * weight<METHOD>((uh.y - c_bin) + ul.y, p.inv_sigma_sqr);
-            wv[i4 * 4 + 2] = iy.z * weight<METHOD>((uh.z - c_bin) + ul.z, p.inv_sigma_sqr);
-            wv[i4 * 4 + 3] = iy.w * weight<METHOD>((uh.w - c_bin) + ul.w, p.inv_sigma_sqr);
-          }
-          uint32_t out[32];
+          for (int i4 = 0; i4 < 2; ++i4) {
+            const float4 uh = *reinterpret_cast<const float4*>(&in.u_hi[c][px_own + i4 * 4]);
+            const float4 ul = *reinterpret_cast<const float4*>(&in.u_lo[c][px_own + i4 * 4]);
+            const float4 iy = *reinterpret_cast<const float4*>(&in.iy[px_own + i4 * 4]);
+            const float wv[4] = {iy.x * weight<METHOD>((uh.x - c_bin) + ul.x, p.inv_sigma_sqr),
+                                 iy.y * weight<METHOD>((uh.y - c_bin) + ul.y, p.inv_sigma_sqr),
+                                 iy.z * weight<METHOD>((uh.z - c_bin) + ul.z, p.inv_sigma_sqr),
+                                 iy.w * weight<METHOD>((uh.w - c_bin) + ul.w, p.inv_sigma_sqr)};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float other = __shfl_xor_sync(0xffffffffu, wv[i], 16);
-            const float lo_px = half ? other : wv[i];   // pixel i      (computed by the hi half-warp)
-            const float hi_px = half ? wv[i] : other;   // pixel 16 + i (computed by the lo half-warp)
-            out[i] = half ? tf32_lo(lo_px) : tf32_hi(lo_px);
-            out[16 + i] = half ? tf32_lo(hi_px) : tf32_hi(hi_px);
+            for (int e = 0; e < 4; ++e) {
+              // split once, keep the part this row needs, send the other part to the partner row
+              const uint32_t hi = tf32_hi(wv[e]);
+              const uint32_t lo = __float_as_uint(wv[e] - __uint_as_float(hi));
+              const uint32_t keep = half ? lo : hi;
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, half ? hi : lo, 16);
+              const int i = i4 * 4 + e;
+              out[i] = half ? recv : keep;      // pixels sub*16 + 0..7  (evaluated by the hi half-warp)
+              out[8 + i] = half ? keep : recv;  // pixels sub*16 + 8..15 (evaluated by the lo half-warp)
+            }
           }
-          tmem_st32(tmem + lane_addr + A_COL0 + stage * A_STAGE_COLS + c * KB, out);
+          tmem_st16(tmem + lane_addr + A_COL0 + stage * A_STAGE_COLS + c * KB + sub * 16, out);
         }
         tmem_st_wait();
         tc_fence_before_sync();
         mbar_arrive(&S.px_empty[slot]);
         mbar_arrive(&S.ab_full[stage]);
       }
-      // ---- epilogue: D (TMEM) -> partial histogram of this work item ----
+      // ---- epilogue: D (TMEM) -> partial histogram of this work item; warps w / w+4 take 32 columns each ----
       mbar_wait(&S.d_full, item_idx & 1);
       tc_fence_after_sync();
       float* dst = p.partial + ((b * p.splits + split) * 3) * (int64_t)(BINS * BINS);
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
-#pragma unroll 1
-        for (int part = 0; part < 2; ++part) {
-          uint32_t v[32];
-          tmem_ld32(tmem + lane_addr + c * D_COLS + part * 32, v);
-          tmem_ld_wait();
-          float f[32];
+        uint32_t v[32];
+        tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
+        tmem_ld_wait();
+        float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float mine = __uint_as_float(v[i]);
-            f[i] = mine + __shfl_xor_sync(0xffffffffu, mine, 16);  // hi-row sum + lo-row sum
-          }
-          if (half == 0) {
-            float4* row = reinterpret_cast<float4*>(dst + (int64_t)c * BINS * BINS + bin * BINS + part * 32);
+        for (int i = 0; i < 32; ++i) {
+          const float mine = __uint_as_float(v[i]);
+          f[i] = mine + __shfl_xor_sync(0xffffffffu, mine, 16);  // hi-row sum + lo-row sum
+        }
+        if (half == 0) {
+          float4* row = reinterpret_cast<float4*>(dst + (int64_t)c * BINS * BINS + bin * BINS + sub * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) row[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-          }
+          for (int i = 0; i < 8; ++i) row[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
         }
       }
       tc_fence_before_sync();
       mbar_arrive(&S.d_empty);
     }
-  } else if (warp < 8) {
+  } else if (warp < MMA_WARP) {
     // ===================== B operand (shared memory) =====================
-    const int t = tid - 128;
-    const int j = t & 63, half = t >> 6;  // half: which 16 of the 32 pixels
+    const int t = tid - A_WARPS * 32;
+    const int j = t & 63, part = t >> 6;  // part: which 8 of the 32 pixels (two 4-pixel quads)
     const float c_bin = S.dom[j];
     const uint32_t row_off = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);  // hi row j; lo row j + 64 is +1024
     uint32_t it = 0;
@@ -222,8 +227,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         for (int c = 0; c < 3; ++c) {
           unsigned char* tile = &S.b[stage][c * B_CH_BYTES];
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int kq = half * 4 + q4;
+          for (int q4 = 0; q4 < 2; ++q4) {
+            const int kq = part * 2 + q4;
             const float4 vh = *reinterpret_cast<const float4*>(&in.v_hi[c][kq * 4]);
             const float4 vl = *reinterpret_cast<const float4*>(&in.v_lo[c][kq * 4]);
             const float w0 = weight<METHOD>((vh.x - c_bin) + vl.x, p.inv_sigma_sqr);
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         mbar_arrive(&S.ab_full[stage]);
       }
     }
-  } else if (warp == 8 && lane == 0) {
+  } else if (warp == MMA_WARP && lane == 0) {
     // ===================== MMA issue =====================
     constexpr uint32_t IDESC = idesc_tf32(128, 64);
     const uint32_t b_base = smem_u32(&S.b[0][0]);
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, TMEM_COLS);
+  if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 }  // namespace fwdtc
@@ -355,15 +360,6 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   launch_finalize(p.partial, p.splits, 3, bins, 1, hist, denom, batch, st);
   PH_LAUNCH_OK("hist_finalize_kernel");
   return PH_OK;
-}
-
-int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int bins,
-                     int method, float sigma_sqr, float eps, const float* hist_pred, const float* denom,
-                     const float* grad_hist, const float* hist_true, const double* ssum, int64_t global_batch,
-                     const float* loss_scale, float* grad_image, void* workspace, cudaStream_t st) {
-  // backward contraction on tensor cores: next milestone; the CUDA-core kernel serves it meanwhile
-  return simt_hist_backward(image, batch, npix, channels, dom, bins, method, sigma_sqr, eps, hist_pred, denom,
-                            grad_hist, hist_true, ssum, global_batch, loss_scale, grad_image, workspace, st);
 }
 
 }  // namespace ph
