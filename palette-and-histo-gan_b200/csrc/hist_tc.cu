@@ -1,18 +1,25 @@
 // RGB-uv histogram, tensor-core engine (tcgen05, sm_100a): the Ku^T.Kv contraction over pixels
 // (histogram.py:29-30) as kind::tf32 MMAs with fp32 emulation by operand splitting
-// (w = hi + lo, both tf32; hi.hi + hi.lo + lo.hi + lo.lo accumulated in fp32 in TMEM).
+// (w = hi + lo, both tf32; hi.hi + hi.lo + lo.hi + lo.lo accumulated in fp32 in TMEM), fused with the
+// per-image normalisation (histogram.py:75-79).
 //
 // Forward, 64 bins, one persistent CTA per SM, 21 warps:
-//   warps 17-20 pixel terms: RGBA load, float64 log-chroma (hi+lo), intensity -> smem ring
-//               (round-robin over 32-pixel rounds)
-//   warps 0-7   A operand (u side, Iy-weighted) written straight into TMEM: lane = bin, the two
-//               half-warps of a TMEM sub-partition hold the hi and the lo rows of the same 16 bins,
-//               so M = 128 = 64 bins x {hi, lo}; warps w and w+4 share a sub-partition and take 16 of
-//               the 32 pixels of a stage each;   also the epilogue (TMEM -> global) warps
+//   warps 17-20 pixel pass: 128-bit RGBA loads, log-chroma u/v per channel and intensity Iy -> smem ring
+//   warps 0-7   A operand (u side, Iy-weighted) written straight into TMEM, M = 128 rows =
+//               64 bins x {hi, lo}: TMEM sub-partitions 0,1 hold the hi rows of bins 0-31 / 32-63,
+//               sub-partitions 2,3 the lo rows, so a warp's role is uniform.  The hi warp and the lo
+//               warp of the same bins evaluate 8 pixels each and swap halves through shared memory.
+//               The same warps drain the accumulators (epilogue).
 //   warps 8-15  B operand (v side) hi|lo into shared memory, K-major no-swizzle core matrices
 //   warp 16     one thread issues tcgen05.mma (M=128, N=64, K=8) twice per k-step: B_hi and B_lo,
 //               accumulating all four cross terms into the same 64 TMEM columns per channel
-// The operands never exist in global memory: they are generated from 16 B per pixel.
+// The bin weights never exist in global memory: they are generated from 16 B per pixel with packed
+// fp32x2 arithmetic (FADD2/FMUL2/FFMA2) and one MUFU.RCP per weight.
+//
+// Accuracy: the tensor core adds every K=8 block into the fp32 accumulator with truncation, so the
+// error grows with the chain length (measured 8e-6 for 4096 pixels in one chain, ~1e-6 for 1024).
+// Chains are cut at 1024 pixels and summed in fp32 in a shared-memory accumulator; when a CTA owns a
+// whole image the normaliser D and H/D are produced in the same kernel.
 #include "common.cuh"
 #include "hist_internal.cuh"
 #include "tc_ptx.cuh"
@@ -24,13 +31,14 @@ using namespace tc;
 namespace fwdtc {
 
 constexpr int BINS = 64;
-constexpr int KB = 32;        // pixels per pipeline stage
-constexpr int NS = 3;         // A/B operand stages
+constexpr int KB = 32;         // pixels per pipeline stage
+constexpr int NS = 3;          // A/B operand stages
+constexpr int CHAIN_KB = 32;   // stages per TMEM accumulation chain (1024 pixels)
 constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 4;
-constexpr int MMA_WARP = A_WARPS + B_WARPS;  // 16
-constexpr int PX_WARP0 = MMA_WARP + 1;       // 17
-constexpr int PR = 8;         // pixel-term ring slots
-constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 21 warps
+constexpr int MMA_WARP = A_WARPS + B_WARPS;     // 16
+constexpr int PX_WARP0 = MMA_WARP + 1;          // 17
+constexpr int PR = 6;                           // pixel ring slots
+constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 672
 constexpr int TMEM_COLS = 512;
 constexpr int D_COLS = 64;                 // per channel
 constexpr int A_COL0 = 3 * D_COLS;         // 192
@@ -41,13 +49,16 @@ constexpr int B_KQ_BYTES = 16 * 128;       // 2048: one 4-pixel quad for all 128
 static_assert(A_COL0 + NS * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
 
 struct PxSlot {
-  float u_hi[3][KB], u_lo[3][KB], v_hi[3][KB], v_lo[3][KB], iy[KB];
+  float u[3][KB], v[3][KB], iy[KB];
 };
 
 struct Smem {
-  alignas(128) unsigned char b[NS][B_STAGE_BYTES];
+  alignas(128) unsigned char b[NS][B_STAGE_BYTES];  // 144 KB
+  float acc[3][BINS][BINS];                         // [c][j][i] running fp32 sum over chains, 48 KB
+  float4 xbuf[4][2][3][2][32];                      // [pair][direction][channel][quad of 4 px][lane], 24 KB
   PxSlot px[PR];
   float dom[BINS];
+  double red[8];
   alignas(8) uint64_t px_full[PR], px_empty[PR], ab_full[NS], ab_empty[NS], d_full, d_empty;
   uint32_t tmem_base;
 };
@@ -55,7 +66,9 @@ struct Smem {
 struct Params {
   const float* image;
   const float* dom;
-  float* partial;  // (B, splits, 3, 64, 64)
+  float* partial;  // (B, splits, 3, 64, 64) raw sums, used when splits > 1
+  float* hist;     // (B, 64, 64, 3) normalised, written directly when splits == 1
+  float* denom;    // (B)
   int64_t npix;
   int channels;
   int splits;
@@ -65,11 +78,154 @@ struct Params {
   float eps;
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// two bin weights at once: d = x + (-c);  IQ: 1/(1 + d^2/s^2), RBF: exp(-d^2/s^2)
 template <int METHOD>
-__device__ __forceinline__ float weight(float d, float inv_s2) {
-  const float t = d * d;
-  if (METHOD == PH_METHOD_INVERSE_QUADRATIC) return fast_rcp(fmaf(t, inv_s2, 1.0f));
-  return __expf(-t * inv_s2);
+__device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 inv2, f32x2 one2) {
+  const f32x2 d = add2(x, negc);
+  const f32x2 t = mul2(d, d);
+  if (METHOD == PH_METHOD_INVERSE_QUADRATIC) {
+    const f32x2 e = fma2(t, inv2, one2);
+    return pack2(fast_rcp(lo_of(e)), fast_rcp(hi_of(e)));
+  } else {
+    const f32x2 e = mul2(t, inv2);
+    return pack2(__expf(-lo_of(e)), __expf(-hi_of(e)));
+  }
+}
+
+// A-operand producer + epilogue warp.  ROLE (0: hi rows, 1: lo rows) is a template parameter so the
+// keep/hand-over choices compile to plain register assignments.
+template <int METHOD, int ROLE>
+__device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t tmem, int tid, int warp, int lane,
+                                            int64_t first, int64_t step, f32x2 inv2, f32x2 one2, f32x2 mone2) {
+    // ===================== A operand (TMEM) + epilogue =====================
+    const int quad = warp & 3;        // TMEM sub-partition of this warp
+    const int sub = warp >> 2;        // which 16 of the 32 pixels of a stage
+    constexpr int role = ROLE;        // 0: hi rows, 1: lo rows (warp-uniform, compile-time here)
+    const int bin = (quad & 1) * 32 + lane;
+    const int pair = (quad & 1) * 2 + sub;            // the two warps sharing (bins, pixel half)
+    const float c_bin = S.dom[bin];
+    const f32x2 negc = pack2(-c_bin, -c_bin);
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int px_own = sub * 16 + role * 8;  // the 8 pixels this warp evaluates
+    uint32_t it = 0, chain = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const int64_t b = w / p.splits, split = w % p.splits;
+      const int64_t px0 = split * p.px_per_split;
+      const int64_t px1 = min(px0 + p.px_per_split, p.npix);
+      const int64_t nkb = (px1 - px0 + KB - 1) / KB;
+      for (int64_t kb = 0; kb < nkb; ++kb, ++it) {
+        const int slot = it % PR, stage = it % NS;
+        mbar_wait(&S.px_full[slot], (it / PR) & 1);
+        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
+        tc_fence_after_sync();
+        const PxSlot& in = S.px[slot];
+        // all three channels at once: 24 weights per thread in flight, one hand-over with the partner warp
+        // (barrier 1: partner has consumed the previous stage's hand-over; barrier 2: this stage's is written)
+        f32x2 keep[3][4];
+        named_bar_sync(1 + pair, 64);
+        ulonglong2* xs = reinterpret_cast<ulonglong2*>(&S.xbuf[pair][role][0][0][lane]);
+        const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(&S.xbuf[pair][role ^ 1][0][0][lane]);
+        const ulonglong2 ia = *reinterpret_cast<const ulonglong2*>(&in.iy[px_own]);
+        const ulonglong2 ib = *reinterpret_cast<const ulonglong2*>(&in.iy[px_own + 4]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const ulonglong2 ua = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own]);
+          const ulonglong2 ub = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own + 4]);
+          const f32x2 w0 = mul2(weight2<METHOD>(ua.x, negc, inv2, one2), ia.x);
+          const f32x2 w1 = mul2(weight2<METHOD>(ua.y, negc, inv2, one2), ia.y);
+          const f32x2 w2 = mul2(weight2<METHOD>(ub.x, negc, inv2, one2), ib.x);
+          const f32x2 w3 = mul2(weight2<METHOD>(ub.y, negc, inv2, one2), ib.y);
+          const f32x2 h0 = w0 & TF32_MASK2, h1 = w1 & TF32_MASK2, h2 = w2 & TF32_MASK2, h3 = w3 & TF32_MASK2;
+          const f32x2 l0 = fma2(h0, mone2, w0), l1 = fma2(h1, mone2, w1), l2 = fma2(h2, mone2, w2),
+                      l3 = fma2(h3, mone2, w3);
+          // keep the part this row set needs, hand the other part to the partner warp
+          if (role == 0) {
+            keep[c][0] = h0; keep[c][1] = h1; keep[c][2] = h2; keep[c][3] = h3;
+            xs[c * 64] = make_ulonglong2(l0, l1); xs[c * 64 + 32] = make_ulonglong2(l2, l3);
+          } else {
+            keep[c][0] = l0; keep[c][1] = l1; keep[c][2] = l2; keep[c][3] = l3;
+            xs[c * 64] = make_ulonglong2(h0, h1); xs[c * 64 + 32] = make_ulonglong2(h2, h3);
+          }
+        }
+        named_bar_sync(1 + pair, 64);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const ulonglong2 ra = xr[c * 64], rb = xr[c * 64 + 32];
+          const f32x2 got[4] = {ra.x, ra.y, rb.x, rb.y};
+          uint32_t out[16];
+          // columns sub*16 + 0..7 are the pixels of the hi warp, + 8..15 those of the lo warp
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const f32x2 first8 = role == 0 ? keep[c][e] : got[e];
+            const f32x2 second8 = role == 0 ? got[e] : keep[c][e];
+            out[2 * e] = (uint32_t)first8;
+            out[2 * e + 1] = (uint32_t)(first8 >> 32);
+            out[8 + 2 * e] = (uint32_t)second8;
+            out[8 + 2 * e + 1] = (uint32_t)(second8 >> 32);
+          }
+          tmem_st16(tmem + lane_addr + A_COL0 + stage * A_STAGE_COLS + c * KB + sub * 16, out);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&S.px_empty[slot]);
+        mbar_arrive(&S.ab_full[stage]);
+
+        const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
+        if (!chain_end) continue;
+        // ---- chain epilogue: D (TMEM) += into the fp32 shared-memory accumulator ----
+        mbar_wait(&S.d_full, chain & 1);
+        ++chain;
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(&S.acc[c][sub * 32 + i][bin], __uint_as_float(v[i]));
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&S.d_empty);
+        if (kb + 1 != nkb) continue;
+
+        // ---- item epilogue: all 8 warps, normalise (whole image) or emit the raw partial ----
+        named_bar_sync(5, A_WARPS * 32);
+        const int t = tid;  // 0..255
+        float* accf = &S.acc[0][0][0];
+        if (p.splits == 1) {
+          double s = 0.0;
+          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) s += (double)accf[e];
+          s = warp_sum(s);
+          if (lane == 0) S.red[warp] = s;
+          named_bar_sync(5, A_WARPS * 32);
+          double tot = 0.0;
+#pragma unroll
+          for (int k = 0; k < A_WARPS; ++k) tot += S.red[k];
+          const float d = (float)tot;
+          if (t == 0) p.denom[b] = d;
+          float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
+          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
+            const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
+            float* a = &S.acc[c][j][i];
+            dst[e] = *a / d;
+            *a = 0.f;
+          }
+        } else {
+          float* dst = p.partial + ((b * p.splits + split) * 3) * (int64_t)(BINS * BINS);
+          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
+            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
+            float* a = &S.acc[c][j][i];
+            dst[e] = *a;
+            *a = 0.f;
+          }
+        }
+        named_bar_sync(5, A_WARPS * 32);
+      }
+    }
 }
 
 template <int METHOD>
@@ -78,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
   // __shared__ symbol (no integer round trip) lets ptxas emit LDS/STS instead of generic LD/ST
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 32); mbar_init(&S.px_empty[i], (A_WARPS + B_WARPS) * 32); }
@@ -88,6 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     fence_mbar_init();
   }
   if (tid < BINS) S.dom[tid] = p.dom[tid];
+  for (int i = tid; i < 3 * BINS * BINS; i += THREADS) (&S.acc[0][0][0])[i] = 0.f;
   if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
@@ -95,9 +252,12 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
   const uint32_t tmem = S.tmem_base;
 
   const int64_t first = blockIdx.x, step = gridDim.x;
+  const f32x2 inv2 = pack2(p.inv_sigma_sqr, p.inv_sigma_sqr);
+  const f32x2 one2 = pack2(1.0f, 1.0f);
+  const f32x2 mone2 = pack2(-1.0f, -1.0f);
 
   if (warp >= PX_WARP0) {
-    // ===================== pixel terms (PXW warps, round-robin over rounds) =====================
+    // ===================== pixel pass (PXW warps, round-robin over 32-pixel rounds) =====================
     const int me = warp - PX_WARP0;
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
@@ -119,99 +279,30 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
             r = __ldg(src); g = __ldg(src + 1); bl = __ldg(src + 2);
           }
         }
-        const PixelTerms t = pixel_terms(r, g, bl, p.eps);
+        // histogram.py:58-66, :13-17 — log of the ratio: one rounding instead of two at magnitude 13.8
+        const float x0 = fmaf(r, 0.5f, 0.5f), x1 = fmaf(g, 0.5f, 0.5f), x2 = fmaf(bl, 0.5f, 0.5f);
+        const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
+        const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
+        const float d_rg = logf(e0 / e1), d_rb = logf(e0 / e2), d_gb = logf(e1 / e2);
         mbar_wait(&S.px_empty[slot], ((it / PR) & 1) ^ 1);
         PxSlot& o = S.px[slot];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float u, ul, v, vl;
-          channel_uv(t, c, u, ul, v, vl);
-          o.u_hi[c][lane] = u; o.u_lo[c][lane] = ul; o.v_hi[c][lane] = v; o.v_lo[c][lane] = vl;
-        }
-        o.iy[lane] = valid ? t.iy : 0.f;  // masked pixels contribute nothing (A operand = 0)
+        // (u,v): R:(rg, rb)  G:(-rg, gb)  B:(-rb, -gb)   (histogram.py:72-74)
+        o.u[0][lane] = d_rg;  o.v[0][lane] = d_rb;
+        o.u[1][lane] = -d_rg; o.v[1][lane] = d_gb;
+        o.u[2][lane] = -d_rb; o.v[2][lane] = -d_gb;
+        o.iy[lane] = valid ? iy : 0.f;  // masked pixels contribute nothing (A operand = 0)
         mbar_arrive(&S.px_full[slot]);
       }
     }
   } else if (warp < A_WARPS) {
-    // ===================== A operand (TMEM) + epilogue =====================
-    const int quad = warp & 3;                  // TMEM sub-partition of this warp
-    const int sub = warp >> 2;                  // which 16 of the 32 pixels of a stage
-    const int half = lane >> 4;                 // 0: hi rows, 1: lo rows
-    const int bin = quad * 16 + (lane & 15);
-    const float c_bin = S.dom[bin];
-    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int px_own = sub * 16 + half * 8;     // the 8 pixels this thread evaluates
-    uint32_t it = 0, item_idx = 0;
-    for (int64_t w = first; w < p.items; w += step, ++item_idx) {
-      const int64_t b = w / p.splits, split = w % p.splits;
-      const int64_t px0 = split * p.px_per_split;
-      const int64_t px1 = min(px0 + p.px_per_split, p.npix);
-      for (int64_t base = px0; base < px1; base += KB, ++it) {
-        const int slot = it % PR, stage = it % NS;
-        mbar_wait(&S.px_full[slot], (it / PR) & 1);
-        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
-        tc_fence_after_sync();
-        const PxSlot& in = S.px[slot];
-#pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-          uint32_t out[16];
-#pragma unroll
-          for (int i4 = 0; i4 < 2; ++i4) {
-            const float4 uh = *reinterpret_cast<const float4*>(&in.u_hi[c][px_own + i4 * 4]);
-            const float4 ul = *reinterpret_cast<const float4*>(&in.u_lo[c][px_own + i4 * 4]);
-            const float4 iy = *reinterpret_cast<const float4*>(&in.iy[px_own + i4 * 4]);
-            const float wv[4] = {iy.x * weight<METHOD>((uh.x - c_bin) + ul.x, p.inv_sigma_sqr),
-                                 iy.y * weight<METHOD>((uh.y - c_bin) + ul.y, p.inv_sigma_sqr),
-                                 iy.z * weight<METHOD>((uh.z - c_bin) + ul.z, p.inv_sigma_sqr),
-                                 iy.w * weight<METHOD>((uh.w - c_bin) + ul.w, p.inv_sigma_sqr)};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // split once, keep the part this row needs, send the other part to the partner row
-              const uint32_t hi = tf32_hi(wv[e]);
-              const uint32_t lo = __float_as_uint(wv[e] - __uint_as_float(hi));
-              const uint32_t keep = half ? lo : hi;
-              const uint32_t recv = __shfl_xor_sync(0xffffffffu, half ? hi : lo, 16);
-              const int i = i4 * 4 + e;
-              out[i] = half ? recv : keep;      // pixels sub*16 + 0..7  (evaluated by the hi half-warp)
-              out[8 + i] = half ? keep : recv;  // pixels sub*16 + 8..15 (evaluated by the lo half-warp)
-            }
-          }
-          tmem_st16(tmem + lane_addr + A_COL0 + stage * A_STAGE_COLS + c * KB + sub * 16, out);
-        }
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive(&S.px_empty[slot]);
-        mbar_arrive(&S.ab_full[stage]);
-      }
-      // ---- epilogue: D (TMEM) -> partial histogram of this work item; warps w / w+4 take 32 columns each ----
-      mbar_wait(&S.d_full, item_idx & 1);
-      tc_fence_after_sync();
-      float* dst = p.partial + ((b * p.splits + split) * 3) * (int64_t)(BINS * BINS);
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float mine = __uint_as_float(v[i]);
-          f[i] = mine + __shfl_xor_sync(0xffffffffu, mine, 16);  // hi-row sum + lo-row sum
-        }
-        if (half == 0) {
-          float4* row = reinterpret_cast<float4*>(dst + (int64_t)c * BINS * BINS + bin * BINS + sub * 32);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) row[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        }
-      }
-      tc_fence_before_sync();
-      mbar_arrive(&S.d_empty);
-    }
+    if (((warp & 3) >> 1) == 0) a_warp_loop<METHOD, 0>(S, p, tmem, tid, warp, lane, first, step, inv2, one2, mone2);
+    else a_warp_loop<METHOD, 1>(S, p, tmem, tid, warp, lane, first, step, inv2, one2, mone2);
   } else if (warp < MMA_WARP) {
     // ===================== B operand (shared memory) =====================
     const int t = tid - A_WARPS * 32;
     const int j = t & 63, part = t >> 6;  // part: which 8 of the 32 pixels (two 4-pixel quads)
     const float c_bin = S.dom[j];
+    const f32x2 negc = pack2(-c_bin, -c_bin);
     const uint32_t row_off = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);  // hi row j; lo row j + 64 is +1024
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
@@ -223,23 +314,19 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
         mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
         const PxSlot& in = S.px[slot];
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
           unsigned char* tile = &S.b[stage][c * B_CH_BYTES];
 #pragma unroll
           for (int q4 = 0; q4 < 2; ++q4) {
             const int kq = part * 2 + q4;
-            const float4 vh = *reinterpret_cast<const float4*>(&in.v_hi[c][kq * 4]);
-            const float4 vl = *reinterpret_cast<const float4*>(&in.v_lo[c][kq * 4]);
-            const float w0 = weight<METHOD>((vh.x - c_bin) + vl.x, p.inv_sigma_sqr);
-            const float w1 = weight<METHOD>((vh.y - c_bin) + vl.y, p.inv_sigma_sqr);
-            const float w2 = weight<METHOD>((vh.z - c_bin) + vl.z, p.inv_sigma_sqr);
-            const float w3 = weight<METHOD>((vh.w - c_bin) + vl.w, p.inv_sigma_sqr);
-            uint4 hi, lo;
-            hi.x = tf32_hi(w0); hi.y = tf32_hi(w1); hi.z = tf32_hi(w2); hi.w = tf32_hi(w3);
-            lo.x = tf32_lo(w0); lo.y = tf32_lo(w1); lo.z = tf32_lo(w2); lo.w = tf32_lo(w3);
-            *reinterpret_cast<uint4*>(tile + kq * B_KQ_BYTES + row_off) = hi;
-            *reinterpret_cast<uint4*>(tile + kq * B_KQ_BYTES + row_off + 1024) = lo;
+            const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(&in.v[c][kq * 4]);
+            const f32x2 w0 = weight2<METHOD>(vv.x, negc, inv2, one2);
+            const f32x2 w1 = weight2<METHOD>(vv.y, negc, inv2, one2);
+            const f32x2 h0 = w0 & TF32_MASK2, h1 = w1 & TF32_MASK2;
+            const f32x2 l0 = fma2(h0, mone2, w0), l1 = fma2(h1, mone2, w1);
+            *reinterpret_cast<ulonglong2*>(tile + kq * B_KQ_BYTES + row_off) = make_ulonglong2(h0, h1);
+            *reinterpret_cast<ulonglong2*>(tile + kq * B_KQ_BYTES + row_off + 1024) = make_ulonglong2(l0, l1);
           }
         }
         fence_proxy_async_smem();
@@ -247,41 +334,50 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         mbar_arrive(&S.ab_full[stage]);
       }
     }
-  } else if (warp == MMA_WARP && lane == 0) {
-    // ===================== MMA issue =====================
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issue: the whole warp runs the (uniform) loop, one elected lane issues ====
     constexpr uint32_t IDESC = idesc_tf32(128, 64);
-    const uint32_t b_base = smem_u32(&S.b[0][0]);
-    uint32_t it = 0, item_idx = 0;
-    for (int64_t w = first; w < p.items; w += step, ++item_idx) {
+    const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(&S.b[0][0]), B_KQ_BYTES, 128);
+    const uint32_t dlo0 = (uint32_t)desc0, dhi = (uint32_t)(desc0 >> 32);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);  // provably uniform copy
+    uint32_t it = 0, chain = 0;
+    for (int64_t w = first; w < p.items; w += step) {
       const int64_t split = w % p.splits;
       const int64_t px0 = split * p.px_per_split;
       const int64_t px1 = min(px0 + p.px_per_split, p.npix);
-      if (item_idx > 0) {
-        mbar_wait(&S.d_empty, (item_idx - 1) & 1);
-        tc_fence_after_sync();
-      }
-      bool first_kb = true;
-      for (int64_t base = px0; base < px1; base += KB, ++it) {
-        const int stage = it % NS;
+      const int64_t nkb = (px1 - px0 + KB - 1) / KB;
+      for (int64_t kb = 0; kb < nkb; ++kb, ++it) {
+        const bool chain_start = (kb % CHAIN_KB) == 0;
+        if (chain_start && chain > 0) {
+          mbar_wait(&S.d_empty, (chain - 1) & 1);
+          tc_fence_after_sync();
+        }
+        const uint32_t stage = it % NS;
         mbar_wait(&S.ab_full[stage], (it / NS) & 1);
         tc_fence_after_sync();
+        // the start-address field (bits 0-13, units of 16 B) never carries into the next field
+        const uint32_t dstage = dlo0 + ((stage * B_STAGE_BYTES) >> 4);
+        const uint32_t a_stage = tm + A_COL0 + stage * A_STAGE_COLS;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const uint32_t d_addr = tmem + c * D_COLS;
-          const uint32_t a_addr = tmem + A_COL0 + stage * A_STAGE_COLS + c * KB;
-          const uint32_t b_addr = b_base + stage * B_STAGE_BYTES + c * B_CH_BYTES;
 #pragma unroll
           for (int ks = 0; ks < KB / 8; ++ks) {
-            const uint64_t desc_hi = smem_desc_kmajor_noswizzle(b_addr + ks * 2 * B_KQ_BYTES, B_KQ_BYTES, 128);
-            const uint64_t desc_lo = smem_desc_kmajor_noswizzle(b_addr + ks * 2 * B_KQ_BYTES + 1024, B_KQ_BYTES, 128);
-            mma_tf32_ts(d_addr, a_addr + ks * 8, desc_hi, IDESC, (first_kb && ks == 0) ? 0u : 1u);
-            mma_tf32_ts(d_addr, a_addr + ks * 8, desc_lo, IDESC, 1u);
+            const uint32_t b_hi = dstage + ((c * B_CH_BYTES + ks * 2 * B_KQ_BYTES) >> 4);
+            const uint32_t b_lo = b_hi + (1024 >> 4);
+            const uint32_t acc0 = (chain_start && ks == 0) ? 0u : 1u;
+            if (elect_one_sync()) {
+              mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_hi, dhi, IDESC, acc0);
+              mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_lo, dhi, IDESC, 1u);
+            }
           }
         }
-        mma_commit(&S.ab_empty[stage]);
-        first_kb = false;
+        const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
+        if (elect_one_sync()) {
+          mma_commit(&S.ab_empty[stage]);
+          if (chain_end) mma_commit(&S.d_full);
+        }
+        if (chain_end) ++chain;
       }
-      mma_commit(&S.d_full);
     }
   }
 
@@ -300,26 +396,22 @@ bool tc_supported(int64_t npix, int bins, int method) {
   return bins == 64 && npix >= 1;
 }
 
-// Pixel slices per image.  Two constraints: enough work items to fill the SMs, and at most
-// MAX_CHAIN_PX pixels accumulated in one TMEM accumulator: the tensor core adds each K=8 product
-// block into the fp32 accumulator with truncation, so the error grows with the number of chained
-// MMAs (measured: 4096 px in one chain -> 8e-6 relative, 1024 px -> ~1e-6); slices are summed in
-// fp32 by the finalise kernel.
-constexpr int64_t MAX_CHAIN_PX = 1024;
+// Pixel slices per image: 1 (whole image per CTA, normalisation fused) once the batch fills the SMs,
+// otherwise enough slices to occupy them; the slices are summed by the finalise kernel.
 static int tc_fwd_splits(int64_t batch, int64_t npix) {
-  const int64_t target = (int64_t)cached_sm_count() * 2;
-  int64_t s = ceil_div(target, batch);
+  const int64_t sms = cached_sm_count();
+  if (batch >= sms) return 1;
+  int64_t s = ceil_div(2 * sms, batch);
   const int64_t max_s = ceil_div(npix, 8 * fwdtc::KB);
   if (s > max_s) s = max_s;
-  const int64_t min_s = ceil_div(npix, MAX_CHAIN_PX);
-  if (s < min_s) s = min_s;
   if (s < 1) s = 1;
   return (int)s;
 }
 
 size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins) {
   if (bins != 64) return 0;
-  const size_t fwd = (size_t)batch * tc_fwd_splits(batch, npix) * 3 * bins * bins * sizeof(float);
+  const int splits = tc_fwd_splits(batch, npix);
+  const size_t fwd = splits > 1 ? (size_t)batch * splits * 3 * bins * bins * sizeof(float) : 0;
   const size_t bwd = (size_t)batch * 3 * bins * bins * sizeof(float);
   return align_up(fwd > bwd ? fwd : bwd, 256) + 256;
 }
@@ -337,6 +429,8 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.image = image;
   p.dom = dom;
   p.partial = static_cast<float*>(workspace);
+  p.hist = hist;
+  p.denom = denom;
   p.npix = npix;
   p.channels = channels;
   p.splits = tc_fwd_splits(batch, npix);
@@ -357,8 +451,10 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     hist_fwd_tc_kernel<PH_METHOD_RBF><<<grid, THREADS, smem, st>>>(p);
   }
   PH_LAUNCH_OK("hist_fwd_tc_kernel");
-  launch_finalize(p.partial, p.splits, 3, bins, 1, hist, denom, batch, st);
-  PH_LAUNCH_OK("hist_finalize_kernel");
+  if (p.splits > 1) {
+    launch_finalize(p.partial, p.splits, 3, bins, 1, hist, denom, batch, st);
+    PH_LAUNCH_OK("hist_finalize_kernel");
+  }
   return PH_OK;
 }
 
