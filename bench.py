@@ -153,6 +153,7 @@ def cpu_hist_images_per_s(sample_batch, repeats, seed=47):
     import torch
     from oracle import torch_port as tp
 
+    torch.set_num_threads(os.cpu_count() or 1)
     real, fake = make_hist_inputs(sample_batch, seed)
     real_t, fake_t = torch.from_numpy(real), torch.from_numpy(fake)
     tp.hist_loss_fwd_bwd(real_t[:4], fake_t[:4], BINS)  # warm-up (thread pool, allocator)
@@ -183,6 +184,7 @@ def run_reference(args, rank):
         return
     import torch
 
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; use every host core
     sample = 32
     real, fake = make_hist_inputs(sample, 47)
     real_t, fake_t = torch.from_numpy(real), torch.from_numpy(fake)
@@ -207,7 +209,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -272,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
     ms = timed(step, args.steps)
     t1 = time.time()
     launches = _lib.launch_count()
-    loss_val = float(step())
+    loss_val = float(step().detach())
     value = GLOBAL_BATCH * args.steps / (ms / 1e3)
 
     # ---- per-phase breakdown (same kernels, CUDA events between phases on the launching stream) ----
@@ -380,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -458,7 +460,25 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
     }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Exactly one JSON line on the process's real stdout (everything else went to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL prints its version banner) write to fd 1: keep stdout clean for the one JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
