@@ -3,8 +3,8 @@
 // (w = hi + lo, both tf32; hi.hi + hi.lo + lo.hi + lo.lo accumulated in fp32 in TMEM), fused with the
 // per-image normalisation (histogram.py:75-79).
 //
-// Forward, 64 bins, one persistent CTA per SM, 21 warps:
-//   warps 17-20 pixel pass: 128-bit RGBA loads, log-chroma u/v per channel and intensity Iy -> smem ring
+// Forward, 64 bins, one persistent CTA per SM, 20 warps:
+//   warps 17-19 pixel pass: 128-bit RGBA loads, log-chroma u/v per channel and intensity Iy -> smem ring
 //   warps 0-7   A operand (u side, Iy-weighted) written straight into TMEM, M = 128 rows =
 //               64 bins x {hi, lo}: TMEM sub-partitions 0,1 hold the hi rows of bins 0-31 / 32-63,
 //               sub-partitions 2,3 the lo rows, so a warp's role is uniform.  The hi warp and the lo
@@ -34,7 +34,7 @@ constexpr int BINS = 64;
 constexpr int KB = 32;         // pixels per pipeline stage
 constexpr int NS = 3;          // A/B operand stages
 constexpr int CHAIN_KB = 32;   // stages per TMEM accumulation chain (1024 pixels)
-constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 4;
+constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 3;  // 20 warps: 640 threads leave 96 registers per thread
 constexpr int MMA_WARP = A_WARPS + B_WARPS;     // 16
 constexpr int PX_WARP0 = MMA_WARP + 1;          // 17
 constexpr int PR = 6;                           // pixel ring slots
@@ -120,8 +120,6 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
       for (int64_t kb = 0; kb < nkb; ++kb, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
-        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
-        tc_fence_after_sync();
         const PxSlot& in = S.px[slot];
         // all three channels at once: 24 weights per thread in flight, one hand-over with the partner warp
         // (barrier 1: partner has consumed the previous stage's hand-over; barrier 2: this stage's is written)
@@ -131,10 +129,16 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
         const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(&S.xbuf[pair][role ^ 1][0][0][lane]);
         const ulonglong2 ia = *reinterpret_cast<const ulonglong2*>(&in.iy[px_own]);
         const ulonglong2 ib = *reinterpret_cast<const ulonglong2*>(&in.iy[px_own + 4]);
+        ulonglong2 uu[3][2];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const ulonglong2 ua = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own]);
-          const ulonglong2 ub = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own + 4]);
+          uu[c][0] = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own]);
+          uu[c][1] = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own + 4]);
+        }
+        mbar_arrive(&S.px_empty[slot]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const ulonglong2 ua = uu[c][0], ub = uu[c][1];
           const f32x2 w0 = mul2(weight2<METHOD>(ua.x, negc, inv2, one2), ia.x);
           const f32x2 w1 = mul2(weight2<METHOD>(ua.y, negc, inv2, one2), ia.y);
           const f32x2 w2 = mul2(weight2<METHOD>(ub.x, negc, inv2, one2), ib.x);
@@ -152,6 +156,8 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
           }
         }
         named_bar_sync(1 + pair, 64);
+        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this TMEM stage are done
+        tc_fence_after_sync();
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const ulonglong2 ra = xr[c * 64], rb = xr[c * 64 + 32];
@@ -171,7 +177,6 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
         }
         tmem_st_wait();
         tc_fence_before_sync();
-        mbar_arrive(&S.px_empty[slot]);
         mbar_arrive(&S.ab_full[stage]);
 
         const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
@@ -312,17 +317,23 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
       for (int64_t base = px0; base < px1; base += KB, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
-        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
         const PxSlot& in = S.px[slot];
+        // all loads first (the compiler cannot hoist them across the shared-memory stores below)
+        ulonglong2 vv[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int q4 = 0; q4 < 2; ++q4) vv[c][q4] = *reinterpret_cast<const ulonglong2*>(&in.v[c][(part * 2 + q4) * 4]);
+        mbar_arrive(&S.px_empty[slot]);
+        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           unsigned char* tile = &S.b[stage][c * B_CH_BYTES];
 #pragma unroll
           for (int q4 = 0; q4 < 2; ++q4) {
             const int kq = part * 2 + q4;
-            const ulonglong2 vv = *reinterpret_cast<const ulonglong2*>(&in.v[c][kq * 4]);
-            const f32x2 w0 = weight2<METHOD>(vv.x, negc, inv2, one2);
-            const f32x2 w1 = weight2<METHOD>(vv.y, negc, inv2, one2);
+            const f32x2 w0 = weight2<METHOD>(vv[c][q4].x, negc, inv2, one2);
+            const f32x2 w1 = weight2<METHOD>(vv[c][q4].y, negc, inv2, one2);
             const f32x2 h0 = w0 & TF32_MASK2, h1 = w1 & TF32_MASK2;
             const f32x2 l0 = fma2(h0, mone2, w0), l1 = fma2(h1, mone2, w1);
             *reinterpret_cast<ulonglong2*>(tile + kq * B_KQ_BYTES + row_off) = make_ulonglong2(h0, h1);
@@ -330,7 +341,6 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&S.px_empty[slot]);
         mbar_arrive(&S.ab_full[stage]);
       }
     }
