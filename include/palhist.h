@@ -183,12 +183,14 @@ PH_API int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const flo
 
 /* The same in two phases for a batch sharded over processes: `begin` uploads, runs both forward
  * passes and returns this shard's sum of squares (host double); the caller all-reduces it; `finish`
- * takes the whole-batch sum and batch size, returns the loss and this shard's gradient. */
+ * takes the whole-batch sum and batch size, returns the loss (host float) and this shard's gradient:
+ * downloaded into grad_fake_host and/or left in the caller's DEVICE buffer grad_fake_device (either
+ * may be NULL; the usual consumer, the generator's backward pass, lives on the device). */
 PH_API int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
                        int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
                        float sigma_sqr, float epsilon, int impl, double* ssum_local_host);
 PH_API int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
-                        float* grad_fake_host);
+                        float* grad_fake_host, float* grad_fake_device);
 
 /* dataset_utils.py:138-151 for host images (+ optional one-hot of the target indices). */
 PH_API int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,

@@ -254,12 +254,9 @@ int ph_load_indexed_images(const int32_t* source, const int32_t* target, int64_t
   PH_CHECK_ARG((reinterpret_cast<uintptr_t>(source) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(palette) & 15) == 0,
                "source / target / palette must be 16-byte aligned");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = launch_extract_palette(source, target, batch, 2 * npix, ordering, palette, ncolors, st);
-  if (rc != PH_OK) return rc;
-  rc = ph_rgba_to_indexed(source, batch, npix, palette, batch, PH_INDEX_EXACT_SUM, source_indexed, nullptr, 0, stream);
-  if (rc != PH_OK) return rc;
-  return ph_rgba_to_indexed(target, batch, npix, palette, batch, PH_INDEX_EXACT_SUM, target_indexed, nullptr, 0, stream);
+  // one launch: the palette is extracted and both images are indexed from the same CTA-resident table
+  return launch_load_indexed_fused(source, target, batch, npix, ordering, source_indexed, target_indexed, palette,
+                                   ncolors, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

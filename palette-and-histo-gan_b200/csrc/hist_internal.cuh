@@ -48,6 +48,9 @@ int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channe
 // ---- palette.cu -------------------------------------------------------------------------------
 int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows,
                            int ordering, int32_t* palette, int32_t* ncolors, cudaStream_t st);
+int launch_load_indexed_fused(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
+                              int ordering, int32_t* source_indexed, int32_t* target_indexed, int32_t* palette,
+                              int32_t* ncolors, cudaStream_t st);
 int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,
                            int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
                            cudaStream_t st);

@@ -121,7 +121,9 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
   if (ceil_div(batch, chunk) > ph_host_ctx::kMaxChunks) chunk = ceil_div(batch, ph_host_ctx::kMaxChunks);
   const int nchunks = (int)ceil_div(batch, chunk);
   const size_t hist_elems = (size_t)bins * bins * 3;
-  const size_t ws_bytes = ph_hist_workspace_bytes(chunk, npix, bins, impl);
+  size_t ws_bytes = ph_hist_workspace_bytes(chunk, npix, bins, impl);
+  const size_t ws_full = ph_hist_workspace_bytes(batch, npix, bins, impl);  // whole-batch backward (device gradient)
+  if (ws_full > ws_bytes) ws_bytes = ws_full;
 
   ph_host_ctx::Job& J = ctx->job;
   for (int pass = 0; pass < 2; ++pass) {
@@ -182,7 +184,7 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
 }
 
 int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
-                        float* grad_fake_host) {
+                        float* grad_fake_host, float* grad_fake_device) {
   PH_CHECK_ARG(ctx && loss_host, "NULL pointer argument");
   PH_CHECK_ARG(ctx->job_valid, "ph_host_hist_finish without a preceding successful ph_host_hist_begin");
   PH_CHECK_ARG(global_batch > 0, "global_batch must be positive");
@@ -194,7 +196,14 @@ int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_bat
   int rc = ph_hellinger_finish(J.d_ssum, global_batch, J.d_loss, ctx->s_compute);
   if (rc != PH_OK) return rc;
   PH_CUDA_OK(cudaMemcpyAsync(loss_host, J.d_loss, sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
-  // ---- phase B: backward + download, chunk by chunk ----
+  // ---- phase B: backward; the gradient either stays on the device (the consumer — the generator's
+  //      backward — lives there) or is downloaded chunk by chunk, overlapped with the kernels ----
+  if (grad_fake_device) {
+    rc = ph_hist_backward(J.d_fake, J.batch, J.npix, J.channels, J.d_dom, J.bins, J.method, J.sigma_sqr, J.epsilon,
+                          J.d_hfake, J.d_denom_f, nullptr, J.d_hreal, J.d_ssum, global_batch, nullptr, grad_fake_device,
+                          J.d_ws, J.ws_bytes, J.impl, ctx->s_compute);
+    if (rc != PH_OK) return rc;
+  }
   if (grad_fake_host) {
     for (int k = 0; k < J.nchunks; ++k) {
       const int64_t b0 = (int64_t)k * J.chunk;
@@ -226,7 +235,7 @@ int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const float* fak
   int rc = ph_host_hist_begin(ctx, real_host, fake_host, batch, npix, channels, bin_centers_host, bins, method,
                               sigma_sqr, epsilon, impl, &ssum);
   if (rc != PH_OK) return rc;
-  return ph_host_hist_finish(ctx, ssum, batch, loss_host, grad_fake_host);
+  return ph_host_hist_finish(ctx, ssum, batch, loss_host, grad_fake_host, nullptr);
 }
 
 int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,

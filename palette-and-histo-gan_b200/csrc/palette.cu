@@ -41,9 +41,13 @@ constexpr int PAL_HASH_BITS = 11;
 constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;
 constexpr int PAL_MAX = PH_MAX_PALETTE_SIZE;
 
+// FUSED_INDEX: also index both images of the pair from the same CTA-resident table
+// (dataset_utils.py:148-149 in the same launch): after the colours are ranked, each table slot is
+// rewritten to (key, final palette index) and every pixel is looked up with one probe.
+template <bool FUSED_INDEX>
 __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
     const int4* __restrict__ image, const int4* __restrict__ image2, int64_t rows, int ordering,
-    int4* __restrict__ palette, int* __restrict__ ncolors) {
+    int4* __restrict__ palette, int* __restrict__ ncolors, int* __restrict__ indexed, int* __restrict__ indexed2) {
   __shared__ unsigned long long table[PAL_HASH_SIZE];
   __shared__ unsigned long long entries[PAL_MAX];
   __shared__ unsigned first_order[PAL_MAX];  // keys in first-occurrence order
@@ -105,6 +109,9 @@ __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
     if (tid == 0) ncolors[b] = s_bad ? PH_PALETTE_BAD_VALUE : count;
     const int4 filler = make_int4(255, 0, 220, 255);
     for (int k = tid; k < PAL_MAX; k += PAL_THREADS) palette[b * PAL_MAX + k] = filler;
+    if (FUSED_INDEX) {  // the host raises for this image; keep the outputs defined
+      for (int64_t r = tid; r < per_image; r += PAL_THREADS) { indexed[b * per_image + r] = 0; indexed2[b * per_image + r] = 0; }
+    }
     return;
   }
 
@@ -151,6 +158,40 @@ __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
   }
   for (int k = n + tid; k < PAL_MAX; k += PAL_THREADS) out[k] = filler;
   if (tid == 0) ncolors[b] = n;
+
+  if (FUSED_INDEX) {
+    // final index of each colour -> its table slot (low word); first_order[] is reused as scratch
+    __syncthreads();
+    if (tid < n) {
+      int final_rank = tid;
+      if (ordering == PH_ORDER_GRAYNESS && n > 1) {
+        const float mine = gray[tid];
+        final_rank = 0;
+        for (int e = 0; e < n; ++e) {
+          const float other = gray[e];
+          final_rank += (other < mine || (other == mine && e < tid)) ? 1 : 0;
+        }
+      }
+      const unsigned key = first_order[tid];
+      unsigned h = hash_slot<PAL_HASH_BITS>(key);
+      while ((unsigned)(table[h] >> 32) != key || table[h] == SLOT_EMPTY) h = (h + 1) & (PAL_HASH_SIZE - 1);
+      table[h] = ((unsigned long long)key << 32) | (unsigned)final_rank;
+    }
+    __syncthreads();
+    // a pixel equal to the filler colour also matches every padding row: scatter_nd adds them (io_utils.py:84-91)
+    const unsigned filler_key = pack_rgba(filler);
+    const int filler_extra = (PAL_MAX * (PAL_MAX - 1) - n * (n - 1)) / 2;  // sum of n..255
+    for (int64_t r = tid; r < rows; r += PAL_THREADS) {
+      const int4 c = __ldg(((r & 1) ? src1 : src0) + (r >> 1));
+      const unsigned key = pack_rgba(c);
+      unsigned h = hash_slot<PAL_HASH_BITS>(key);
+      unsigned long long w = table[h];
+      while ((unsigned)(w >> 32) != key || w == SLOT_EMPTY) { h = (h + 1) & (PAL_HASH_SIZE - 1); w = table[h]; }
+      int idx = (int)(unsigned)w;
+      if (key == filler_key) idx += filler_extra;
+      ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = idx;
+    }
+  }
 }
 
 // =============================================================================================
@@ -315,10 +356,24 @@ int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t 
   PH_CHECK_ARG(batch < (1ll << 31), "batch too large");
   PH_CHECK_ARG(rows < (1ll << 31), "too many rows per image (%lld)", (long long)rows);
   if (batch == 0) return PH_OK;
-  extract_palette_kernel<<<(unsigned)batch, PAL_THREADS, 0, st>>>(
+  extract_palette_kernel<false><<<(unsigned)batch, PAL_THREADS, 0, st>>>(
       reinterpret_cast<const int4*>(image), reinterpret_cast<const int4*>(image2), rows, ordering,
-      reinterpret_cast<int4*>(palette), ncolors);
+      reinterpret_cast<int4*>(palette), ncolors, nullptr, nullptr);
   PH_LAUNCH_OK("extract_palette_kernel");
+  return PH_OK;
+}
+
+// dataset_utils.py:138-151 in ONE launch: shared palette of source||target and both index images.
+int launch_load_indexed_fused(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
+                              int ordering, int32_t* source_indexed, int32_t* target_indexed, int32_t* palette,
+                              int32_t* ncolors, cudaStream_t st) {
+  PH_CHECK_ARG(batch < (1ll << 31), "batch too large");
+  PH_CHECK_ARG(2 * npix < (1ll << 31), "too many pixels per image (%lld)", (long long)npix);
+  if (batch == 0) return PH_OK;
+  extract_palette_kernel<true><<<(unsigned)batch, PAL_THREADS, 0, st>>>(
+      reinterpret_cast<const int4*>(source), reinterpret_cast<const int4*>(target), 2 * npix, ordering,
+      reinterpret_cast<int4*>(palette), ncolors, source_indexed, target_indexed);
+  PH_LAUNCH_OK("extract_palette_kernel<fused index>");
   return PH_OK;
 }
 

@@ -97,14 +97,22 @@ def histogram_loss_begin(real_image, fake_image, size=64, method="inverse-quadra
     return float(ssum.value)
 
 
-def histogram_loss_finish(ssum_global: float, global_batch: int, out_grad, *, ctx=None, device=0):
-    """Phase 2: loss of the whole batch and the gradient of this shard into `out_grad` (host float32
-    array shaped like the shard's fake images, or None)."""
+def histogram_loss_finish(ssum_global: float, global_batch: int, out_grad=None, *, out_grad_device=None, ctx=None,
+                          device=0):
+    """Phase 2: loss of the whole batch and the gradient of this shard, downloaded into `out_grad` (host
+    float32 array shaped like the shard's fake images) and/or left in `out_grad_device` (a CUDA float32
+    tensor of that shape: the generator's backward consumes it on the device)."""
     loss = np.zeros((1,), np.float32)
     grad = _np(out_grad, np.float32, "out_grad") if out_grad is not None else None
+    dptr = None
+    if out_grad_device is not None:
+        if not (out_grad_device.is_cuda and out_grad_device.is_contiguous() and out_grad_device.dtype.is_floating_point
+                and out_grad_device.element_size() == 4):
+            raise ValueError("out_grad_device must be a contiguous float32 CUDA tensor")
+        dptr = out_grad_device.data_ptr()
     ctx = ctx or default_context(device)
     _lib.call("ph_host_hist_finish", ctx._h, float(ssum_global), int(global_batch), loss.ctypes.data,
-              grad.ctypes.data if grad is not None else None)
+              grad.ctypes.data if grad is not None else None, dptr)
     return float(loss[0]), grad
 
 

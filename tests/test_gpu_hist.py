@@ -186,3 +186,30 @@ def test_simt_and_auto_engines_agree(H, cuda):
     a = H.calculate_rgbuv_histogram(img, impl="simt").cpu().numpy()
     b = H.calculate_rgbuv_histogram(img, impl="auto").cpu().numpy()
     assert ho.rel_l2(a, b) < 5e-6
+
+
+def test_host_buffer_api(cuda):
+    """ph_host_hist_loss / begin+finish: numpy in, loss + gradient out (host and device-resident forms)."""
+    from palette_and_histo_gan_b200 import hostapi
+
+    rng = np.random.default_rng(12)
+    real = np.tanh(rng.standard_normal((6, 32, 32, 4))).astype(np.float32)
+    fake = np.tanh(rng.standard_normal((6, 32, 32, 4))).astype(np.float32)
+    ref = ho.hist_loss_and_grad_f64(real, fake)
+    loss, grad = hostapi.histogram_loss(real, fake)
+    assert abs(loss - ref["loss"]) / ref["loss"] < LOSS_TOL
+    assert ho.rel_l2(grad, ref["grad"]) < GRAD_TOL
+    # two-phase form, as two "ranks" would use it, gradient left on the device
+    ctx = hostapi.HostContext(0)
+    ssums = []
+    for lo in (0, 3):
+        ssums.append(hostapi.histogram_loss_begin(real[lo:lo + 3], fake[lo:lo + 3], ctx=ctx))
+    total = sum(ssums)
+    assert abs(total - ref["ssum"]) / ref["ssum"] < 1e-5
+    for lo in (0, 3):
+        hostapi.histogram_loss_begin(real[lo:lo + 3], fake[lo:lo + 3], ctx=ctx)
+        gd = torch.empty((3, 32, 32, 4), dtype=torch.float32, device=cuda)
+        l2, _ = hostapi.histogram_loss_finish(total, 6, None, out_grad_device=gd, ctx=ctx)
+        assert abs(l2 - ref["loss"]) / ref["loss"] < LOSS_TOL
+        assert ho.rel_l2(gd.cpu().numpy(), ref["grad"][lo:lo + 3]) < GRAD_TOL
+    ctx.close()

@@ -169,3 +169,21 @@ def test_host_api_matches_device_api(P, cuda, sprites):
         es, et, ep = po.load_indexed_images(s[i], t[i], "grayness")
         assert np.array_equal(hs[i], es) and np.array_equal(ht[i], et) and np.array_equal(hp[i], ep)
         assert np.array_equal(oh[i], po.one_hot(et))
+
+
+def test_fused_loader_filler_colour_and_batching(P, cuda):
+    """The one-launch loader (dataset_utils.py:138-151) must keep the scatter-add semantics: a pixel equal
+    to INVALID_INDEX_COLOR also matches every padding row (io_utils.py:84-91)."""
+    rng = np.random.default_rng(8)
+    cols = np.array([[0, 0, 0, 0], [255, 0, 220, 255], [10, 20, 30, 255], [255, 255, 255, 255], [9, 9, 9, 9]], np.int32)
+    src = cols[rng.integers(0, 5, size=(3, 16, 16))]
+    tgt = cols[rng.integers(0, 4, size=(3, 16, 16))]
+    for ordering in ("grayness", "top2bottom", "bottom2top"):
+        s_idx, t_idx, pal = P.dataset_utils.load_indexed_images(dev_i32(src, cuda), dev_i32(tgt, cuda), ordering)
+        for i in range(3):
+            es, et, ep = po.load_indexed_images(src[i], tgt[i], ordering)
+            assert np.array_equal(pal[i].cpu().numpy(), ep), ordering
+            assert np.array_equal(s_idx[i].cpu().numpy(), es) and np.array_equal(t_idx[i].cpu().numpy(), et), ordering
+    # un-batched call keeps the reference shapes
+    s1, t1, p1 = P.dataset_utils.load_indexed_images(dev_i32(src[0], cuda), dev_i32(tgt[0], cuda), "grayness")
+    assert tuple(s1.shape) == (16, 16, 1) and tuple(p1.shape) == (256, 4)
