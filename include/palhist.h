@@ -61,6 +61,12 @@ enum ph_impl {
   PH_IMPL_AUTO = 0, /* tensor cores when the shape allows, else SIMT */
   PH_IMPL_SIMT = 1, /* fp32 CUDA-core contraction (any bin count) */
   PH_IMPL_TC = 2,   /* tcgen05 3xTF32 contraction, accumulators in TMEM */
+  PH_IMPL_ENGINE_MASK = 3,
+  /* flag, OR-ed into impl for ph_hist_forward: first reduce every image to its unique colours with
+   * multiplicities and contract those (exact: the histogram is a sum over pixels of a function of the
+   * colour).  Pays off for palette images such as the reference's real sprites (10-54 colours); an
+   * image with more than 512 colours is contracted densely.  Ignored by the CUDA-core engine. */
+  PH_IMPL_DEDUP = 8,
 };
 
 /* per-image status written by ph_extract_palette into ncolors[]: >=0 colour count (may exceed 256 =

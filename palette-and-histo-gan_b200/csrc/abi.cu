@@ -37,6 +37,7 @@ int cached_sm_count() {
 }
 
 static int resolve_impl(int impl, int64_t npix, int bins, int method) {
+  impl &= PH_IMPL_ENGINE_MASK;
   if (impl == PH_IMPL_AUTO) return tc_supported(npix, bins, method) ? PH_IMPL_TC : PH_IMPL_SIMT;
   return impl;
 }
@@ -78,7 +79,7 @@ int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
 size_t ph_hist_workspace_bytes(int64_t batch, int64_t npix, int bins, int impl) {
   if (batch <= 0 || npix <= 0 || bins <= 0) return 256;
   size_t s = simt_workspace_bytes(batch, npix, bins);
-  if (impl != PH_IMPL_SIMT) {
+  if ((impl & PH_IMPL_ENGINE_MASK) != PH_IMPL_SIMT) {
     const size_t t = tc_workspace_bytes(batch, npix, bins);
     if (t > s) s = t;
   }
@@ -92,7 +93,8 @@ int ph_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   int rc = check_hist_args(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr);
   if (rc != PH_OK) return rc;
   PH_CHECK_ARG(hist != nullptr && denom != nullptr, "hist / denom must not be NULL");
-  PH_CHECK_ARG(impl >= PH_IMPL_AUTO && impl <= PH_IMPL_TC, "bad impl %d", impl);
+  PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
+               "bad impl %d", impl);
   if (batch == 0) return PH_OK;
   const int eng = resolve_impl(impl, npix, bins, method);
   PH_CHECK_ARG(workspace != nullptr && workspace_bytes >= ph_hist_workspace_bytes(batch, npix, bins, eng),
@@ -104,7 +106,7 @@ int ph_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
       return PH_ERR_UNSUPPORTED;
     }
     return tc_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist,
-                           denom, workspace, st);
+                           denom, workspace, (impl & PH_IMPL_DEDUP) != 0, st);
   }
   return simt_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist,
                            denom, workspace, st);
@@ -137,7 +139,8 @@ int ph_hist_backward(const float* image, int64_t batch, int64_t npix, int channe
   PH_CHECK_ARG(hist_pred && denom_pred && grad_image, "hist_pred / denom_pred / grad_image must not be NULL");
   PH_CHECK_ARG(grad_hist != nullptr || (hist_true != nullptr && ssum != nullptr && global_batch > 0),
                "either grad_hist or (hist_true, ssum, global_batch>0) must be given");
-  PH_CHECK_ARG(impl >= PH_IMPL_AUTO && impl <= PH_IMPL_TC, "bad impl %d", impl);
+  PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
+               "bad impl %d", impl);
   PH_CHECK_ARG(channels != 4 || (reinterpret_cast<uintptr_t>(grad_image) & 15) == 0,
                "RGBA gradient pointer must be 16-byte aligned");
   if (batch == 0) return PH_OK;

@@ -38,7 +38,7 @@ bool tc_supported(int64_t npix, int bins, int method);
 size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins);
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                     int bins, int method, float sigma_sqr, float eps, float* hist, float* denom,
-                    void* workspace, cudaStream_t st);
+                    void* workspace, bool dedup, cudaStream_t st);
 int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                      int bins, int method, float sigma_sqr, float eps, const float* hist_pred,
                      const float* denom, const float* grad_hist, const float* hist_true,

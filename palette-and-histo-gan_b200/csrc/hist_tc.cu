@@ -38,6 +38,8 @@ constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 3;  // 20 warps: 640 threads leave
 constexpr int MMA_WARP = A_WARPS + B_WARPS;     // 16
 constexpr int PX_WARP0 = MMA_WARP + 1;          // 17
 constexpr int PR = 6;                           // pixel ring slots
+constexpr int DEDUP_MAX = 512;                  // unique colours kept per image by the de-duplication pass
+constexpr int DEDUP_SLOTS = 1024;
 constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 672
 constexpr int TMEM_COLS = 512;
 constexpr int D_COLS = 64;                 // per channel
@@ -69,6 +71,8 @@ struct Params {
   float* partial;  // (B, splits, 3, 64, 64) raw sums, used when splits > 1
   float* hist;     // (B, 64, 64, 3) normalised, written directly when splits == 1
   float* denom;    // (B)
+  const float4* ulist;  // optional (B, DEDUP_MAX): unique colours (r,g,b,count) of each image, or NULL
+  const int* nunique;   // optional (B): number of unique colours, < 0 = image not de-duplicated
   int64_t npix;
   int channels;
   int splits;
@@ -80,6 +84,21 @@ struct Params {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Pixel range of a work item.  A de-duplicated image is a list of (colour, multiplicity) entries: the
+// histogram is linear in the pixels, so identical pixels are contracted once with weight count*Iy.
+struct ItemRange { int64_t px0, px1; bool dedup; };
+__device__ __forceinline__ ItemRange item_range(const Params& p, int64_t b, int64_t split) {
+  ItemRange r;
+  if (p.nunique != nullptr) {
+    const int nu = __ldg(p.nunique + b);
+    if (nu >= 0) { r.px0 = 0; r.px1 = nu; r.dedup = true; return r; }
+  }
+  r.px0 = split * p.px_per_split;
+  r.px1 = min(r.px0 + p.px_per_split, p.npix);
+  r.dedup = false;
+  return r;
 }
 
 // two bin weights at once: d = x + (-c);  IQ: 1/(1 + d^2/s^2), RBF: exp(-d^2/s^2)
@@ -114,9 +133,8 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
     uint32_t it = 0, chain = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const int64_t b = w / p.splits, split = w % p.splits;
-      const int64_t px0 = split * p.px_per_split;
-      const int64_t px1 = min(px0 + p.px_per_split, p.npix);
-      const int64_t nkb = (px1 - px0 + KB - 1) / KB;
+      const ItemRange ir = item_range(p, b, split);
+      const int64_t nkb = (ir.px1 - ir.px0 + KB - 1) / KB;
       for (int64_t kb = 0; kb < nkb; ++kb, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
@@ -185,13 +203,34 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
         mbar_wait(&S.d_full, chain & 1);
         ++chain;
         tc_fence_after_sync();
+        // hi-row warps first (plain stores on the first chain of an item, else read-add-write), then the
+        // lo-row warps add their share: no shared-memory float atomics (those are CAS loops)
+        const bool first_chain = kb < CHAIN_KB;
+        if (role == 0) {
 #pragma unroll 1
-        for (int c = 0; c < 3; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
-          tmem_ld_wait();
+          for (int c = 0; c < 3; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
+            tmem_ld_wait();
+            if (first_chain) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(&S.acc[c][sub * 32 + i][bin], __uint_as_float(v[i]));
+              for (int i = 0; i < 32; ++i) S.acc[c][sub * 32 + i][bin] = __uint_as_float(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) S.acc[c][sub * 32 + i][bin] += __uint_as_float(v[i]);
+            }
+          }
+        }
+        named_bar_sync(5, A_WARPS * 32);
+        if (role == 1) {
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) S.acc[c][sub * 32 + i][bin] += __uint_as_float(v[i]);
+          }
         }
         tc_fence_before_sync();
         mbar_arrive(&S.d_empty);
@@ -215,17 +254,13 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
           float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
           for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
             const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-            float* a = &S.acc[c][j][i];
-            dst[e] = *a / d;
-            *a = 0.f;
+            dst[e] = S.acc[c][j][i] / d;
           }
         } else {
           float* dst = p.partial + ((b * p.splits + split) * 3) * (int64_t)(BINS * BINS);
           for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
             const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
-            float* a = &S.acc[c][j][i];
-            dst[e] = *a;
-            *a = 0.f;
+            dst[e] = S.acc[c][j][i];
           }
         }
         named_bar_sync(5, A_WARPS * 32);
@@ -249,7 +284,6 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     fence_mbar_init();
   }
   if (tid < BINS) S.dom[tid] = p.dom[tid];
-  for (int i = tid; i < 3 * BINS * BINS; i += THREADS) (&S.acc[0][0][0])[i] = 0.f;
   if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
@@ -267,15 +301,18 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const int64_t b = w / p.splits, split = w % p.splits;
-      const int64_t px0 = split * p.px_per_split;
-      const int64_t px1 = min(px0 + p.px_per_split, p.npix);
+      const ItemRange ir = item_range(p, b, split);
+      const int64_t px0 = ir.px0, px1 = ir.px1;
       for (int64_t base = px0; base < px1; base += KB, ++it) {
         if ((int)(it % PXW) != me) continue;
         const int slot = it % PR;
         const int64_t px = base + lane;
-        float r = 0.f, g = 0.f, bl = 0.f;
+        float r = 0.f, g = 0.f, bl = 0.f, mult = 1.f;
         const bool valid = px < px1;
-        if (valid) {
+        if (valid && ir.dedup) {
+          const float4 q = __ldg(p.ulist + b * DEDUP_MAX + px);
+          r = q.x; g = q.y; bl = q.z; mult = q.w;
+        } else if (valid) {
           const float* src = p.image + (b * p.npix + px) * p.channels;
           if (p.channels == 4) {
             const float4 q = __ldg(reinterpret_cast<const float4*>(src));
@@ -295,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         o.u[0][lane] = d_rg;  o.v[0][lane] = d_rb;
         o.u[1][lane] = -d_rg; o.v[1][lane] = d_gb;
         o.u[2][lane] = -d_rb; o.v[2][lane] = -d_gb;
-        o.iy[lane] = valid ? iy : 0.f;  // masked pixels contribute nothing (A operand = 0)
+        o.iy[lane] = valid ? iy * mult : 0.f;  // masked pixels contribute nothing (A operand = 0)
         mbar_arrive(&S.px_full[slot]);
       }
     }
@@ -311,10 +348,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     const uint32_t row_off = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);  // hi row j; lo row j + 64 is +1024
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
-      const int64_t split = w % p.splits;
-      const int64_t px0 = split * p.px_per_split;
-      const int64_t px1 = min(px0 + p.px_per_split, p.npix);
-      for (int64_t base = px0; base < px1; base += KB, ++it) {
+      const ItemRange ir = item_range(p, w / p.splits, w % p.splits);
+      for (int64_t base = ir.px0; base < ir.px1; base += KB, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
         const PxSlot& in = S.px[slot];
@@ -352,10 +387,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);  // provably uniform copy
     uint32_t it = 0, chain = 0;
     for (int64_t w = first; w < p.items; w += step) {
-      const int64_t split = w % p.splits;
-      const int64_t px0 = split * p.px_per_split;
-      const int64_t px1 = min(px0 + p.px_per_split, p.npix);
-      const int64_t nkb = (px1 - px0 + KB - 1) / KB;
+      const ItemRange ir = item_range(p, w / p.splits, w % p.splits);
+      const int64_t nkb = (ir.px1 - ir.px0 + KB - 1) / KB;
       for (int64_t kb = 0; kb < nkb; ++kb, ++it) {
         const bool chain_start = (kb % CHAIN_KB) == 0;
         if (chain_start && chain > 0) {
@@ -398,6 +431,90 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
 
 }  // namespace fwdtc
 
+
+// =============================================================================================
+// De-duplication pass: unique RGB triples of each image with their multiplicities.  The histogram is
+// a sum over pixels of a function of the pixel's colour, so identical pixels contribute
+// count x (one pixel): palette images (the reference's `real` sprites have 10-54 colours)
+// contract 1-2 stages instead of 128.  One CTA per image; an open-addressing table in shared memory
+// keyed by the bit pattern of (r,g,b): a slot is claimed by the index of the first pixel that hashes
+// there (32-bit CAS) and later pixels compare their colour with that pixel's.  Lanes of a warp that
+// hold the same colour are aggregated first (match + ballot), so the fully transparent background
+// costs one table operation per warp.  More than DEDUP_MAX colours (a generator output): the image
+// is flagged dense (nunique = -1) and the contraction reads its pixels directly.
+// =============================================================================================
+__global__ void __launch_bounds__(256) hist_dedup_kernel(const float* __restrict__ image, int64_t npix, int channels,
+                                                         float4* __restrict__ ulist, int* __restrict__ nunique) {
+  using namespace fwdtc;
+  __shared__ int owner[DEDUP_SLOTS];
+  __shared__ int count[DEDUP_SLOTS];
+  __shared__ int s_n, s_out;
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float* img = image + b * npix * channels;
+  for (int i = tid; i < DEDUP_SLOTS; i += 256) { owner[i] = -1; count[i] = 0; }
+  if (tid == 0) { s_n = 0; s_out = 0; }
+  __syncthreads();
+  const int64_t padded = (npix + 31) / 32 * 32;
+  for (int64_t px = tid; px < padded; px += 256) {
+    const bool active = px < npix;
+    unsigned r = 0, g = 0, bl = 0;
+    if (active) {
+      const float* src = img + px * channels;
+      if (channels == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+        r = __float_as_uint(q.x); g = __float_as_uint(q.y); bl = __float_as_uint(q.z);
+      } else {
+        r = __float_as_uint(__ldg(src)); g = __float_as_uint(__ldg(src + 1)); bl = __float_as_uint(__ldg(src + 2));
+      }
+    }
+    const unsigned h = (r * 2654435761u) ^ (g * 2246822519u) ^ (bl * 3266489917u);
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    const bool dense = __any_sync(0xffffffffu, *(volatile int*)&s_n > DEDUP_MAX);  // warp-uniform exit
+    if (!active || dense) continue;
+    // warp aggregation: lanes with the same hash, then verified against the group leader's colour
+    const unsigned peers = __match_any_sync(amask, h);
+    const int leader = __ffs(peers) - 1;
+    const unsigned lr = __shfl_sync(peers, r, leader), lg = __shfl_sync(peers, g, leader), lb = __shfl_sync(peers, bl, leader);
+    const bool same = (r == lr) && (g == lg) && (bl == lb);
+    const unsigned agree = __ballot_sync(peers, same) & peers;
+    int add = 0;
+    if (lane == leader) add = __popc(agree);
+    else if (!same) add = 1;  // hash collision inside the warp: insert on its own
+    if (add == 0) continue;
+    unsigned slot = (h >> 16 ^ h) & (DEDUP_SLOTS - 1);
+    for (int probe = 0; probe < DEDUP_SLOTS; ++probe) {
+      int o = *(volatile int*)&owner[slot];
+      if (o == -1) {
+        o = atomicCAS(&owner[slot], -1, (int)px);
+        if (o == -1) { o = (int)px; atomicAdd(&s_n, 1); }
+      }
+      const float* op = img + (int64_t)o * channels;
+      if (__float_as_uint(__ldg(op)) == r && __float_as_uint(__ldg(op + 1)) == g && __float_as_uint(__ldg(op + 2)) == bl) {
+        atomicAdd(&count[slot], add);
+        break;
+      }
+      slot = (slot + 1) & (DEDUP_SLOTS - 1);
+      if (*(volatile int*)&s_n > DEDUP_MAX) break;
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n > DEDUP_MAX) {
+    if (tid == 0) nunique[b] = -1;
+    return;
+  }
+  float4* out = ulist + b * DEDUP_MAX;
+  for (int i = tid; i < DEDUP_SLOTS; i += 256) {
+    const int o = owner[i];
+    if (o >= 0) {
+      const float* op = img + (int64_t)o * channels;
+      out[atomicAdd(&s_out, 1)] = make_float4(__ldg(op), __ldg(op + 1), __ldg(op + 2), (float)count[i]);
+    }
+  }
+  if (tid == 0) nunique[b] = n;
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -418,10 +535,14 @@ static int tc_fwd_splits(int64_t batch, int64_t npix) {
   return (int)s;
 }
 
+static size_t dedup_bytes(int64_t batch) {
+  return align_up((size_t)batch * fwdtc::DEDUP_MAX * sizeof(float4), 256) + align_up((size_t)batch * sizeof(int), 256);
+}
+
 size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins) {
   if (bins != 64) return 0;
   const int splits = tc_fwd_splits(batch, npix);
-  const size_t fwd = splits > 1 ? (size_t)batch * splits * 3 * bins * bins * sizeof(float) : 0;
+  const size_t fwd = splits > 1 ? (size_t)batch * splits * 3 * bins * bins * sizeof(float) : dedup_bytes(batch);
   const size_t bwd = (size_t)batch * 3 * bins * bins * sizeof(float);
   return align_up(fwd > bwd ? fwd : bwd, 256) + 256;
 }
@@ -431,7 +552,7 @@ void launch_finalize(const float* partial, int splits, int nch, int bins, int no
                      float* denom, int64_t batch, cudaStream_t st);
 
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int bins,
-                    int method, float sigma_sqr, float eps, float* hist, float* denom, void* workspace,
+                    int method, float sigma_sqr, float eps, float* hist, float* denom, void* workspace, bool dedup,
                     cudaStream_t st) {
   using namespace fwdtc;
   PH_CHECK_ARG(bins == BINS, "tensor-core forward is specialised for 64 bins");
@@ -448,6 +569,16 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.items = batch * p.splits;
   p.inv_sigma_sqr = 1.0f / sigma_sqr;
   p.eps = eps;
+  if (dedup && p.splits == 1) {
+    // unique colours + multiplicities per image (only worth it when a CTA owns whole images)
+    float4* ulist = static_cast<float4*>(workspace);
+    int* nunique = reinterpret_cast<int*>(static_cast<char*>(workspace) +
+                                          align_up((size_t)batch * DEDUP_MAX * sizeof(float4), 256));
+    hist_dedup_kernel<<<(unsigned)batch, 256, 0, st>>>(image, npix, channels, ulist, nunique);
+    PH_LAUNCH_OK("hist_dedup_kernel");
+    p.ulist = ulist;
+    p.nunique = nunique;
+  }
   const size_t smem = sizeof(Smem);
   int grid = cached_sm_count();
   if (grid > p.items) grid = (int)p.items;

@@ -173,8 +173,8 @@ class _HistogramLossFn(torch.autograd.Function):
     """fwd(real) + fwd(fake) + Hellinger, backward to the fake image only (pix2pix_model.py:243-245)."""
 
     @staticmethod
-    def forward(ctx, real, fake, dom, method_id, sigma_sqr, impl, group, global_batch):
-        hist_real, _ = _forward(real, dom, method_id, sigma_sqr, impl)
+    def forward(ctx, real, fake, dom, method_id, sigma_sqr, impl, group, global_batch, dedup_real):
+        hist_real, _ = _forward(real, dom, method_id, sigma_sqr, impl | (DEDUP_FLAG if dedup_real else 0))
         hist_fake, denom_fake = _forward(fake, dom, method_id, sigma_sqr, impl)
         ssum = _ssum(hist_real, hist_fake)
         gb = _reduce_over_ranks(ssum, real.shape[0], group, global_batch)
@@ -189,17 +189,24 @@ class _HistogramLossFn(torch.autograd.Function):
         scale = grad_loss.to(torch.float32).contiguous()
         grad = _backward(fake, dom, method_id, sigma_sqr, impl, hist_fake, denom_fake, hist_true=hist_real,
                          ssum=ssum, global_batch=gb, loss_scale=scale)
-        return None, grad, None, None, None, None, None, None
+        return None, grad, None, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
 # public API — reference signatures
 # ------------------------------------------------------------------------------------------------
-def calculate_rgbuv_histogram(image_batch, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto"):
-    """histogram.py:36-81.  image_batch (B,H,W,3|4) float32 in [-1,1] -> (B,size,size,3), sums to 1 per image."""
+DEDUP_FLAG = 8  # PH_IMPL_DEDUP
+
+
+def calculate_rgbuv_histogram(image_batch, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",
+                              dedup=False):
+    """histogram.py:36-81.  image_batch (B,H,W,3|4) float32 in [-1,1] -> (B,size,size,3), sums to 1 per image.
+    `dedup=True`: contract each image's unique colours with their multiplicities (exact; pays off for
+    palette images such as dataset sprites, falls back to the dense contraction per image otherwise)."""
     image = require_cuda(from_any(image_batch, name="image_batch"), torch.float32, name="image_batch")
     dom = histogram_domain(size, image.device)
-    out = _RgbuvHistogramFn.apply(image, dom, _method_id(method), _sigma_sqr(sigma), _lib.IMPLS[impl])
+    out = _RgbuvHistogramFn.apply(image, dom, _method_id(method), _sigma_sqr(sigma),
+                                  _lib.IMPLS[impl] | (DEDUP_FLAG if dedup else 0))
     return to_caller_framework(out, image_batch)
 
 
@@ -256,14 +263,16 @@ def l2_loss(y_true, y_pred):
 
 
 def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", sigma=0.02, *, group=None,
-                   global_batch=None, impl="auto"):
+                   global_batch=None, impl="auto", dedup_real=True):
     """`hellinger_loss(calculate_rgbuv_histogram(real), calculate_rgbuv_histogram(fake))` as one call
-    (pix2pix_model.py:243-245); differentiable with respect to `fake_image`."""
+    (pix2pix_model.py:243-245); differentiable with respect to `fake_image`.  `dedup_real`: the real images
+    come from the dataset and are palette sprites, so their histogram is contracted over unique colours
+    (images that are not palette-like are detected on the device and contracted densely)."""
     real = require_cuda(from_any(real_image, name="real_image"), torch.float32, name="real_image")
     fake = require_cuda(from_any(fake_image, name="fake_image"), torch.float32, name="fake_image")
     if real.shape != fake.shape:
         raise ValueError("real_image and fake_image must have the same shape")
     dom = histogram_domain(size, fake.device)
     out = _HistogramLossFn.apply(real, fake, dom, _method_id(method), _sigma_sqr(sigma), _lib.IMPLS[impl], group,
-                                 global_batch)
+                                 global_batch, bool(dedup_real))
     return to_caller_framework(out, fake_image)

@@ -213,3 +213,28 @@ def test_host_buffer_api(cuda):
         assert abs(l2 - ref["loss"]) / ref["loss"] < LOSS_TOL
         assert ho.rel_l2(gd.cpu().numpy(), ref["grad"][lo:lo + 3]) < GRAD_TOL
     ctx.close()
+
+
+def test_dedup_forward_matches_dense(H, cuda, sprites):
+    """Unique-colour contraction (PH_IMPL_DEDUP): exact regrouping of the pixel sum.  Batch >= SM count so
+    the whole-image path is taken; sprite images de-duplicate, dense images are detected and fall back."""
+    rng = np.random.default_rng(21)
+    spr = normalize(np.concatenate([sprites["front"], sprites["right"]])[:200].astype(np.float32))   # palette images
+    dense = np.tanh(rng.standard_normal((24, 64, 64, 4))).astype(np.float32)
+    few = np.tile(np.array([[0.25, -0.5, 0.75, 1.0]], np.float32), (2, 64, 64, 1))                     # one colour
+    batch = np.concatenate([spr[:100], dense[:12], few, spr[100:], dense[12:]]).astype(np.float32)
+    x = torch.from_numpy(batch).to(cuda)
+    a = H.calculate_rgbuv_histogram(x, impl="tc", dedup=True).cpu().numpy()
+    b = H.calculate_rgbuv_histogram(x, impl="tc", dedup=False).cpu().numpy()
+    assert ho.rel_l2(a, b) < 3e-6
+    pick = [0, 57, 100, 105, 112, 113, 150, 225]
+    ref, _ = ho.rgbuv_histogram_f64(batch[pick])
+    assert ho.rel_l2(a[pick], ref) < HIST_TOL and ho.rel_max(a[pick], ref) < HIST_TOL
+    # loss + gradient with de-duplicated real images (the default of histogram_loss)
+    fake = torch.tanh(torch.randn(x.shape, device=cuda, generator=torch.Generator(cuda).manual_seed(3)))
+    f1 = fake.clone().requires_grad_(True)
+    f2 = fake.clone().requires_grad_(True)
+    l1 = H.histogram_loss(x, f1, dedup_real=True); l1.backward()
+    l2 = H.histogram_loss(x, f2, dedup_real=False); l2.backward()
+    assert abs(float(l1.detach()) - float(l2.detach())) / float(l2.detach()) < 1e-6
+    assert ho.rel_l2(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < 1e-5
