@@ -49,6 +49,7 @@ constexpr int B_CH_BYTES = KB * 128 * 4;   // 16384: [kq 0..7][n-group 0..15][n%
 constexpr int B_STAGE_BYTES = 3 * B_CH_BYTES;
 constexpr int B_KQ_BYTES = 16 * 128;       // 2048: one 4-pixel quad for all 128 rows
 static_assert(A_COL0 + NS * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
+static_assert(KB == 32, "stage = 32 pixels (shifts below)");
 
 struct PxSlot {
   float u[3][KB], v[3][KB], iy[KB];
@@ -88,15 +89,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Pixel range of a work item.  A de-duplicated image is a list of (colour, multiplicity) entries: the
 // histogram is linear in the pixels, so identical pixels are contracted once with weight count*Iy.
-struct ItemRange { int64_t px0, px1; bool dedup; };
+struct ItemRange { uint32_t px0, px1; bool dedup; };  // 32-bit: keeps the role loops in the uniform datapath
 __device__ __forceinline__ ItemRange item_range(const Params& p, int64_t b, int64_t split) {
   ItemRange r;
   if (p.nunique != nullptr) {
-    const int nu = __ldg(p.nunique + b);
-    if (nu >= 0) { r.px0 = 0; r.px1 = nu; r.dedup = true; return r; }
+    // broadcast from lane 0: lets ptxas prove the loop bounds derived from it warp-uniform
+    const int nu = __shfl_sync(0xffffffffu, __ldg(p.nunique + b), 0);
+    if (nu >= 0) { r.px0 = 0; r.px1 = (uint32_t)nu; r.dedup = true; return r; }
   }
-  r.px0 = split * p.px_per_split;
-  r.px1 = min(r.px0 + p.px_per_split, p.npix);
+  r.px0 = (uint32_t)split * (uint32_t)p.px_per_split;
+  r.px1 = min(r.px0 + (uint32_t)p.px_per_split, (uint32_t)p.npix);
   r.dedup = false;
   return r;
 }
@@ -134,8 +136,8 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
     for (int64_t w = first; w < p.items; w += step) {
       const int64_t b = w / p.splits, split = w % p.splits;
       const ItemRange ir = item_range(p, b, split);
-      const int64_t nkb = (ir.px1 - ir.px0 + KB - 1) / KB;
-      for (int64_t kb = 0; kb < nkb; ++kb, ++it) {
+      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
+      for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
         const PxSlot& in = S.px[slot];
@@ -302,11 +304,11 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     for (int64_t w = first; w < p.items; w += step) {
       const int64_t b = w / p.splits, split = w % p.splits;
       const ItemRange ir = item_range(p, b, split);
-      const int64_t px0 = ir.px0, px1 = ir.px1;
-      for (int64_t base = px0; base < px1; base += KB, ++it) {
+      const uint32_t px0 = ir.px0, px1 = ir.px1;
+      for (uint32_t base = px0; base < px1; base += KB, ++it) {
         if ((int)(it % PXW) != me) continue;
         const int slot = it % PR;
-        const int64_t px = base + lane;
+        const uint32_t px = base + lane;
         float r = 0.f, g = 0.f, bl = 0.f, mult = 1.f;
         const bool valid = px < px1;
         if (valid && ir.dedup) {
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const ItemRange ir = item_range(p, w / p.splits, w % p.splits);
-      for (int64_t base = ir.px0; base < ir.px1; base += KB, ++it) {
+      for (uint32_t base = ir.px0; base < ir.px1; base += KB, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
         const PxSlot& in = S.px[slot];
@@ -385,41 +387,42 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(&S.b[0][0]), B_KQ_BYTES, 128);
     const uint32_t dlo0 = (uint32_t)desc0, dhi = (uint32_t)(desc0 >> 32);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);  // provably uniform copy
-    uint32_t it = 0, chain = 0;
+    // Wrap-around counters only (no % or /) and no conditionally executed waits: ptxas then keeps the whole
+    // loop in the uniform datapath and the MMA operands in uniform registers (a conditional mbarrier wait
+    // inside the stage loop was enough to push every operand through R2UR moves).
+    uint32_t stage = 0, phase = 0, chain_par = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const ItemRange ir = item_range(p, w / p.splits, w % p.splits);
-      const int64_t nkb = (ir.px1 - ir.px0 + KB - 1) / KB;
-      for (int64_t kb = 0; kb < nkb; ++kb, ++it) {
-        const bool chain_start = (kb % CHAIN_KB) == 0;
-        if (chain_start && chain > 0) {
-          mbar_wait(&S.d_empty, (chain - 1) & 1);
+      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
+      for (uint32_t kb0 = 0; kb0 < nkb; kb0 += CHAIN_KB) {
+        const uint32_t n_this = min((uint32_t)CHAIN_KB, nkb - kb0);
+        for (uint32_t k = 0; k < n_this; ++k) {
+          mbar_wait(&S.ab_full[stage], phase);
           tc_fence_after_sync();
-        }
-        const uint32_t stage = it % NS;
-        mbar_wait(&S.ab_full[stage], (it / NS) & 1);
-        tc_fence_after_sync();
-        // the start-address field (bits 0-13, units of 16 B) never carries into the next field
-        const uint32_t dstage = dlo0 + ((stage * B_STAGE_BYTES) >> 4);
-        const uint32_t a_stage = tm + A_COL0 + stage * A_STAGE_COLS;
+          // the start-address field (bits 0-13, units of 16 B) never carries into the next field
+          const uint32_t dstage = dlo0 + stage * (B_STAGE_BYTES >> 4);
+          const uint32_t a_stage = tm + A_COL0 + stage * A_STAGE_COLS;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+          for (int c = 0; c < 3; ++c) {
 #pragma unroll
-          for (int ks = 0; ks < KB / 8; ++ks) {
-            const uint32_t b_hi = dstage + ((c * B_CH_BYTES + ks * 2 * B_KQ_BYTES) >> 4);
-            const uint32_t b_lo = b_hi + (1024 >> 4);
-            const uint32_t acc0 = (chain_start && ks == 0) ? 0u : 1u;
-            if (elect_one_sync()) {
-              mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_hi, dhi, IDESC, acc0);
-              mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_lo, dhi, IDESC, 1u);
+            for (int ks = 0; ks < KB / 8; ++ks) {
+              const uint32_t b_hi = dstage + ((c * B_CH_BYTES + ks * 2 * B_KQ_BYTES) >> 4);
+              const uint32_t b_lo = b_hi + (1024 >> 4);
+              const uint32_t acc0 = (k == 0 && ks == 0) ? 0u : 1u;
+              if (elect_one_sync()) {
+                mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_hi, dhi, IDESC, acc0);
+                mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_lo, dhi, IDESC, 1u);
+              }
             }
           }
+          if (elect_one_sync()) mma_commit(&S.ab_empty[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
         }
-        const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
-        if (elect_one_sync()) {
-          mma_commit(&S.ab_empty[stage]);
-          if (chain_end) mma_commit(&S.d_full);
-        }
-        if (chain_end) ++chain;
+        if (elect_one_sync()) mma_commit(&S.d_full);
+        // the accumulators are free again once the epilogue warps have drained this chain
+        mbar_wait(&S.d_empty, chain_par);
+        tc_fence_after_sync();
+        chain_par ^= 1;
       }
     }
   }
