@@ -67,12 +67,13 @@ def make_sprites_u8(rng, batch, hw=HW):
     return out
 
 
-def make_hist_inputs(batch, seed):
+def make_hist_inputs(batch, seed, with_u8=False):
     """real = palette-quantised sprite-like images in [-1,1]; fake = tanh(N(0,1)) (dense worst case)."""
     rng = np.random.default_rng(seed)
-    real = (make_sprites_u8(rng, batch).astype(np.float32) / np.float32(127.5)) - np.float32(1.0)
+    real_u8 = make_sprites_u8(rng, batch)
+    real = (real_u8.astype(np.float32) / np.float32(127.5)) - np.float32(1.0)
     fake = np.tanh(rng.standard_normal((batch, HW, HW, 4), dtype=np.float32)).astype(np.float32)
-    return real, fake
+    return (real, fake, real_u8) if with_u8 else (real, fake)
 
 
 def make_palette_inputs(batch, seed):
@@ -234,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
 
     lo, hi = shard_bounds(GLOBAL_BATCH, world, rank)
     local_b = hi - lo
-    real_np, fake_np = make_hist_inputs(local_b, 47 + rank)
+    real_np, fake_np, real_u8_np = make_hist_inputs(local_b, 47 + rank, with_u8=True)
     real = torch.from_numpy(real_np).to(dev)
     fake = torch.from_numpy(fake_np).to(dev).requires_grad_(True)
 
@@ -318,7 +319,7 @@ def run_ours(args, rank, world, local_rank):
     }
 
     # ---- e2e: host buffers through the C ABI (pinned in, loss + gradient out) ----
-    real_h = torch.from_numpy(real_np).pin_memory()
+    real_h = torch.from_numpy(real_u8_np).pin_memory()   # sprites as the decoder delivers them: uint8 RGBA
     fake_h = torch.from_numpy(fake_np).pin_memory()
     grad_d = torch.empty((local_b, HW, HW, 4), dtype=torch.float32, device=dev)  # consumed on the device
     ctx = hostapi.HostContext(local_rank)
@@ -344,10 +345,10 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = GLOBAL_BATCH * e2e_steps / float(tw)
     img_bytes = local_b * npix * 4 * 4
-    e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": 2 * img_bytes * world,
+    e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": (img_bytes + img_bytes // 4) * world,
            "d2h_bytes_per_step": (4 + 8) * world, "steps": e2e_steps,
-           "api": "hostapi.histogram_loss_begin/finish -> ph_host_hist_begin/finish: real + fake from pinned host "
-                  "memory every step, loss (and the shard's sum of squares) read back, gradient left on the device "
+           "api": "hostapi.histogram_loss_begin/finish -> ph_host_hist_begin_u8real/finish: real (uint8 RGBA sprites, "
+                  "blackened + normalised on the device) + fake (float32) from pinned host memory every step, loss (and the shard's sum of squares) read back, gradient left on the device "
                   "for the generator's backward",
            "loss": e2e_loss}
     ctx.close()

@@ -155,6 +155,12 @@ PH_API int ph_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix,
                        int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
                        void* stream);
 
+/* dataset_utils.py:66-77 `load_image` after PNG decode: uint8 RGBA (npixels,4) -> float32 (npixels,4) with
+ * blacken_transparent_pixels (:11-20, applied when blacken != 0) and normalize (:39-48, x/127.5-1, when
+ * normalize != 0).  Lets a host caller upload sprites as uint8 (4 B/pixel instead of 16). */
+PH_API int ph_u8_to_float_image(const uint8_t* image_u8, int64_t npixels, int blacken, int normalize, float* image,
+                         void* stream);
+
 /* pix2pix_model.py:300-301 `tf.one_hot(idx, depth)`: indexed (n) int32 -> one_hot (n,depth) float32. */
 PH_API int ph_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, void* stream);
 
@@ -195,6 +201,11 @@ PH_API int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const flo
 PH_API int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
                        int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
                        float sigma_sqr, float epsilon, int impl, double* ssum_local_host);
+/* Same with the real images as uint8 RGBA sprites straight from the decoder (batch,npix,4): they are
+ * blackened + normalised on the device (dataset_utils.py:66-77); fake stays float32 RGBA. */
+PH_API int ph_host_hist_begin_u8real(ph_host_ctx* ctx, const uint8_t* real_u8_host, const float* fake_host,
+                              int64_t batch, int64_t npix, const float* bin_centers_host, int bins, int method,
+                              float sigma_sqr, float epsilon, int impl, double* ssum_local_host);
 PH_API int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
                         float* grad_fake_host, float* grad_fake_device);
 

@@ -53,12 +53,14 @@ PROTOTYPES = {
     "ph_extract_palette": (_int, [_p, _i64, _i64, _int, _p, _p, _p]),
     "ph_rgba_to_indexed": (_int, [_p, _i64, _i64, _p, _i64, _int, _p, _p, _int, _p]),
     "ph_one_hot": (_int, [_p, _i64, _int, _p, _p]),
+    "ph_u8_to_float_image": (_int, [_p, _i64, _int, _int, _p, _p]),
     "ph_indexed_to_rgba": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _p]),
     "ph_load_indexed_images": (_int, [_p, _p, _i64, _i64, _int, _p, _p, _p, _p, _p]),
     "ph_host_ctx_create": (_int, [_int, C.POINTER(_p)]),
     "ph_host_ctx_destroy": (None, [_p]),
     "ph_host_hist_loss": (_int, [_p, _p, _p, _i64, _i64, _int, _p, _int, _int, _f, _f, _int, _p, _p]),
     "ph_host_hist_begin": (_int, [_p, _p, _p, _i64, _i64, _int, _p, _int, _int, _f, _f, _int, _p]),
+    "ph_host_hist_begin_u8real": (_int, [_p, _p, _p, _i64, _i64, _p, _int, _int, _f, _f, _int, _p]),
     "ph_host_hist_finish": (_int, [_p, C.c_double, _i64, _p, _p, _p]),
     "ph_host_load_indexed_images": (_int, [_p, _p, _p, _i64, _i64, _int, _p, _p, _p, _p, _p]),
 }

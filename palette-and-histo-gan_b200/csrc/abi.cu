@@ -222,6 +222,14 @@ int ph_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const 
   return PH_OK;
 }
 
+int ph_u8_to_float_image(const uint8_t* image_u8, int64_t npixels, int blacken, int normalize, float* image,
+                         void* stream) {
+  PH_CHECK_ARG(image_u8 && image && npixels >= 0, "bad argument");
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(image_u8) & 3) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0,
+               "uint8 image must be 4-byte aligned and the float image 16-byte aligned");
+  return launch_u8_to_float_image(image_u8, npixels, blacken, normalize, image, static_cast<cudaStream_t>(stream));
+}
+
 int ph_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, void* stream) {
   PH_CHECK_ARG(indexed && one_hot && n >= 0 && depth > 0, "bad argument");
   PH_CHECK_ARG((reinterpret_cast<uintptr_t>(one_hot) & 15) == 0, "one_hot must be 16-byte aligned");

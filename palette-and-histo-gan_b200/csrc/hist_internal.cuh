@@ -54,6 +54,8 @@ int launch_load_indexed_fused(const int32_t* source, const int32_t* target, int6
 int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,
                            int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
                            cudaStream_t st);
+int launch_u8_to_float_image(const uint8_t* src, int64_t npixels, int blacken, int normalize, float* dst,
+                             cudaStream_t st);
 int launch_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, cudaStream_t st);
 int launch_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npix, const int32_t* palette,
                            int64_t palette_batch, int palette_rows, int channels, int32_t* out,

@@ -21,6 +21,7 @@ struct ph_host_ctx {
   bool events_ready = false;
   // state carried from ph_host_hist_begin to ph_host_hist_finish
   struct Job {
+    unsigned char* d_u8[2];
     float *d_fake, *d_real[2], *d_hreal, *d_hfake, *d_denom_r, *d_denom_f, *d_grad[2], *d_dom, *d_loss;
     double* d_ssum;
     char* d_ws;
@@ -105,9 +106,9 @@ void ph_host_ctx_destroy(ph_host_ctx* ctx) {
 
 // Two-phase form (ph_host_hist_begin / ph_host_hist_finish): the caller may all-reduce the local sum
 // of squares over ranks between the phases; ph_host_hist_loss is the single-process composition.
-int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
-                       int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
-                       float sigma_sqr, float epsilon, int impl, double* ssum_local_host) {
+static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool real_is_u8, const float* fake_host,
+                                int64_t batch, int64_t npix, int channels, const float* bin_centers_host, int bins,
+                                int method, float sigma_sqr, float epsilon, int impl, double* ssum_local_host) {
   PH_CHECK_ARG(ctx && real_host && fake_host && bin_centers_host && ssum_local_host, "NULL pointer argument");
   PH_CHECK_ARG(batch > 0 && npix > 0 && (channels == 3 || channels == 4), "bad shape");
   PH_CHECK_ARG(bins >= 1 && bins <= 1024, "bins must be in [1,1024]");
@@ -117,6 +118,8 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
   // chunking: at least 8 MiB per copy, at most kMaxChunks chunks
   const size_t img_bytes = (size_t)npix * channels * sizeof(float);
   int64_t chunk = (int64_t)((8u << 20) / img_bytes);
+  if (chunk < 296) chunk = 296;  // at least two images per SM, so each chunk takes the whole-image kernel path
+  if (chunk > batch) chunk = batch;
   if (chunk < 1) chunk = 1;
   if (ceil_div(batch, chunk) > ph_host_ctx::kMaxChunks) chunk = ceil_div(batch, ph_host_ctx::kMaxChunks);
   const int nchunks = (int)ceil_div(batch, chunk);
@@ -141,6 +144,8 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
     J.d_ssum = cv.take<double>(1);
     J.d_loss = cv.take<float>(1);
     J.d_ws = cv.take<char>(ws_bytes);
+    J.d_u8[0] = real_is_u8 ? cv.take<unsigned char>((size_t)chunk * npix * 4) : nullptr;
+    J.d_u8[1] = real_is_u8 ? cv.take<unsigned char>((size_t)chunk * npix * 4) : nullptr;
     if (pass == 0) {
       int rc = ensure_arena(ctx, align_up(cv.off, 256) + 256);
       if (rc != PH_OK) return rc;
@@ -158,14 +163,24 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
     const size_t n = (size_t)nb * npix * channels;
     const int slot = k & 1;
     if (k >= 2) PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_free[slot], 0));
-    PH_CUDA_OK(cudaMemcpyAsync(J.d_real[slot], real_host + (size_t)b0 * npix * channels, n * sizeof(float),
-                               cudaMemcpyHostToDevice, ctx->s_in));
+    if (real_is_u8) {
+      PH_CUDA_OK(cudaMemcpyAsync(J.d_u8[slot], static_cast<const unsigned char*>(real_host) + (size_t)b0 * npix * 4,
+                                 (size_t)nb * npix * 4, cudaMemcpyHostToDevice, ctx->s_in));
+    } else {
+      PH_CUDA_OK(cudaMemcpyAsync(J.d_real[slot], static_cast<const float*>(real_host) + (size_t)b0 * npix * channels,
+                                 n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_in));
+    }
     PH_CUDA_OK(cudaMemcpyAsync(J.d_fake + (size_t)b0 * npix * channels, fake_host + (size_t)b0 * npix * channels,
                                n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_in));
     PH_CUDA_OK(cudaEventRecord(ctx->ev_in[k], ctx->s_in));
     PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[k], 0));
+    if (real_is_u8) {  // blacken + normalise on the device (dataset_utils.py:66-77)
+      int rcu = ph_u8_to_float_image(J.d_u8[slot], nb * npix, 1, 1, J.d_real[slot], ctx->s_compute);
+      if (rcu != PH_OK) return rcu;
+    }
     int rc = ph_hist_forward(J.d_real[slot], nb, npix, channels, J.d_dom, bins, method, sigma_sqr, epsilon,
-                             J.d_hreal + (size_t)b0 * hist_elems, J.d_denom_r + b0, J.d_ws, ws_bytes, impl,
+                             J.d_hreal + (size_t)b0 * hist_elems, J.d_denom_r + b0, J.d_ws, ws_bytes,
+                             impl | PH_IMPL_DEDUP,  // real images are dataset sprites: contract unique colours
                              ctx->s_compute);
     if (rc != PH_OK) return rc;
     PH_CUDA_OK(cudaEventRecord(ctx->ev_free[slot], ctx->s_compute));
@@ -181,6 +196,20 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
   PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
   ctx->job_valid = true;
   return PH_OK;
+}
+
+int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
+                       int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
+                       float sigma_sqr, float epsilon, int impl, double* ssum_local_host) {
+  return host_hist_begin_impl(ctx, real_host, false, fake_host, batch, npix, channels, bin_centers_host, bins, method,
+                              sigma_sqr, epsilon, impl, ssum_local_host);
+}
+
+int ph_host_hist_begin_u8real(ph_host_ctx* ctx, const uint8_t* real_u8_host, const float* fake_host, int64_t batch,
+                              int64_t npix, const float* bin_centers_host, int bins, int method, float sigma_sqr,
+                              float epsilon, int impl, double* ssum_local_host) {
+  return host_hist_begin_impl(ctx, real_u8_host, true, fake_host, batch, npix, 4, bin_centers_host, bins, method,
+                              sigma_sqr, epsilon, impl, ssum_local_host);
 }
 
 int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,

@@ -349,6 +349,43 @@ __global__ void __launch_bounds__(256) indexed_to_rgba_kernel(
 }
 
 // =============================================================================================
+// Loader-side pixel prep (dataset_utils.py:66-77 after decode_png): uint8 RGBA -> float32 with
+// blacken_transparent_pixels (:11-20, alpha == 0 -> the whole pixel becomes 0) and normalize
+// (:39-48, x/127.5 - 1) in one pass.  4 B in, 16 B out per pixel; lets the host ship sprites as the
+// uint8 they are on disk (4x fewer PCIe bytes than the float32 tensor the reference uploads).
+// =============================================================================================
+__global__ void __launch_bounds__(256) u8_to_float_image_kernel(const uchar4* __restrict__ src, int64_t npixels,
+                                                                int blacken, int normalize,
+                                                                float4* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npixels; i += stride) {
+    uchar4 q = __ldg(src + i);
+    if (blacken && q.w == 0) q = make_uchar4(0, 0, 0, 0);
+    float4 o = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
+    if (normalize) {
+      // same two roundings as the reference: (image / 127.5) - 1
+      o.x = __fsub_rn(__fdiv_rn(o.x, 127.5f), 1.0f);
+      o.y = __fsub_rn(__fdiv_rn(o.y, 127.5f), 1.0f);
+      o.z = __fsub_rn(__fdiv_rn(o.z, 127.5f), 1.0f);
+      o.w = __fsub_rn(__fdiv_rn(o.w, 127.5f), 1.0f);
+    }
+    dst[i] = o;
+  }
+}
+
+int launch_u8_to_float_image(const uint8_t* src, int64_t npixels, int blacken, int normalize, float* dst,
+                             cudaStream_t st) {
+  if (npixels == 0) return PH_OK;
+  int64_t grid = ceil_div(npixels, 256 * 4);
+  const int64_t cap = (int64_t)cached_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  u8_to_float_image_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const uchar4*>(src), npixels, blacken,
+                                                           normalize, reinterpret_cast<float4*>(dst));
+  PH_LAUNCH_OK("u8_to_float_image_kernel");
+  return PH_OK;
+}
+
+// =============================================================================================
 // launchers
 // =============================================================================================
 int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows,

@@ -33,6 +33,20 @@ def denormalize(image):
     return to_caller_framework((from_any(image) + 1) * 127.5, image)
 
 
+def load_image(image_u8, should_normalize=True):
+    """dataset_utils.py:66-77 after `decode_png`: uint8 RGBA (…,4) CUDA tensor -> float32 with
+    `blacken_transparent_pixels` and (optionally) `normalize` fused in one pass on the device."""
+    img = require_cuda(from_any(image_u8, name="image"), torch.uint8, name="image")
+    if img.shape[-1] != 4:
+        raise ValueError("load_image expects RGBA uint8 pixels (last dimension 4)")
+    out = torch.empty(img.shape, dtype=torch.float32, device=img.device)
+    if img.numel():
+        with torch.cuda.device(img.device):
+            _lib.call("ph_u8_to_float_image", ptr(img), img.numel() // 4, 1, 1 if should_normalize else 0, ptr(out),
+                      stream_ptr(img.device))
+    return to_caller_framework(out, image_u8)
+
+
 def load_indexed_images(source_image, target_image, palette_ordering="grayness", *, check=True):
     """dataset_utils.py:138-151 for decoded images: `concat([source, target], -1)` -> `extract_palette`
     -> `rgba_to_indexed` twice with the shared palette.  (H,W,4) or (B,H,W,4) int32 CUDA tensors.

@@ -84,14 +84,24 @@ def histogram_loss_begin(real_image, fake_image, size=64, method="inverse-quadra
                          ctx=None, device=0) -> float:
     """Phase 1 of a sharded evaluation: upload + both forward passes; returns this shard's sum of squares
     (all-reduce it over ranks, then call `histogram_loss_finish`)."""
-    real = _np(real_image, np.float32, "real_image")
     fake = _np(fake_image, np.float32, "fake_image")
-    if real.shape != fake.shape or real.ndim != 4 or real.shape[-1] not in (3, 4):
-        raise ValueError("real_image and fake_image must both be (B,H,W,3|4)")
-    b, h, w, ch = real.shape
+    real = real_image.numpy() if hasattr(real_image, "numpy") and not isinstance(real_image, np.ndarray) else np.asarray(real_image)
     dom = tf_linspace(-3.0, 3.0, int(size))
     ssum = C.c_double(0.0)
     ctx = ctx or default_context(device)
+    if real.dtype == np.uint8:
+        # sprites straight from the PNG decoder: blacken + normalise happen on the device (dataset_utils.py:66-77)
+        real = np.ascontiguousarray(real)
+        if real.shape != fake.shape or real.ndim != 4 or real.shape[-1] != 4:
+            raise ValueError("uint8 real_image and float32 fake_image must both be (B,H,W,4)")
+        b, h, w, _ = real.shape
+        _lib.call("ph_host_hist_begin_u8real", ctx._h, real.ctypes.data, fake.ctypes.data, b, h * w, dom.ctypes.data,
+                  int(size), _method_id(method), _sigma_sqr(sigma), EPSILON, _lib.IMPLS[impl], C.byref(ssum))
+        return float(ssum.value)
+    real = _np(real, np.float32, "real_image")
+    if real.shape != fake.shape or real.ndim != 4 or real.shape[-1] not in (3, 4):
+        raise ValueError("real_image and fake_image must both be (B,H,W,3|4)")
+    b, h, w, ch = real.shape
     _lib.call("ph_host_hist_begin", ctx._h, real.ctypes.data, fake.ctypes.data, b, h * w, ch, dom.ctypes.data,
               int(size), _method_id(method), _sigma_sqr(sigma), EPSILON, _lib.IMPLS[impl], C.byref(ssum))
     return float(ssum.value)

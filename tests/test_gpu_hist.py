@@ -238,3 +238,30 @@ def test_dedup_forward_matches_dense(H, cuda, sprites):
     l2 = H.histogram_loss(x, f2, dedup_real=False); l2.backward()
     assert abs(float(l1.detach()) - float(l2.detach())) / float(l2.detach()) < 1e-6
     assert ho.rel_l2(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < 1e-5
+
+
+def test_u8_loader_prep_and_u8_host_path(cuda, sprites):
+    """f2: uint8 sprites in, blacken + normalise fused on the device."""
+    from palette_and_histo_gan_b200 import dataset_utils as D, hostapi
+    from oracle.palette_oracle import blacken_transparent_pixels
+
+    raw = sprites["right"][:6].copy()
+    raw[0, :4, :4] = [200, 10, 30, 0]       # non-black transparent pixels must be blackened
+    out = D.load_image(torch.from_numpy(raw).to(cuda)).cpu().numpy()
+    ref = normalize(blacken_transparent_pixels(raw).astype(np.float32))
+    assert np.array_equal(out, ref)
+    out255 = D.load_image(torch.from_numpy(raw).to(cuda), should_normalize=False).cpu().numpy()
+    assert np.array_equal(out255, blacken_transparent_pixels(raw).astype(np.float32))
+    # host path with uint8 real images equals the float path
+    rng = np.random.default_rng(5)
+    fake = np.tanh(rng.standard_normal(raw.shape)).astype(np.float32)
+    ctx = hostapi.HostContext(0)
+    s_u8 = hostapi.histogram_loss_begin(raw, fake, ctx=ctx)
+    l_u8, g_u8 = hostapi.histogram_loss_finish(s_u8, 6, np.empty_like(fake), ctx=ctx)
+    s_f = hostapi.histogram_loss_begin(ref, fake, ctx=ctx)
+    l_f, g_f = hostapi.histogram_loss_finish(s_f, 6, np.empty_like(fake), ctx=ctx)
+    ctx.close()
+    assert abs(s_u8 - s_f) / s_f < 1e-6 and abs(l_u8 - l_f) / l_f < 1e-6
+    assert ho.rel_l2(g_u8, g_f) < 1e-6
+    oracle = ho.hist_loss_and_grad_f64(ref, fake)
+    assert abs(l_u8 - oracle["loss"]) / oracle["loss"] < LOSS_TOL and ho.rel_l2(g_u8, oracle["grad"]) < GRAD_TOL
