@@ -4,7 +4,7 @@ import torch
 from palette_and_histo_gan_b200 import histogram as H, _lib
 dev = torch.device("cuda:0")
 def ev(): return torch.cuda.Event(enable_timing=True)
-for B in (296, 1184, 4096):
+for B in (296, 512, 1024, 4096):
     real = torch.tanh(torch.randn(B, 64, 64, 4, device=dev)); fake = torch.tanh(torch.randn(B, 64, 64, 4, device=dev))
     dom = H.histogram_domain(64, dev); s2 = H._sigma_sqr(0.02)
     for impl in (1, 2):
