@@ -28,7 +28,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "histogram-loss fwd+bwd images/s at 64x64"
-GLOBAL_BATCH = 4096  # cfgC
+GLOBAL_BATCH = int(os.environ.get("PH_BENCH_BATCH", "4096"))  # cfgC (override only for tuning runs)
 HW = 64
 BINS = 64
 PALETTE_BATCH = 256  # cfgB

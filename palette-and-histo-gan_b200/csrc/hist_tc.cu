@@ -20,6 +20,8 @@
 // error grows with the chain length (measured 8e-6 for 4096 pixels in one chain, ~1e-6 for 1024).
 // Chains are cut at 1024 pixels and summed in fp32 in a shared-memory accumulator; when a CTA owns a
 // whole image the normaliser D and H/D are produced in the same kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "hist_internal.cuh"
 #include "tc_ptx.cuh"
@@ -57,11 +59,13 @@ struct PxSlot {
 
 struct Smem {
   alignas(128) unsigned char b[NS][B_STAGE_BYTES];  // 144 KB
-  float acc[3][BINS][BINS];                         // [c][j][i] running fp32 sum over chains, 48 KB
+  float acc[3][BINS][BINS + 1];                     // [c][j][i] running fp32 sum over chains; rows padded to 65
+                                                    // floats so both the bin-major drain and the j-major
+                                                    // write-out are free of bank conflicts
   float4 xbuf[4][2][3][2][32];                      // [pair][direction][channel][quad of 4 px][lane], 24 KB
   PxSlot px[PR];
   float dom[BINS];
-  double red[8];
+  float red[8];
   alignas(8) uint64_t px_full[PR], px_empty[PR], ab_full[NS], ab_empty[NS], d_full, d_empty;
   uint32_t tmem_base;
 };
@@ -69,16 +73,20 @@ struct Smem {
 struct Params {
   const float* image;
   const float* dom;
-  float* partial;  // (B, splits, 3, 64, 64) raw sums, used when splits > 1
-  float* hist;     // (B, 64, 64, 3) normalised, written directly when splits == 1
+  float* partial;  // (B - n_whole, splits, 3, 64, 64) raw sums of the sliced ("tail") images
+  float* hist;     // (B, 64, 64, 3) normalised, written directly for whole-image items
   float* denom;    // (B)
   const float4* ulist;  // optional (B, DEDUP_MAX): unique colours (r,g,b,count) of each image, or NULL
   const int* nunique;   // optional (B): number of unique colours, < 0 = image not de-duplicated
   int64_t npix;
   int channels;
+  // Work items: images [0, n_whole) are contracted whole by one CTA (normalisation fused); the remaining
+  // "tail" images are cut into `splits` pixel slices so that the last, partial wave of images does not leave
+  // most SMs idle (their raw sums go to `partial` and are normalised by the finalise kernel).
+  int64_t n_whole;
   int splits;
   int64_t px_per_split;
-  int64_t items;  // B * splits
+  int64_t items;  // n_whole + (B - n_whole) * splits
   float inv_sigma_sqr;
   float eps;
 };
@@ -89,17 +97,30 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Pixel range of a work item.  A de-duplicated image is a list of (colour, multiplicity) entries: the
 // histogram is linear in the pixels, so identical pixels are contracted once with weight count*Iy.
-struct ItemRange { uint32_t px0, px1; bool dedup; };  // 32-bit: keeps the role loops in the uniform datapath
-__device__ __forceinline__ ItemRange item_range(const Params& p, int64_t b, int64_t split) {
+struct ItemRange {  // 32-bit pixel range: keeps the role loops in the uniform datapath
+  int64_t b;        // image
+  int64_t pidx;     // slice index in `partial` (tail items)
+  uint32_t px0, px1;
+  bool dedup, whole;
+};
+__device__ __forceinline__ ItemRange item_range(const Params& p, int64_t w) {
   ItemRange r;
-  if (p.nunique != nullptr) {
-    // broadcast from lane 0: lets ptxas prove the loop bounds derived from it warp-uniform
-    const int nu = __shfl_sync(0xffffffffu, __ldg(p.nunique + b), 0);
-    if (nu >= 0) { r.px0 = 0; r.px1 = (uint32_t)nu; r.dedup = true; return r; }
+  r.dedup = false;
+  if (w < p.n_whole) {
+    r.b = w; r.pidx = 0; r.whole = true;
+    r.px0 = 0; r.px1 = (uint32_t)p.npix;
+    if (p.nunique != nullptr) {
+      // broadcast from lane 0: lets ptxas prove the loop bounds derived from it warp-uniform
+      const int nu = __shfl_sync(0xffffffffu, __ldg(p.nunique + w), 0);
+      if (nu >= 0) { r.px1 = (uint32_t)nu; r.dedup = true; }
+    }
+    return r;
   }
+  const int64_t t = w - p.n_whole;
+  const int64_t split = t % p.splits;
+  r.b = p.n_whole + t / p.splits; r.pidx = t; r.whole = false;
   r.px0 = (uint32_t)split * (uint32_t)p.px_per_split;
   r.px1 = min(r.px0 + (uint32_t)p.px_per_split, (uint32_t)p.npix);
-  r.dedup = false;
   return r;
 }
 
@@ -134,8 +155,8 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
     const int px_own = sub * 16 + role * 8;  // the 8 pixels this warp evaluates
     uint32_t it = 0, chain = 0;
     for (int64_t w = first; w < p.items; w += step) {
-      const int64_t b = w / p.splits, split = w % p.splits;
-      const ItemRange ir = item_range(p, b, split);
+      const ItemRange ir = item_range(p, w);
+      const int64_t b = ir.b;
       const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
       for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
         const int slot = it % PR, stage = it % NS;
@@ -241,25 +262,24 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
         // ---- item epilogue: all 8 warps, normalise (whole image) or emit the raw partial ----
         named_bar_sync(5, A_WARPS * 32);
         const int t = tid;  // 0..255
-        float* accf = &S.acc[0][0][0];
-        if (p.splits == 1) {
-          double s = 0.0;
-          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) s += (double)accf[e];
+        if (ir.whole) {
+          float s = 0.f;
+          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
           s = warp_sum(s);
           if (lane == 0) S.red[warp] = s;
           named_bar_sync(5, A_WARPS * 32);
-          double tot = 0.0;
+          float d = 0.f;
 #pragma unroll
-          for (int k = 0; k < A_WARPS; ++k) tot += S.red[k];
-          const float d = (float)tot;
+          for (int k = 0; k < A_WARPS; ++k) d += S.red[k];
           if (t == 0) p.denom[b] = d;
+          const float inv_d = 1.0f / d;
           float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
           for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
             const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-            dst[e] = S.acc[c][j][i] / d;
+            dst[e] = S.acc[c][j][i] * inv_d;
           }
         } else {
-          float* dst = p.partial + ((b * p.splits + split) * 3) * (int64_t)(BINS * BINS);
+          float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
           for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
             const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
             dst[e] = S.acc[c][j][i];
@@ -302,8 +322,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     const int me = warp - PX_WARP0;
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
-      const int64_t b = w / p.splits, split = w % p.splits;
-      const ItemRange ir = item_range(p, b, split);
+      const ItemRange ir = item_range(p, w);
+      const int64_t b = ir.b;
       const uint32_t px0 = ir.px0, px1 = ir.px1;
       for (uint32_t base = px0; base < px1; base += KB, ++it) {
         if ((int)(it % PXW) != me) continue;
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     const uint32_t row_off = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);  // hi row j; lo row j + 64 is +1024
     uint32_t it = 0;
     for (int64_t w = first; w < p.items; w += step) {
-      const ItemRange ir = item_range(p, w / p.splits, w % p.splits);
+      const ItemRange ir = item_range(p, w);
       for (uint32_t base = ir.px0; base < ir.px1; base += KB, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
@@ -392,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     // inside the stage loop was enough to push every operand through R2UR moves).
     uint32_t stage = 0, phase = 0, chain_par = 0;
     for (int64_t w = first; w < p.items; w += step) {
-      const ItemRange ir = item_range(p, w / p.splits, w % p.splits);
+      const ItemRange ir = item_range(p, w);
       const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
       for (uint32_t kb0 = 0; kb0 < nkb; kb0 += CHAIN_KB) {
         const uint32_t n_this = min((uint32_t)CHAIN_KB, nkb - kb0);
@@ -528,26 +548,44 @@ bool tc_supported(int64_t npix, int bins, int method) {
 
 // Pixel slices per image: 1 (whole image per CTA, normalisation fused) once the batch fills the SMs,
 // otherwise enough slices to occupy them; the slices are summed by the finalise kernel.
-static int tc_fwd_splits(int64_t batch, int64_t npix, bool dedup) {
-  const int64_t sms = cached_sm_count();
-  const int64_t max_s = ceil_div(npix, 8 * fwdtc::KB);
-  (void)dedup;
-  if (batch >= sms) return 1;  // whole images per CTA: fused normalisation (slicing measured slower: 0.60 vs 0.47 ms @512)
-  int64_t s = ceil_div(2 * sms, batch);
-  if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  return (int)s;
-}
-
 static size_t dedup_bytes(int64_t batch) {
   return align_up((size_t)batch * fwdtc::DEDUP_MAX * sizeof(float4), 256) + align_up((size_t)batch * sizeof(int), 256);
 }
 
+struct FwdPlan { int64_t n_whole; int splits; };
+
+// Which images a CTA contracts whole (normalisation fused) and how the rest are sliced.
+static FwdPlan tc_fwd_plan(int64_t batch, int64_t npix, bool dedup) {
+  const int64_t sms = cached_sm_count();
+  const int64_t max_s = ceil_div(npix, 8 * fwdtc::KB);
+  FwdPlan pl{batch, 1};
+  if (batch < sms) {  // few images: slice all of them to occupy the SMs
+    int64_t s = ceil_div(2 * sms, batch);
+    if (s > max_s) s = max_s;
+    if (s > 1) { pl.n_whole = 0; pl.splits = (int)s; }
+    return pl;
+  }
+  if (dedup) return pl;  // de-duplicated images are a stage or two each
+  static const bool tail_off = getenv("PH_FWD_TAIL") && atoi(getenv("PH_FWD_TAIL")) == 0;  // tuning knob
+  if (tail_off) return pl;
+  const int64_t n_tail = batch % sms;
+  if (n_tail == 0) return pl;
+  // the last partial wave: n_tail whole images keep sms - n_tail SMs idle for one image time; slices shorten it
+  int best = 1;
+  double best_cost = 1.0;
+  for (int sidx = 2; sidx <= 4 && sidx <= max_s; ++sidx) {
+    const double cost = (double)ceil_div(n_tail * sidx, sms) / sidx + 0.08;  // + finalise pass and per-item overhead
+    if (cost < best_cost) { best_cost = cost; best = sidx; }
+  }
+  if (best > 1) { pl.n_whole = batch - n_tail; pl.splits = best; }
+  return pl;
+}
+
 size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins) {
   if (bins != 64) return 0;
-  const int splits = tc_fwd_splits(batch, npix, false);
-  size_t fwd = splits > 1 ? (size_t)batch * splits * 3 * bins * bins * sizeof(float) : 0;
-  if (tc_fwd_splits(batch, npix, true) == 1 && dedup_bytes(batch) > fwd) fwd = dedup_bytes(batch);
+  const FwdPlan pl = tc_fwd_plan(batch, npix, false);
+  size_t fwd = (size_t)(batch - pl.n_whole) * pl.splits * 3 * bins * bins * sizeof(float);
+  if (tc_fwd_plan(batch, npix, true).n_whole == batch && dedup_bytes(batch) > fwd) fwd = dedup_bytes(batch);
   const size_t bwd = (size_t)batch * 3 * bins * bins * sizeof(float);
   return align_up(fwd > bwd ? fwd : bwd, 256) + 256;
 }
@@ -569,12 +607,14 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.denom = denom;
   p.npix = npix;
   p.channels = channels;
-  p.splits = tc_fwd_splits(batch, npix, dedup);
+  const FwdPlan pl = tc_fwd_plan(batch, npix, dedup);
+  p.n_whole = pl.n_whole;
+  p.splits = pl.splits;
   p.px_per_split = ceil_div(ceil_div(npix, p.splits), KB) * KB;
-  p.items = batch * p.splits;
+  p.items = p.n_whole + (batch - p.n_whole) * p.splits;
   p.inv_sigma_sqr = 1.0f / sigma_sqr;
   p.eps = eps;
-  if (dedup && p.splits == 1) {
+  if (dedup && p.n_whole == batch) {
     // unique colours + multiplicities per image (only worth it when a CTA owns whole images)
     float4* ulist = static_cast<float4*>(workspace);
     int* nunique = reinterpret_cast<int*>(static_cast<char*>(workspace) +
@@ -597,8 +637,9 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     hist_fwd_tc_kernel<PH_METHOD_RBF><<<grid, THREADS, smem, st>>>(p);
   }
   PH_LAUNCH_OK("hist_fwd_tc_kernel");
-  if (p.splits > 1) {
-    launch_finalize(p.partial, p.splits, 3, bins, 1, hist, denom, batch, st);
+  if (p.n_whole < batch) {
+    launch_finalize(p.partial, p.splits, 3, bins, 1, hist + p.n_whole * (int64_t)(3 * bins * bins), denom + p.n_whole,
+                    batch - p.n_whole, st);
     PH_LAUNCH_OK("hist_finalize_kernel");
   }
   return PH_OK;
