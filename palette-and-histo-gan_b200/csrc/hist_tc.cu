@@ -176,7 +176,7 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
           uu[c][0] = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own]);
           uu[c][1] = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own + 4]);
         }
-        mbar_arrive(&S.px_empty[slot]);
+        mbar_arrive_warp(&S.px_empty[slot]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const ulonglong2 ua = uu[c][0], ub = uu[c][1];
@@ -218,7 +218,7 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
         }
         tmem_st_wait();
         tc_fence_before_sync();
-        mbar_arrive(&S.ab_full[stage]);
+        mbar_arrive_warp(&S.ab_full[stage]);
 
         const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
         if (!chain_end) continue;
@@ -256,7 +256,7 @@ __device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t t
           }
         }
         tc_fence_before_sync();
-        mbar_arrive(&S.d_empty);
+        mbar_arrive_warp(&S.d_empty);
         if (kb + 1 != nkb) continue;
 
         // ---- item epilogue: all 8 warps, normalise (whole image) or emit the raw partial ----
@@ -299,10 +299,11 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 32); mbar_init(&S.px_empty[i], (A_WARPS + B_WARPS) * 32); }
-    for (int i = 0; i < NS; ++i) { mbar_init(&S.ab_full[i], (A_WARPS + B_WARPS) * 32); mbar_init(&S.ab_empty[i], 1); }
+    // producer/consumer barriers count WARPS (mbar_arrive_warp), the tcgen05.commit ones count 1
+    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 1); mbar_init(&S.px_empty[i], A_WARPS + B_WARPS); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&S.ab_full[i], A_WARPS + B_WARPS); mbar_init(&S.ab_empty[i], 1); }
     mbar_init(&S.d_full, 1);
-    mbar_init(&S.d_empty, A_WARPS * 32);
+    mbar_init(&S.d_empty, A_WARPS);
     fence_mbar_init();
   }
   if (tid < BINS) S.dom[tid] = p.dom[tid];
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         o.u[1][lane] = -d_rg; o.v[1][lane] = d_gb;
         o.u[2][lane] = -d_rb; o.v[2][lane] = -d_gb;
         o.iy[lane] = valid ? iy * mult : 0.f;  // masked pixels contribute nothing (A operand = 0)
-        mbar_arrive(&S.px_full[slot]);
+        mbar_arrive_warp(&S.px_full[slot]);
       }
     }
   } else if (warp < A_WARPS) {
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         for (int c = 0; c < 3; ++c)
 #pragma unroll
           for (int q4 = 0; q4 < 2; ++q4) vv[c][q4] = *reinterpret_cast<const ulonglong2*>(&in.v[c][(part * 2 + q4) * 4]);
-        mbar_arrive(&S.px_empty[slot]);
+        mbar_arrive_warp(&S.px_empty[slot]);
         mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(&S.ab_full[stage]);
+        mbar_arrive_warp(&S.ab_full[stage]);
       }
     }
   } else if (warp == MMA_WARP) {
