@@ -289,33 +289,67 @@ __global__ void __launch_bounds__(256) hist_bwd_prep_kernel(
     int transposed, float* __restrict__ ghat) {
   __shared__ double scratch[32];
   const int64_t b = blockIdx.x;
-  const int64_t plane = (int64_t)bins * bins, per_image = plane * 3;
-  const float* hp = hist_pred + b * per_image;
+  const int plane = bins * bins, per_image = plane * 3;  // 32-bit indexing inside an image
+  const float* hp = hist_pred + b * (int64_t)per_image;
   float coef = 0.f;
   if (grad_hist == nullptr) {
     // dL/dHp = (1 - sqrt(Ht/Hp)) / (2 sqrt2 B sqrt(S));  S == 0 gives inf/NaN exactly like TF's 0*inf
     coef = (float)((double)(loss_scale ? *loss_scale : 1.0f) / (2.0 * 1.41421356237309504880 * global_batch * sqrt(*ssum)));
   }
-  const float* gh = grad_hist ? grad_hist + b * per_image : nullptr;
-  const float* ht = hist_true ? hist_true + b * per_image : nullptr;
+  const float* gh = grad_hist ? grad_hist + b * (int64_t)per_image : nullptr;
+  const float* ht = hist_true ? hist_true + b * (int64_t)per_image : nullptr;
+  // pass 1: g and sum(g * Hp); g stays in registers when the image is small enough (64 bins: 48 per thread)
+  constexpr int KEEP = 48;
+  float kept[KEEP];
+  const bool keep = per_image <= KEEP * 256;
   double dot = 0.0;
-  for (int64_t e = threadIdx.x; e < per_image; e += blockDim.x) {
-    const float h = hp[e];
-    const float g = gh ? gh[e] : coef * (1.0f - sqrtf(ht[e] / h));
-    dot += (double)g * (double)h;
+  if (keep) {
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) {
+      const int e = threadIdx.x + k * 256;
+      float g = 0.f;
+      if (e < per_image) {
+        const float h = __ldg(hp + e);
+        g = gh ? __ldg(gh + e) : coef * (1.0f - sqrtf(__ldg(ht + e) / h));
+        part = fmaf(g, h, part);
+      }
+      kept[k] = g;
+    }
+    dot = (double)part;
+  } else {
+    for (int e = threadIdx.x; e < per_image; e += 256) {
+      const float h = hp[e];
+      const float g = gh ? gh[e] : coef * (1.0f - sqrtf(ht[e] / h));
+      dot += (double)g * (double)h;
+    }
   }
   dot = block_sum(dot, scratch);
   const float fdot = (float)dot;
   const float inv_d = 1.0f / denom[b];
-  float* out = ghat + b * per_image;
-  for (int64_t e = threadIdx.x; e < per_image; e += blockDim.x) {
-    const float h = hp[e];
-    const float g = gh ? gh[e] : coef * (1.0f - sqrtf(ht[e] / h));
-    const int64_t ij = e / 3;
-    const int c = (int)(e % 3);
-    const int64_t i = ij / bins, j = ij % bins;
-    // transposed: [c][j][i] (CUDA-core kernel); else [c][i][j] (K-major B operand of the tensor-core kernel)
-    out[c * plane + (transposed ? j * bins + i : i * bins + j)] = (g - fdot) * inv_d;
+  float* out = ghat + b * (int64_t)per_image;
+  // pass 2: G^ = (g - dot) / D, channel-planar.  transposed: [c][j][i] (CUDA-core kernel);
+  // else [c][i][j] (K-major B operand of the tensor-core kernel)
+  if (keep) {
+#pragma unroll
+    for (int k = 0; k < KEEP; ++k) {
+      const int e = threadIdx.x + k * 256;
+      if (e < per_image) {
+        const int ij = e / 3, c = e - ij * 3;
+        int o = ij;
+        if (transposed) { const int i = ij / bins, j = ij - i * bins; o = j * bins + i; }
+        out[c * plane + o] = (kept[k] - fdot) * inv_d;
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < per_image; e += 256) {
+      const float h = hp[e];
+      const float g = gh ? gh[e] : coef * (1.0f - sqrtf(ht[e] / h));
+      const int ij = e / 3, c = e - ij * 3;
+      int o = ij;
+      if (transposed) { const int i = ij / bins, j = ij - i * bins; o = j * bins + i; }
+      out[c * plane + o] = (g - fdot) * inv_d;
+    }
   }
 }
 
