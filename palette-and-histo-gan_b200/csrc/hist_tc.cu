@@ -89,6 +89,11 @@ struct Params {
   int64_t items;  // n_whole + (B - n_whole) * splits
   float inv_sigma_sqr;
   float eps;
+  int debug_skip_mma;  // tuning experiments only (env PH_DEBUG_SKIP_MMA): bit 0 = issue no MMA, bit 1 = B warps
+                       // generate nothing.  Result (B200): skipping all MMAs does not shorten the kernel and
+                       // skipping B saves 20 %: at 64 bins the A-operand chain (px wait -> weights -> hand-over
+                       // barrier -> tcgen05.st -> wait::st -> arrive) and shared-memory bandwidth (145 KB per
+                       // 32-pixel stage = 1 130 cycles) bound the forward, not the tensor pipe.
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -384,6 +389,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
           for (int q4 = 0; q4 < 2; ++q4) vv[c][q4] = *reinterpret_cast<const ulonglong2*>(&in.v[c][(part * 2 + q4) * 4]);
         mbar_arrive_warp(&S.px_empty[slot]);
         mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
+        if (!(p.debug_skip_mma & 2))
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           unsigned char* tile = &S.b[stage][c * B_CH_BYTES];
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
               const uint32_t b_hi = dstage + ((c * B_CH_BYTES + ks * 2 * B_KQ_BYTES) >> 4);
               const uint32_t b_lo = b_hi + (1024 >> 4);
               const uint32_t acc0 = (k == 0 && ks == 0) ? 0u : 1u;
-              if (elect_one_sync()) {
+              if (!(p.debug_skip_mma & 1) && elect_one_sync()) {
                 mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_hi, dhi, IDESC, acc0);
                 mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_lo, dhi, IDESC, 1u);
               }
@@ -615,6 +621,8 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.items = p.n_whole + (batch - p.n_whole) * p.splits;
   p.inv_sigma_sqr = 1.0f / sigma_sqr;
   p.eps = eps;
+  static const int skip_mma = getenv("PH_DEBUG_SKIP_MMA") ? atoi(getenv("PH_DEBUG_SKIP_MMA")) : 0;
+  p.debug_skip_mma = skip_mma;
   if (dedup && p.n_whole == batch) {
     // unique colours + multiplicities per image (only worth it when a CTA owns whole images)
     float4* ulist = static_cast<float4*>(workspace);
