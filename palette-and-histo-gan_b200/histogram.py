@@ -170,20 +170,49 @@ class _HellingerFn(torch.autograd.Function):
 
 
 class _HistogramLossFn(torch.autograd.Function):
-    """fwd(real) + fwd(fake) + Hellinger, backward to the fake image only (pix2pix_model.py:243-245)."""
+    """fwd(real) + fwd(fake) + Hellinger, backward to the fake image only (pix2pix_model.py:243-245).
+
+    Sharded batches: the only exchange is the all-reduce of the sum of squares S.  The gradient is
+    (S-independent per-pixel terms) / (2*sqrt2*B*sqrt(S)), so the backward kernels are launched right away
+    with this rank's S while the all-reduce is in flight, and the result is corrected by sqrt(S_local/S_global)
+    in the single elementwise pass that also applies the upstream scalar: the NVLink latency of the
+    collective hides behind the contraction instead of idling the GPU."""
 
     @staticmethod
     def forward(ctx, real, fake, dom, method_id, sigma_sqr, impl, group, global_batch, dedup_real):
         hist_real, _ = _forward(real, dom, method_id, sigma_sqr, impl | (DEDUP_FLAG if dedup_real else 0))
         hist_fake, denom_fake = _forward(fake, dom, method_id, sigma_sqr, impl)
         ssum = _ssum(hist_real, hist_fake)
+        sharded = group is not None and group is not False
+        overlap = False
+        if sharded and ctx.needs_input_grad[1]:
+            import torch.distributed as dist
+
+            pg = None if group is True else group
+            # worth one extra elementwise pass over the gradient once the collective's latency exceeds it
+            overlap = dist.get_world_size(pg) >= OVERLAP_MIN_WORLD
+        if overlap:
+            gb = int(global_batch) if global_batch is not None else real.shape[0] * dist.get_world_size(pg)
+            ssum_global = ssum.clone()
+            work = dist.all_reduce(ssum_global, op=dist.ReduceOp.SUM, group=pg, async_op=True)
+            grad = _backward(fake, dom, method_id, sigma_sqr, impl, hist_fake, denom_fake, hist_true=hist_real,
+                             ssum=ssum, global_batch=gb, loss_scale=None)  # overlaps the collective
+            work.wait()
+            corr = torch.sqrt(ssum / ssum_global).to(torch.float32)
+            ctx.save_for_backward(grad, corr)
+            ctx.eager = True
+            return _finish(ssum_global, gb)
         gb = _reduce_over_ranks(ssum, real.shape[0], group, global_batch)
         ctx.save_for_backward(fake, dom, hist_real, hist_fake, denom_fake, ssum)
         ctx.conf = (method_id, sigma_sqr, impl, gb)
+        ctx.eager = False
         return _finish(ssum, gb)
 
     @staticmethod
     def backward(ctx, grad_loss):
+        if ctx.eager:
+            grad, corr = ctx.saved_tensors
+            return None, grad * (grad_loss.to(torch.float32) * corr), None, None, None, None, None, None, None
         fake, dom, hist_real, hist_fake, denom_fake, ssum = ctx.saved_tensors
         method_id, sigma_sqr, impl, gb = ctx.conf
         scale = grad_loss.to(torch.float32).contiguous()
@@ -196,6 +225,7 @@ class _HistogramLossFn(torch.autograd.Function):
 # public API — reference signatures
 # ------------------------------------------------------------------------------------------------
 DEDUP_FLAG = 8  # PH_IMPL_DEDUP
+OVERLAP_MIN_WORLD = 4  # ranks from which the all-reduce of S is overlapped with the backward kernels
 
 
 def calculate_rgbuv_histogram(image_batch, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",

@@ -265,3 +265,39 @@ def test_u8_loader_prep_and_u8_host_path(cuda, sprites):
     assert ho.rel_l2(g_u8, g_f) < 1e-6
     oracle = ho.hist_loss_and_grad_f64(ref, fake)
     assert abs(l_u8 - oracle["loss"]) / oracle["loss"] < LOSS_TOL and ho.rel_l2(g_u8, oracle["grad"]) < GRAD_TOL
+
+
+def test_sharded_path_single_rank_nccl(H, cuda):
+    """The sharded code path (async all-reduce of S overlapped with the backward, gradient corrected by
+    sqrt(S_local/S_global)) run with a one-rank NCCL group must reproduce the unsharded result; with a
+    fake global batch it must match the oracle evaluated with the whole-batch scalars."""
+    import os
+    import socket
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=cuda)
+    try:
+        H.OVERLAP_MIN_WORLD = 1  # force the overlapped path with a single rank
+        rng = np.random.default_rng(31)
+        real = np.tanh(rng.standard_normal((4, 32, 32, 4))).astype(np.float32)
+        fake = np.tanh(rng.standard_normal((4, 32, 32, 4))).astype(np.float32)
+        ref = ho.hist_loss_and_grad_f64(real, fake)
+        f = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+        loss = H.histogram_loss(torch.from_numpy(real).to(cuda), f, group=True)
+        (2.0 * loss).backward()
+        assert abs(float(loss.detach()) - ref["loss"]) / ref["loss"] < LOSS_TOL
+        assert ho.rel_l2(f.grad.cpu().numpy(), 2.0 * ref["grad"]) < GRAD_TOL
+        # as one shard of a batch of 8 whose other half has the same sum of squares: global S = 2 S_local
+        f2 = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+        loss8 = H.histogram_loss(torch.from_numpy(real).to(cuda), f2, group=True, global_batch=8)
+        loss8.backward()
+        sh = ho.hist_loss_and_grad_f64(real, fake, global_batch=8, global_ssum=ref["ssum"])
+        assert abs(float(loss8.detach()) - sh["loss"]) / sh["loss"] < LOSS_TOL
+        assert ho.rel_l2(f2.grad.cpu().numpy(), sh["grad"]) < GRAD_TOL
+    finally:
+        H.OVERLAP_MIN_WORLD = 4
+        dist.destroy_process_group()
