@@ -308,7 +308,11 @@ def run_ours(args, rank, world, local_rank):
     roofline = {
         "bound": "tensor", "kernel": "hist backward (prologue + contraction kernel)",
         "achieved": bwd_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": bwd_tflops / tf32_peak,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of hist_bwd_tc_kernel, one `ncu --set full` capture at 4096
+        # images per launch (profiles/r1_prof_hist_final_raw.csv: 469.9 MB + 240.5 MB), scaled to this rank's share
+        "traffic": 710.4e6 * local_b / 4096.0,
+        "traffic_source": "profiles/r1_prof_hist_final_raw.csv (ncu, 4096 images/launch), scaled by local batch",
+        "algorithmic_bytes": float(local_b) * npix * 4 * 4 * 2 + float(local_b) * 3 * BINS * BINS * 4,
         "peak_source": f"{peaks['source']}: bf16_tflops_sustained/2 (dense TF32 is half of bf16)",
         "frac_of_3xtf32_ceiling": bwd_tflops / (tf32_peak / 3.0),
         "forward": {"achieved": fwd_tflops, "frac": fwd_tflops / tf32_peak},
@@ -454,10 +458,12 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
         "ms": {"extract+index+one_hot": ms_full, "extract+index": ms_index, "one_hot": ms_onehot},
         "gpu_launches_per_step": int(launches),
         "roofline": {"bound": "hbm", "kernel": "one_hot_kernel", "achieved": oh_gbs, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": oh_gbs / peaks["hbm_gbs"], "traffic": None,
+                     "unit": "GB/s", "frac": oh_gbs / peaks["hbm_gbs"],
+                     # ncu --set full, profiles/r1_prof_palette_final_raw.csv: 4.3 MB read + 1018 MB written per launch
+                     "traffic": 1022.3e6, "algorithmic_bytes": float(oh_px) * (4 + 1024),
                      "peak_source": peaks["source"],
                      "extract+index": {"achieved": idx_gbs, "frac": idx_gbs / peaks["hbm_gbs"],
-                                       "note": "36 B/px over 3 launches of ~2 Mpix: launch-latency bound"}},
+                                       "note": "36 B/px, one fused launch of 256 CTAs (one per pair) over ~2 Mpix: latency bound"}},
         "e2e": {"value": npx / e2e_s / 1e9, "unit": "Gpix/s", "h2d_bytes_per_step": int(2 * src_np.nbytes),
                 "d2h_bytes_per_step": int(npx * 4 + PALETTE_BATCH * (256 * 16 + 4)),
                 "api": "hostapi.load_indexed_images -> ph_host_load_indexed_images (no one-hot download)"},
