@@ -593,7 +593,7 @@ size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins) {
   const FwdPlan pl = tc_fwd_plan(batch, npix, false);
   size_t fwd = (size_t)(batch - pl.n_whole) * pl.splits * 3 * bins * bins * sizeof(float);
   if (tc_fwd_plan(batch, npix, true).n_whole == batch && dedup_bytes(batch) > fwd) fwd = dedup_bytes(batch);
-  const size_t bwd = (size_t)batch * 3 * bins * bins * sizeof(float);
+  const size_t bwd = tc_bwd_workspace_bytes(batch);
   return align_up(fwd > bwd ? fwd : bwd, 256) + 256;
 }
 

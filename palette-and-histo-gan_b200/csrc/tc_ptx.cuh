@@ -55,17 +55,45 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Same with an explicit suspend-time hint: the thread sleeps in hardware until the phase completes or `ns`
+// nanoseconds have passed.  Without the hint try_wait returns after a few tens of cycles, and the polling loops
+// of the waiting warps (pixel and B-operand warps run far ahead of their consumers) took ~30 % of all issued
+// instructions of the forward kernel (ncu source page), competing with the producer warps for issue slots.
+__device__ __forceinline__ bool mbar_try_wait_for(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_for(bar, parity, 200000u)) {
     if (clock64() - t0 > 4000000000ll) {
       printf("palhist: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
+}
+
+// ---- bulk asynchronous copy global -> shared (TMA, 1-D): completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---- proxies / fences ---------------------------------------------------------------------------
@@ -113,6 +141,11 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
          | ((uint32_t)(m >> 4) << 24); // m_dim
 }
 
+// kind::f16 instruction descriptor: fp32 accumulate, fp16 A and B (format 0), both K-major, dense.
+__host__ __device__ constexpr uint32_t idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 // ---- MMA: D[tmem] (+)= A[tmem] * B[smem], issued by ONE thread ---------------------------------
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -133,6 +166,19 @@ __device__ __forceinline__ void mma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem, u
       "setp.ne.b32 p, %5, 0;\n\t"
       "mov.b64 bd, {%2, %3};\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], bd, %4, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// kind::f16, K = 16 per instruction.  A in TMEM: lane = row, each 32-bit column holds two consecutive K
+// elements (low half = even k); B in shared memory: core matrix = 8 rows x 8 halfs (tools/f16_layout_test.cu).
+__device__ __forceinline__ void mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t b_desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
       :
       : "r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -237,6 +283,27 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   return r;
 }
 constexpr unsigned long long TF32_MASK2 = 0xFFFFE000FFFFE000ull;
+
+// ---- fp16 operand split: w (already scaled into fp16's range) = hi + lo, both fp16 ----------------------
+// hi = w truncated to 11 significant bits (a mask: exactly representable in fp16, so the conversion is exact),
+// lo = fp16(w - hi): hi.hi + hi.lo + lo.hi recovers the fp32 product to ~2^-21 like the tf32 split does, at
+// twice the tensor-core rate (K = 16 per instruction) and half the operand bytes.
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ void split_f16x2(f32x2 w, f32x2 mone2, uint32_t& hi, uint32_t& lo) {
+  const f32x2 h = w & TF32_MASK2;
+  const f32x2 l = fma2(h, mone2, w);
+  hi = cvt_f16x2(lo_of(h), hi_of(h));
+  lo = cvt_f16x2(lo_of(l), hi_of(l));
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 __device__ __forceinline__ float fast_rcp(float x) {
   float r;
