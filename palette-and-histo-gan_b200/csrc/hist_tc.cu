@@ -1,22 +1,26 @@
 // RGB-uv histogram, tensor-core engine (tcgen05, sm_100a): the Ku^T.Kv contraction over pixels
-// (histogram.py:29-30) as kind::tf32 MMAs with fp32 emulation by operand splitting
-// (w = hi + lo, both tf32; hi.hi + hi.lo + lo.hi + lo.lo accumulated in fp32 in TMEM), fused with the
+// (histogram.py:29-30) as kind::f16 MMAs with fp32 emulation by operand splitting, fused with the
 // per-image normalisation (histogram.py:75-79).
+//
+// Emulation: every weight is generated directly in a power-of-two scaled form that fits fp16's range and
+// split w = hi + lo (both fp16, 11 significant bits each).  The A tile stacks the hi rows and the lo rows of
+// the 64 u-bins along M (128 rows), the B tile stacks hi and lo of the 64 v-bins along N (128 columns), so
+// ONE M128 x N128 x K16 instruction accumulates all four cross terms hi.hi, hi.lo, lo.hi, lo.lo into four
+// 64 x 64 quadrants of the accumulator, which the epilogue adds up.  (tools/emul_f16split.py: the split
+// error is 1e-7 on the histogram, the same as the tf32 split; K = 16 per instruction and 2-byte operands
+// halve the tensor-pipe time and the shared-memory traffic of the tf32 version.)
 //
 // Forward, 64 bins, one persistent CTA per SM, 20 warps:
 //   warps 17-19 pixel pass: 128-bit RGBA loads, log-chroma u/v per channel and intensity Iy -> smem ring
-//   warps 0-7   A operand (u side, Iy-weighted) written straight into TMEM, M = 128 rows =
-//               64 bins x {hi, lo}: TMEM sub-partitions 0,1 hold the hi rows of bins 0-31 / 32-63,
-//               sub-partitions 2,3 the lo rows, so a warp's role is uniform.  The hi warp and the lo
-//               warp of the same bins evaluate 8 pixels each and swap halves through shared memory.
-//               The same warps drain the accumulators (epilogue).
-//   warps 8-15  B operand (v side) hi|lo into shared memory, K-major no-swizzle core matrices
-//   warp 16     one thread issues tcgen05.mma (M=128, N=64, K=8) twice per k-step: B_hi and B_lo,
-//               accumulating all four cross terms into the same 64 TMEM columns per channel
+//   warps 0-7   A operand (u side, Iy-weighted), warps 8-15 B operand (v side): thread = (bin, 8 pixels);
+//               both operands go to shared memory as K-major no-swizzle core matrices, every thread writes
+//               whole 16-byte core-matrix rows (hi row and lo row), no exchange between threads.
+//               The same 16 warps drain the accumulators at the end of a chain.
+//   warp 16     one thread issues tcgen05.mma (SS, M=128, N=128, K=16): 2 per channel and 32-pixel stage
 // The bin weights never exist in global memory: they are generated from 16 B per pixel with packed
-// fp32x2 arithmetic (FADD2/FMUL2/FFMA2) and one MUFU.RCP per weight.
+// fp32x2 arithmetic (FADD2/FMUL2/FFMA2) and one MUFU.RCP per weight pair.
 //
-// Accuracy: the tensor core adds every K=8 block into the fp32 accumulator with truncation, so the
+// Accuracy: the tensor core adds every K block into the fp32 accumulator with truncation, so the
 // error grows with the chain length (measured 8e-6 for 4096 pixels in one chain, ~1e-6 for 1024).
 // Chains are cut at 1024 pixels and summed in fp32 in a shared-memory accumulator; when a CTA owns a
 // whole image the normaliser D and H/D are produced in the same kernel.
@@ -34,23 +38,27 @@ namespace fwdtc {
 
 constexpr int BINS = 64;
 constexpr int KB = 32;         // pixels per pipeline stage
-constexpr int NS = 3;          // A/B operand stages
+constexpr int NS = 3;          // operand stages
 constexpr int CHAIN_KB = 32;   // stages per TMEM accumulation chain (1024 pixels)
 constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 3;  // 20 warps: 640 threads leave 96 registers per thread
-constexpr int MMA_WARP = A_WARPS + B_WARPS;     // 16
+constexpr int PROD_WARPS = A_WARPS + B_WARPS;
+constexpr int MMA_WARP = PROD_WARPS;            // 16
 constexpr int PX_WARP0 = MMA_WARP + 1;          // 17
 constexpr int PR = 6;                           // pixel ring slots
 constexpr int DEDUP_MAX = 512;                  // unique colours kept per image by the de-duplication pass
 constexpr int DEDUP_SLOTS = 1024;
-constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 672
+constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 640
 constexpr int TMEM_COLS = 512;
-constexpr int D_COLS = 64;                 // per channel
-constexpr int A_COL0 = 3 * D_COLS;         // 192
-constexpr int A_STAGE_COLS = 3 * KB;       // 96
-constexpr int B_CH_BYTES = KB * 128 * 4;   // 16384: [kq 0..7][n-group 0..15][n%8][k%4]
-constexpr int B_STAGE_BYTES = 3 * B_CH_BYTES;
-constexpr int B_KQ_BYTES = 16 * 128;       // 2048: one 4-pixel quad for all 128 rows
-static_assert(A_COL0 + NS * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
+constexpr int D_COLS = 128;                // per channel: [B_hi columns | B_lo columns]
+// operand tile of one channel and stage: 128 rows (64 hi + 64 lo) x 32 pixels of fp16, K-major, no swizzle:
+//   [kb = pixel / 8 (4)][row / 8 (16)][row % 8][pixel % 8]     core matrix = 8 rows x 8 halfs = 128 B
+// (the MN-major variant — thread = (pixel, 8 bins), one 4-byte shared load per coordinate instead of
+// broadcast 16-byte loads — measured 6 % slower: tools/f16_layout_test.cu keeps the layout check for it)
+constexpr int T_KB_BYTES = 16 * 128;       // 2048: one core-matrix column (8 pixels) for all 128 rows
+constexpr int TILE_BYTES = 4 * T_KB_BYTES; // 8192
+constexpr int STAGE_BYTES = 6 * TILE_BYTES;  // A and B tiles of the three channels: [c][A, B]
+constexpr float W_SCALE = 16384.0f;        // weights are generated as 2^14 K, K in (0, 1]
+static_assert(3 * D_COLS <= TMEM_COLS, "TMEM budget");
 static_assert(KB == 32, "stage = 32 pixels (shifts below)");
 
 struct PxSlot {
@@ -58,14 +66,13 @@ struct PxSlot {
 };
 
 struct Smem {
-  alignas(128) unsigned char b[NS][B_STAGE_BYTES];  // 144 KB
+  alignas(128) unsigned char ab[NS][STAGE_BYTES];   // 144 KB
   float acc[3][BINS][BINS + 1];                     // [c][j][i] running fp32 sum over chains; rows padded to 65
                                                     // floats so both the bin-major drain and the j-major
                                                     // write-out are free of bank conflicts
-  float4 xbuf[4][2][3][2][32];                      // [pair][direction][channel][quad of 4 px][lane], 24 KB
   PxSlot px[PR];
   float dom[BINS];
-  float red[8];
+  float red[PROD_WARPS];
   alignas(8) uint64_t px_full[PR], px_empty[PR], ab_full[NS], ab_empty[NS], d_full, d_empty;
   uint32_t tmem_base;
 };
@@ -87,13 +94,12 @@ struct Params {
   int splits;
   int64_t px_per_split;
   int64_t items;  // n_whole + (B - n_whole) * splits
-  float inv_sigma_sqr;
   float eps;
-  int debug_skip_mma;  // tuning experiments only (env PH_DEBUG_SKIP_MMA): bit 0 = issue no MMA, bit 1 = B warps
-                       // generate nothing.  Result (B200): skipping all MMAs does not shorten the kernel and
-                       // skipping B saves 20 %: at 64 bins the A-operand chain (px wait -> weights -> hand-over
-                       // barrier -> tcgen05.st -> wait::st -> arrive) and shared-memory bandwidth (145 KB per
-                       // 32-pixel stage = 1 130 cycles) bound the forward, not the tensor pipe.
+  // scaled weight  2^14 K:  IQ: 1 / (wa t + wb),  RBF: 2^(wa t + wb),  t = (x - c)^2
+  float wa, wb;
+  float iy_scale;    // power of two applied to the intensity (x multiplicity) so that the A operand stays below
+                     // fp16's 65504: 1 for dense images, 2^-ceil(log2 npix) for de-duplicated ones
+  float inv_scale;   // 1 / (2^14 * 2^14 * iy_scale): raw sums -> true scale
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -129,170 +135,20 @@ __device__ __forceinline__ ItemRange item_range(const Params& p, int64_t w) {
   return r;
 }
 
-// two bin weights at once: d = x + (-c);  IQ: 1/(1 + d^2/s^2), RBF: exp(-d^2/s^2)
+// two scaled bin weights at once (two pixels, one bin): d = x + (-c)
 template <int METHOD>
-__device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 inv2, f32x2 one2) {
+__device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 wa2, f32x2 wb2) {
   const f32x2 d = add2(x, negc);
   const f32x2 t = mul2(d, d);
+  const f32x2 e = fma2(t, wa2, wb2);
   if (METHOD == PH_METHOD_INVERSE_QUADRATIC) {
-    const f32x2 e = fma2(t, inv2, one2);
-    return pack2(fast_rcp(lo_of(e)), fast_rcp(hi_of(e)));
+    // one MUFU.RCP for the two weights: 1/e0 = e1 / (e0 e1), 1/e1 = e0 / (e0 e1)
+    const float e0 = lo_of(e), e1 = hi_of(e);
+    const float r = fast_rcp(e0 * e1);
+    return pack2(r * e1, r * e0);
   } else {
-    const f32x2 e = mul2(t, inv2);
-    return pack2(__expf(-lo_of(e)), __expf(-hi_of(e)));
+    return pack2(fast_ex2(lo_of(e)), fast_ex2(hi_of(e)));
   }
-}
-
-// A-operand producer + epilogue warp.  ROLE (0: hi rows, 1: lo rows) is a template parameter so the
-// keep/hand-over choices compile to plain register assignments.
-template <int METHOD, int ROLE>
-__device__ __forceinline__ void a_warp_loop(Smem& S, const Params& p, uint32_t tmem, int tid, int warp, int lane,
-                                            int64_t first, int64_t step, f32x2 inv2, f32x2 one2, f32x2 mone2) {
-    // ===================== A operand (TMEM) + epilogue =====================
-    const int quad = warp & 3;        // TMEM sub-partition of this warp
-    const int sub = warp >> 2;        // which 16 of the 32 pixels of a stage
-    constexpr int role = ROLE;        // 0: hi rows, 1: lo rows (warp-uniform, compile-time here)
-    const int bin = (quad & 1) * 32 + lane;
-    const int pair = (quad & 1) * 2 + sub;            // the two warps sharing (bins, pixel half)
-    const float c_bin = S.dom[bin];
-    const f32x2 negc = pack2(-c_bin, -c_bin);
-    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const int px_own = sub * 16 + role * 8;  // the 8 pixels this warp evaluates
-    uint32_t it = 0, chain = 0;
-    for (int64_t w = first; w < p.items; w += step) {
-      const ItemRange ir = item_range(p, w);
-      const int64_t b = ir.b;
-      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
-      for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
-        const int slot = it % PR, stage = it % NS;
-        mbar_wait(&S.px_full[slot], (it / PR) & 1);
-        const PxSlot& in = S.px[slot];
-        // all three channels at once: 24 weights per thread in flight, one hand-over with the partner warp
-        // (barrier 1: partner has consumed the previous stage's hand-over; barrier 2: this stage's is written)
-        f32x2 keep[3][4];
-        named_bar_sync(1 + pair, 64);
-        ulonglong2* xs = reinterpret_cast<ulonglong2*>(&S.xbuf[pair][role][0][0][lane]);
-        const ulonglong2* xr = reinterpret_cast<const ulonglong2*>(&S.xbuf[pair][role ^ 1][0][0][lane]);
-        const ulonglong2 ia = *reinterpret_cast<const ulonglong2*>(&in.iy[px_own]);
-        const ulonglong2 ib = *reinterpret_cast<const ulonglong2*>(&in.iy[px_own + 4]);
-        ulonglong2 uu[3][2];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          uu[c][0] = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own]);
-          uu[c][1] = *reinterpret_cast<const ulonglong2*>(&in.u[c][px_own + 4]);
-        }
-        mbar_arrive_warp(&S.px_empty[slot]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const ulonglong2 ua = uu[c][0], ub = uu[c][1];
-          const f32x2 w0 = mul2(weight2<METHOD>(ua.x, negc, inv2, one2), ia.x);
-          const f32x2 w1 = mul2(weight2<METHOD>(ua.y, negc, inv2, one2), ia.y);
-          const f32x2 w2 = mul2(weight2<METHOD>(ub.x, negc, inv2, one2), ib.x);
-          const f32x2 w3 = mul2(weight2<METHOD>(ub.y, negc, inv2, one2), ib.y);
-          const f32x2 h0 = w0 & TF32_MASK2, h1 = w1 & TF32_MASK2, h2 = w2 & TF32_MASK2, h3 = w3 & TF32_MASK2;
-          const f32x2 l0 = fma2(h0, mone2, w0), l1 = fma2(h1, mone2, w1), l2 = fma2(h2, mone2, w2),
-                      l3 = fma2(h3, mone2, w3);
-          // keep the part this row set needs, hand the other part to the partner warp
-          if (role == 0) {
-            keep[c][0] = h0; keep[c][1] = h1; keep[c][2] = h2; keep[c][3] = h3;
-            xs[c * 64] = make_ulonglong2(l0, l1); xs[c * 64 + 32] = make_ulonglong2(l2, l3);
-          } else {
-            keep[c][0] = l0; keep[c][1] = l1; keep[c][2] = l2; keep[c][3] = l3;
-            xs[c * 64] = make_ulonglong2(h0, h1); xs[c * 64 + 32] = make_ulonglong2(h2, h3);
-          }
-        }
-        named_bar_sync(1 + pair, 64);
-        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this TMEM stage are done
-        tc_fence_after_sync();
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const ulonglong2 ra = xr[c * 64], rb = xr[c * 64 + 32];
-          const f32x2 got[4] = {ra.x, ra.y, rb.x, rb.y};
-          uint32_t out[16];
-          // columns sub*16 + 0..7 are the pixels of the hi warp, + 8..15 those of the lo warp
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const f32x2 first8 = role == 0 ? keep[c][e] : got[e];
-            const f32x2 second8 = role == 0 ? got[e] : keep[c][e];
-            out[2 * e] = (uint32_t)first8;
-            out[2 * e + 1] = (uint32_t)(first8 >> 32);
-            out[8 + 2 * e] = (uint32_t)second8;
-            out[8 + 2 * e + 1] = (uint32_t)(second8 >> 32);
-          }
-          tmem_st16(tmem + lane_addr + A_COL0 + stage * A_STAGE_COLS + c * KB + sub * 16, out);
-        }
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive_warp(&S.ab_full[stage]);
-
-        const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
-        if (!chain_end) continue;
-        // ---- chain epilogue: D (TMEM) += into the fp32 shared-memory accumulator ----
-        mbar_wait(&S.d_full, chain & 1);
-        ++chain;
-        tc_fence_after_sync();
-        // hi-row warps first (plain stores on the first chain of an item, else read-add-write), then the
-        // lo-row warps add their share: no shared-memory float atomics (those are CAS loops)
-        const bool first_chain = kb < CHAIN_KB;
-        if (role == 0) {
-#pragma unroll 1
-          for (int c = 0; c < 3; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
-            tmem_ld_wait();
-            if (first_chain) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) S.acc[c][sub * 32 + i][bin] = __uint_as_float(v[i]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) S.acc[c][sub * 32 + i][bin] += __uint_as_float(v[i]);
-            }
-          }
-        }
-        named_bar_sync(5, A_WARPS * 32);
-        if (role == 1) {
-#pragma unroll 1
-          for (int c = 0; c < 3; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem + lane_addr + c * D_COLS + sub * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) S.acc[c][sub * 32 + i][bin] += __uint_as_float(v[i]);
-          }
-        }
-        tc_fence_before_sync();
-        mbar_arrive_warp(&S.d_empty);
-        if (kb + 1 != nkb) continue;
-
-        // ---- item epilogue: all 8 warps, normalise (whole image) or emit the raw partial ----
-        named_bar_sync(5, A_WARPS * 32);
-        const int t = tid;  // 0..255
-        if (ir.whole) {
-          float s = 0.f;
-          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
-          s = warp_sum(s);
-          if (lane == 0) S.red[warp] = s;
-          named_bar_sync(5, A_WARPS * 32);
-          float d = 0.f;
-#pragma unroll
-          for (int k = 0; k < A_WARPS; ++k) d += S.red[k];
-          if (t == 0) p.denom[b] = d;
-          const float inv_d = 1.0f / d;
-          float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
-          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
-            const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-            dst[e] = S.acc[c][j][i] * inv_d;
-          }
-        } else {
-          float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
-          for (int e = t; e < 3 * BINS * BINS; e += A_WARPS * 32) {
-            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
-            dst[e] = S.acc[c][j][i];
-          }
-        }
-        named_bar_sync(5, A_WARPS * 32);
-      }
-    }
 }
 
 template <int METHOD>
@@ -305,10 +161,10 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
 
   if (tid == 0) {
     // producer/consumer barriers count WARPS (mbar_arrive_warp), the tcgen05.commit ones count 1
-    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 1); mbar_init(&S.px_empty[i], A_WARPS + B_WARPS); }
-    for (int i = 0; i < NS; ++i) { mbar_init(&S.ab_full[i], A_WARPS + B_WARPS); mbar_init(&S.ab_empty[i], 1); }
+    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 1); mbar_init(&S.px_empty[i], PROD_WARPS); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&S.ab_full[i], PROD_WARPS); mbar_init(&S.ab_empty[i], 1); }
     mbar_init(&S.d_full, 1);
-    mbar_init(&S.d_empty, A_WARPS);
+    mbar_init(&S.d_empty, PROD_WARPS);
     fence_mbar_init();
   }
   if (tid < BINS) S.dom[tid] = p.dom[tid];
@@ -319,9 +175,6 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
   const uint32_t tmem = S.tmem_base;
 
   const int64_t first = blockIdx.x, step = gridDim.x;
-  const f32x2 inv2 = pack2(p.inv_sigma_sqr, p.inv_sigma_sqr);
-  const f32x2 one2 = pack2(1.0f, 1.0f);
-  const f32x2 mone2 = pack2(-1.0f, -1.0f);
 
   if (warp >= PX_WARP0) {
     // ===================== pixel pass (PXW warps, round-robin over 32-pixel rounds) =====================
@@ -354,64 +207,148 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
         const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
         const float d_rg = logf(e0 / e1), d_rb = logf(e0 / e2), d_gb = logf(e1 / e2);
-        mbar_wait(&S.px_empty[slot], ((it / PR) & 1) ^ 1);
+        mbar_wait_relaxed(&S.px_empty[slot], ((it / PR) & 1) ^ 1, 400);
         PxSlot& o = S.px[slot];
         // (u,v): R:(rg, rb)  G:(-rg, gb)  B:(-rb, -gb)   (histogram.py:72-74)
         o.u[0][lane] = d_rg;  o.v[0][lane] = d_rb;
         o.u[1][lane] = -d_rg; o.v[1][lane] = d_gb;
         o.u[2][lane] = -d_rb; o.v[2][lane] = -d_gb;
-        o.iy[lane] = valid ? iy * mult : 0.f;  // masked pixels contribute nothing (A operand = 0)
+        o.iy[lane] = valid ? iy * mult * p.iy_scale : 0.f;  // masked pixels contribute nothing (A operand = 0)
         mbar_arrive_warp(&S.px_full[slot]);
       }
     }
-  } else if (warp < A_WARPS) {
-    if (((warp & 3) >> 1) == 0) a_warp_loop<METHOD, 0>(S, p, tmem, tid, warp, lane, first, step, inv2, one2, mone2);
-    else a_warp_loop<METHOD, 1>(S, p, tmem, tid, warp, lane, first, step, inv2, one2, mone2);
-  } else if (warp < MMA_WARP) {
-    // ===================== B operand (shared memory) =====================
-    const int t = tid - A_WARPS * 32;
-    const int j = t & 63, part = t >> 6;  // part: which 8 of the 32 pixels (two 4-pixel quads)
-    const float c_bin = S.dom[j];
+  } else if (warp < PROD_WARPS) {
+    // ===================== operand producers (A: warps 0-7, B: warps 8-15) + epilogue =====================
+    const int side = warp >> 3;                 // 0: A (u side, x intensity), 1: B (v side)   — warp-uniform
+    const int bin = tid & 63;
+    const int po = (tid >> 6) & 3;              // which 8 of the stage's 32 pixels
+    const float c_bin = S.dom[bin];
     const f32x2 negc = pack2(-c_bin, -c_bin);
-    const uint32_t row_off = (uint32_t)((j >> 3) * 128 + (j & 7) * 16);  // hi row j; lo row j + 64 is +1024
-    uint32_t it = 0;
+    const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
+    // hi row `bin`, lo row `bin + 64` (+ 8 row groups = 1024 B) of core-matrix column `po`
+    const uint32_t row_off = (uint32_t)(side * TILE_BYTES + po * T_KB_BYTES + (bin >> 3) * 128 + (bin & 7) * 16);
+    // epilogue role: TMEM sub-partition quad = warp % 4 -> rows 32 quad .. (hi rows of bins 0-63 in quads 0,1,
+    // lo rows in quads 2,3); column block cs = warp / 4 -> v-bins j in [16 cs, 16 cs + 16)
+    const int quad = warp & 3, cs = warp >> 2;
+    const int ebin = (quad & 1) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    uint32_t it = 0, chain = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const ItemRange ir = item_range(p, w);
-      for (uint32_t base = ir.px0; base < ir.px1; base += KB, ++it) {
+      const int64_t b = ir.b;
+      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
+      for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
         const int slot = it % PR, stage = it % NS;
         mbar_wait(&S.px_full[slot], (it / PR) & 1);
         const PxSlot& in = S.px[slot];
         // all loads first (the compiler cannot hoist them across the shared-memory stores below)
-        ulonglong2 vv[3][2];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int q4 = 0; q4 < 2; ++q4) vv[c][q4] = *reinterpret_cast<const ulonglong2*>(&in.v[c][(part * 2 + q4) * 4]);
-        mbar_arrive_warp(&S.px_empty[slot]);
-        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);
-        if (!(p.debug_skip_mma & 2))
+        ulonglong2 xx[3][2], iw[2];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          unsigned char* tile = &S.b[stage][c * B_CH_BYTES];
+          const float* src = side == 0 ? &in.u[c][po * 8] : &in.v[c][po * 8];
+          xx[c][0] = *reinterpret_cast<const ulonglong2*>(src);
+          xx[c][1] = *reinterpret_cast<const ulonglong2*>(src + 4);
+        }
+        if (side == 0) {
+          iw[0] = *reinterpret_cast<const ulonglong2*>(&in.iy[po * 8]);
+          iw[1] = *reinterpret_cast<const ulonglong2*>(&in.iy[po * 8 + 4]);
+        }
+        mbar_arrive_warp(&S.px_empty[slot]);
+        uint4 hi[3], lo[3];
 #pragma unroll
-          for (int q4 = 0; q4 < 2; ++q4) {
-            const int kq = part * 2 + q4;
-            const f32x2 w0 = weight2<METHOD>(vv[c][q4].x, negc, inv2, one2);
-            const f32x2 w1 = weight2<METHOD>(vv[c][q4].y, negc, inv2, one2);
-            const f32x2 h0 = w0 & TF32_MASK2, h1 = w1 & TF32_MASK2;
-            const f32x2 l0 = fma2(h0, mone2, w0), l1 = fma2(h1, mone2, w1);
-            *reinterpret_cast<ulonglong2*>(tile + kq * B_KQ_BYTES + row_off) = make_ulonglong2(h0, h1);
-            *reinterpret_cast<ulonglong2*>(tile + kq * B_KQ_BYTES + row_off + 1024) = make_ulonglong2(l0, l1);
-          }
+        for (int c = 0; c < 3; ++c) {
+          f32x2 w0 = weight2<METHOD>(xx[c][0].x, negc, wa2, wb2);
+          f32x2 w1 = weight2<METHOD>(xx[c][0].y, negc, wa2, wb2);
+          f32x2 w2 = weight2<METHOD>(xx[c][1].x, negc, wa2, wb2);
+          f32x2 w3 = weight2<METHOD>(xx[c][1].y, negc, wa2, wb2);
+          if (side == 0) { w0 = mul2(w0, iw[0].x); w1 = mul2(w1, iw[0].y); w2 = mul2(w2, iw[1].x); w3 = mul2(w3, iw[1].y); }
+          split_f16x2(w0, mone2, hi[c].x, lo[c].x);
+          split_f16x2(w1, mone2, hi[c].y, lo[c].y);
+          split_f16x2(w2, mone2, hi[c].z, lo[c].z);
+          split_f16x2(w3, mone2, hi[c].w, lo[c].w);
+        }
+        mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this stage are done
+        unsigned char* tile = &S.ab[stage][row_off];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          *reinterpret_cast<uint4*>(tile + c * 2 * TILE_BYTES) = hi[c];
+          *reinterpret_cast<uint4*>(tile + c * 2 * TILE_BYTES + 1024) = lo[c];
         }
         fence_proxy_async_smem();
         mbar_arrive_warp(&S.ab_full[stage]);
+
+        const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
+        if (!chain_end) continue;
+        // ---- chain epilogue: the four quadrants of D (TMEM) += into the fp32 shared-memory accumulator ----
+        mbar_wait(&S.d_full, chain & 1);
+        ++chain;
+        tc_fence_after_sync();
+        // hi-row warps first (plain stores on the first chain of an item, else read-add-write), then the
+        // lo-row warps add their share: no shared-memory float atomics (those are CAS loops)
+        const bool first_chain = kb < CHAIN_KB;
+        float val[3][16];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t v1[16], v2[16];
+          tmem_ld16(tmem + lane_addr + c * D_COLS + cs * 16, v1);
+          tmem_ld16(tmem + lane_addr + c * D_COLS + 64 + cs * 16, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) val[c][i] = __uint_as_float(v1[i]) + __uint_as_float(v2[i]);
+        }
+        tc_fence_before_sync();
+        mbar_arrive_warp(&S.d_empty);  // the accumulators are in registers: the next chain may start
+        if (quad < 2) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float* a = &S.acc[c][cs * 16 + i][ebin];
+              *a = first_chain ? val[c][i] : *a + val[c][i];
+            }
+        }
+        named_bar_sync(5, PROD_WARPS * 32);
+        if (quad >= 2) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) S.acc[c][cs * 16 + i][ebin] += val[c][i];
+        }
+        if (kb + 1 != nkb) { named_bar_sync(5, PROD_WARPS * 32); continue; }  // acc is read-modified by the next chain
+
+        // ---- item epilogue: all 16 warps, normalise (whole image) or emit the raw partial ----
+        named_bar_sync(5, PROD_WARPS * 32);
+        const int t = tid;  // 0..511
+        if (ir.whole) {
+          float s = 0.f;
+          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
+          s = warp_sum(s);
+          if (lane == 0) S.red[warp] = s;
+          named_bar_sync(5, PROD_WARPS * 32);
+          float d = 0.f;
+#pragma unroll
+          for (int k = 0; k < PROD_WARPS; ++k) d += S.red[k];
+          if (t == 0) p.denom[b] = d * p.inv_scale;
+          const float inv_d = 1.0f / d;
+          float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
+          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+            const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
+            dst[e] = S.acc[c][j][i] * inv_d;
+          }
+        } else {
+          float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
+          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
+            dst[e] = S.acc[c][j][i] * p.inv_scale;
+          }
+        }
+        named_bar_sync(5, PROD_WARPS * 32);
       }
     }
   } else if (warp == MMA_WARP) {
     // ===================== MMA issue: the whole warp runs the (uniform) loop, one elected lane issues ====
-    constexpr uint32_t IDESC = idesc_tf32(128, 64);
-    const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(&S.b[0][0]), B_KQ_BYTES, 128);
+    constexpr uint32_t IDESC = idesc_f16(128, 128);
+    const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(&S.ab[0][0]), T_KB_BYTES, 128);
     const uint32_t dlo0 = (uint32_t)desc0, dhi = (uint32_t)(desc0 >> 32);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);  // provably uniform copy
     // Wrap-around counters only (no % or /) and no conditionally executed waits: ptxas then keeps the whole
@@ -427,19 +364,15 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
           mbar_wait(&S.ab_full[stage], phase);
           tc_fence_after_sync();
           // the start-address field (bits 0-13, units of 16 B) never carries into the next field
-          const uint32_t dstage = dlo0 + stage * (B_STAGE_BYTES >> 4);
-          const uint32_t a_stage = tm + A_COL0 + stage * A_STAGE_COLS;
+          const uint32_t dstage = dlo0 + stage * (STAGE_BYTES >> 4);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
 #pragma unroll
-            for (int ks = 0; ks < KB / 8; ++ks) {
-              const uint32_t b_hi = dstage + ((c * B_CH_BYTES + ks * 2 * B_KQ_BYTES) >> 4);
-              const uint32_t b_lo = b_hi + (1024 >> 4);
+            for (int ks = 0; ks < KB / 16; ++ks) {
+              const uint32_t a_d = dstage + ((c * 2 * TILE_BYTES + ks * 2 * T_KB_BYTES) >> 4);
+              const uint32_t b_d = a_d + (TILE_BYTES >> 4);
               const uint32_t acc0 = (k == 0 && ks == 0) ? 0u : 1u;
-              if (!(p.debug_skip_mma & 1) && elect_one_sync()) {
-                mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_hi, dhi, IDESC, acc0);
-                mma_tf32_ts2(tm + c * D_COLS, a_stage + c * KB + ks * 8, b_lo, dhi, IDESC, 1u);
-              }
+              if (elect_one_sync()) mma_f16_ss2(tm + c * D_COLS, a_d, b_d, dhi, IDESC, acc0);
             }
           }
           if (elect_one_sync()) mma_commit(&S.ab_empty[stage]);
@@ -619,10 +552,22 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.splits = pl.splits;
   p.px_per_split = ceil_div(ceil_div(npix, p.splits), KB) * KB;
   p.items = p.n_whole + (batch - p.n_whole) * p.splits;
-  p.inv_sigma_sqr = 1.0f / sigma_sqr;
   p.eps = eps;
-  static const int skip_mma = getenv("PH_DEBUG_SKIP_MMA") ? atoi(getenv("PH_DEBUG_SKIP_MMA")) : 0;
-  p.debug_skip_mma = skip_mma;
+  if (method == PH_METHOD_INVERSE_QUADRATIC) {
+    p.wa = (float)(1.0 / ((double)sigma_sqr * W_SCALE));
+    p.wb = 1.0f / W_SCALE;
+  } else {
+    p.wa = (float)(-1.4426950408889634 / (double)sigma_sqr);
+    p.wb = 14.0f;
+  }
+  p.iy_scale = 1.0f;
+  if (dedup && p.n_whole == batch) {
+    // multiplicities reach npix: keep count * Iy * 2^14 K below fp16's maximum
+    int e = 0;
+    while (((int64_t)1 << e) < npix) ++e;
+    p.iy_scale = ldexpf(1.0f, -e);
+  }
+  p.inv_scale = 1.0f / ((double)W_SCALE * (double)W_SCALE * (double)p.iy_scale);
   if (dedup && p.n_whole == batch) {
     // unique colours + multiplicities per image (only worth it when a CTA owns whole images)
     float4* ulist = static_cast<float4*>(workspace);

@@ -73,9 +73,25 @@ __device__ __forceinline__ bool mbar_try_wait_for(uint64_t* bar, uint32_t parity
 // Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  // every poll sleeps in hardware (>= tens of ns), so 2^27 polls are several seconds: counting polls instead
+  // of reading the clock keeps the loop at a handful of instructions (the waiting warps share issue slots
+  // with the producers)
+  uint32_t polls = 0;
   while (!mbar_try_wait_for(bar, parity, 200000u)) {
-    if (clock64() - t0 > 4000000000ll) {
+    if (++polls > (1u << 27)) {
+      printf("palhist: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+// Wait of a warp that runs far ahead of its consumer (pixel warps, several ring slots of slack): poll with
+// real sleeps in between, so that the warp leaves the issue slots to the others.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if (++polls > (1u << 24)) {
       printf("palhist: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
@@ -183,6 +199,19 @@ __device__ __forceinline__ void mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, ui
       : "r"(d_tmem), "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 with both operands in shared memory; the two descriptors share their high word
+__device__ __forceinline__ void mma_f16_ss2(uint32_t d_tmem, uint32_t a_desc_lo, uint32_t b_desc_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 ad, {%1, %3};\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_desc_lo), "r"(b_desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -285,19 +314,27 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 constexpr unsigned long long TF32_MASK2 = 0xFFFFE000FFFFE000ull;
 
 // ---- fp16 operand split: w (already scaled into fp16's range) = hi + lo, both fp16 ----------------------
-// hi = w truncated to 11 significant bits (a mask: exactly representable in fp16, so the conversion is exact),
-// lo = fp16(w - hi): hi.hi + hi.lo + lo.hi recovers the fp32 product to ~2^-21 like the tf32 split does, at
+// hi = fp16(w), lo = fp16(w - hi): hi.hi + hi.lo + lo.hi recovers the fp32 product to ~2^-21 like the tf32 split does, at
 // twice the tensor-core rate (K = 16 per instruction) and half the operand bytes.
 __device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
-__device__ __forceinline__ void split_f16x2(f32x2 w, f32x2 mone2, uint32_t& hi, uint32_t& lo) {
-  const f32x2 h = w & TF32_MASK2;
-  const f32x2 l = fma2(h, mone2, w);
-  hi = cvt_f16x2(lo_of(h), hi_of(h));
-  lo = cvt_f16x2(lo_of(l), hi_of(l));
+__device__ __forceinline__ void split_f16x2(f32x2 w, f32x2 /*mone2*/, uint32_t& hi, uint32_t& lo) {
+  // hi = fp16(w) (round to nearest, packed conversion); lo = fp16(w - hi) with the mixed-precision FMA
+  // (FHFMA: fp16 x fp16 + fp32, exact here): 4 instructions per pair of weights
+  const float w0 = lo_of(w), w1 = hi_of(w);
+  float l0, l1;
+  asm("{\n\t.reg .f16 h0, h1, m1;\n\t"
+      "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
+      "mov.b32 {h0, h1}, %0;\n\t"
+      "mov.b16 m1, 0xBC00;\n\t"  // -1.0
+      "fma.rn.f32.f16 %1, h0, m1, %3;\n\t"
+      "fma.rn.f32.f16 %2, h1, m1, %4;\n\t}"
+      : "=&r"(hi), "=f"(l0), "=f"(l1)
+      : "f"(w0), "f"(w1));
+  lo = cvt_f16x2(l0, l1);
 }
 __device__ __forceinline__ float fast_ex2(float x) {
   float r;

@@ -70,6 +70,51 @@ __global__ void test(int N, float* out, long long* cyc) {
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// SS mode, both operands MN-major (row index contiguous), no swizzle:
+//   element (r, k) at (r/8)*rb_stride + (k/8)*kb_stride + (k%8)*16 + (r%8)*2   (core matrix = 8 k x 8 rows = 128 B)
+__global__ void test_ss_mn(int swap, float* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  tc_fence_before_sync(); __syncthreads(); tc_fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const int rb_stride = 512, kb_stride = 128;  // [row block (16)][k block (4)][k%8][row%8]
+  unsigned char* A = smem; unsigned char* B = smem + 8192;
+  for (int e = tid; e < 128 * 32; e += blockDim.x) {
+    const int r = e / 32, k = e % 32;
+    const int off = (r / 8) * rb_stride + (k / 8) * kb_stride + (k % 8) * 16 + (r % 8) * 2;
+    *reinterpret_cast<__half*>(A + off) = __float2half(a_val(r, k));
+    *reinterpret_cast<__half*>(B + off) = __float2half(b_val(r, k));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync(); __syncthreads(); tc_fence_after_sync();
+  if (tid == 0) {
+    // a_major (bit 15) = b_major (bit 16) = 1: MN-major
+    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t sa = smem_u32(A), sb = smem_u32(B);
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint32_t lbo = swap ? rb_stride : kb_stride, sbo = swap ? kb_stride : rb_stride;
+      const uint64_t adesc = smem_desc_kmajor_noswizzle(sa + ks * 2 * kb_stride, lbo, sbo);
+      const uint64_t bdesc = smem_desc_kmajor_noswizzle(sb + ks * 2 * kb_stride, lbo, sbo);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" :: "r"(tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(ks) : "memory");
+    }
+    mma_commit(&bar); mbar_wait(&bar, 0);
+  }
+  tc_fence_before_sync(); __syncthreads(); tc_fence_after_sync();
+  for (int c0 = 0; c0 < 128; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 16; ++i) out[tid * 128 + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before_sync(); __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int main() {
   float* d; long long* c;
   cudaMalloc(&d, 128 * 128 * sizeof(float)); cudaMalloc(&c, 16);
@@ -85,6 +130,19 @@ int main() {
       const double er = fabs(ref - h[m * N + n]); if (er > maxerr) maxerr = er; if (er > 1e-3) ++bad;
     }
     printf("f16 TS M128 N%d K16 x2: %s  max err %.3g  mismatches %d  | %.1f cycles/MMA\n", N, cudaGetErrorString(e), maxerr, bad, hc[0] / 2048.0);
+  }
+  cudaFuncSetAttribute(test_ss_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  for (int swap : {0, 1}) {
+    test_ss_mn<<<1, 128, 65536>>>(swap, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    static float h[128 * 128];
+    cudaMemcpy(h, d, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost);
+    double maxerr = 0; int bad = 0;
+    for (int m = 0; m < 128; ++m) for (int n = 0; n < 128; ++n) {
+      double ref = 0; for (int k = 0; k < 32; ++k) ref += (double)a_val(m, k) * b_val(n, k);
+      const double er = fabs(ref - h[m * 128 + n]); if (er > maxerr) maxerr = er; if (er > 1e-3) ++bad;
+    }
+    printf("f16 SS MN-major M128 N128 K16 x2 (lbo/sbo swap=%d): %s  max err %.3g  mismatches %d\n", swap, cudaGetErrorString(e), maxerr, bad);
   }
   return 0;
 }
