@@ -142,7 +142,8 @@ __device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 wa2, f32x2 w
   const f32x2 t = mul2(d, d);
   const f32x2 e = fma2(t, wa2, wb2);
   if (METHOD == PH_METHOD_INVERSE_QUADRATIC) {
-    // one MUFU.RCP for the two weights: 1/e0 = e1 / (e0 e1), 1/e1 = e0 / (e0 e1)
+    // one MUFU.RCP for the two weights (1/e0 = e1 / (e0 e1), 1/e1 = e0 / (e0 e1)): with one reciprocal per weight
+    // the forward is bound by the MUFU pipe (16/clk/SM: 768 cycles per 32-pixel stage), measured 5 % slower
     const float e0 = lo_of(e), e1 = hi_of(e);
     const float r = fast_rcp(e0 * e1);
     return pack2(r * e1, r * e0);
