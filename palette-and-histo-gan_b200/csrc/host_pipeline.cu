@@ -1,8 +1,13 @@
 // Host-buffer entry points: the calls a CPU-side caller (a tf.data worker, a cgo/JNI-style binding)
 // makes with plain host arrays.  Device staging is owned by an opaque per-thread context; batches
-// are cut into chunks so the H2D copy of chunk k+1 overlaps the forward kernels of chunk k, and the
-// D2H copy of gradient chunk k overlaps the backward kernels of chunk k+1.  The Hellinger loss
-// couples all images through one scalar (histogram.py:88-89), hence the two phases.
+// are cut into chunks so the H2D copy of chunk k+1 overlaps the kernels of chunk k.
+//
+// The Hellinger loss couples all images through one scalar (histogram.py:88-89): loss = sqrt(S) / (sqrt2 B)
+// with S the sum over the whole (global) batch, hence the two phases.  But the gradient depends on S and B
+// only through the common factor 1 / (B sqrt(S)): d loss / d fake_b = h_b / (B sqrt(S)) with h_b a function
+// of image b alone.  So phase 1 already runs the backward kernels of every chunk with S = B = 1, right behind
+// that chunk's forward kernels and under the upload of the next chunk, and phase 2 only multiplies the stored
+// gradient by 1 / (B sqrt(S)) — one pass at HBM speed — once the global S is known.
 #include <new>
 
 #include "common.cuh"
@@ -22,8 +27,9 @@ struct ph_host_ctx {
   // state carried from ph_host_hist_begin to ph_host_hist_finish
   struct Job {
     unsigned char* d_u8[2];
-    float *d_fake, *d_real[2], *d_hreal, *d_hfake, *d_denom_r, *d_denom_f, *d_grad[2], *d_dom, *d_loss;
-    double* d_ssum;
+    float *d_fake, *d_real[2], *d_hreal, *d_hfake, *d_denom_r, *d_denom_f, *d_gradfull, *d_dom, *d_loss;
+    double *d_ssum, *d_one;
+    bool with_grad;
     char* d_ws;
     size_t ws_bytes;
     int64_t batch, npix, chunk;
@@ -34,6 +40,41 @@ struct ph_host_ctx {
 };
 
 namespace ph {
+
+// out[i] = in[i] / (B sqrt(S)): turns the unit-scale gradient of phase 1 into the gradient of the loss
+// (S == 0 gives inf / NaN exactly like the reference's 0 * inf)
+__global__ void __launch_bounds__(256) grad_rescale_kernel(const float4* __restrict__ in, float4* __restrict__ out,
+                                                           int64_t n4, const double* __restrict__ ssum,
+                                                           double global_batch) {
+  const float c = (float)(1.0 / (global_batch * sqrt(*ssum)));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = in[i];
+    v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+    out[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256) grad_rescale_scalar_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                  int64_t n, const double* __restrict__ ssum,
+                                                                  double global_batch) {
+  const float c = (float)(1.0 / (global_batch * sqrt(*ssum)));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i] * c;
+}
+static int launch_grad_rescale(const float* in, float* out, int64_t n, const double* ssum, int64_t global_batch,
+                               cudaStream_t st) {
+  const bool vec = n % 4 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  int64_t grid = ceil_div(vec ? n / 4 : n, 256 * 4);
+  const int64_t cap = (int64_t)cached_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  if (vec)
+    grad_rescale_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in),
+                                                        reinterpret_cast<float4*>(out), n / 4, ssum, (double)global_batch);
+  else
+    grad_rescale_scalar_kernel<<<(unsigned)grid, 256, 0, st>>>(in, out, n, ssum, (double)global_batch);
+  PH_LAUNCH_OK("grad_rescale_kernel");
+  return PH_OK;
+}
 
 static int ensure_arena(ph_host_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->arena_bytes) return PH_OK;
@@ -108,7 +149,8 @@ void ph_host_ctx_destroy(ph_host_ctx* ctx) {
 // of squares over ranks between the phases; ph_host_hist_loss is the single-process composition.
 static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool real_is_u8, const float* fake_host,
                                 int64_t batch, int64_t npix, int channels, const float* bin_centers_host, int bins,
-                                int method, float sigma_sqr, float epsilon, int impl, double* ssum_local_host) {
+                                int method, float sigma_sqr, float epsilon, int impl, bool with_grad,
+                                double* ssum_local_host) {
   PH_CHECK_ARG(ctx && real_host && fake_host && bin_centers_host && ssum_local_host, "NULL pointer argument");
   PH_CHECK_ARG(batch > 0 && npix > 0 && (channels == 3 || channels == 4), "bad shape");
   PH_CHECK_ARG(bins >= 1 && bins <= 1024, "bins must be in [1,1024]");
@@ -124,9 +166,7 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   if (ceil_div(batch, chunk) > ph_host_ctx::kMaxChunks) chunk = ceil_div(batch, ph_host_ctx::kMaxChunks);
   const int nchunks = (int)ceil_div(batch, chunk);
   const size_t hist_elems = (size_t)bins * bins * 3;
-  size_t ws_bytes = ph_hist_workspace_bytes(chunk, npix, bins, impl);
-  const size_t ws_full = ph_hist_workspace_bytes(batch, npix, bins, impl);  // whole-batch backward (device gradient)
-  if (ws_full > ws_bytes) ws_bytes = ws_full;
+  const size_t ws_bytes = ph_hist_workspace_bytes(chunk, npix, bins, impl);
 
   ph_host_ctx::Job& J = ctx->job;
   for (int pass = 0; pass < 2; ++pass) {
@@ -138,10 +178,10 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
     J.d_hfake = cv.take<float>((size_t)batch * hist_elems);
     J.d_denom_r = cv.take<float>((size_t)batch);
     J.d_denom_f = cv.take<float>((size_t)batch);
-    J.d_grad[0] = cv.take<float>((size_t)chunk * npix * channels);
-    J.d_grad[1] = cv.take<float>((size_t)chunk * npix * channels);
+    J.d_gradfull = with_grad ? cv.take<float>((size_t)batch * npix * channels) : nullptr;
     J.d_dom = cv.take<float>((size_t)bins);
     J.d_ssum = cv.take<double>(1);
+    J.d_one = cv.take<double>(1);
     J.d_loss = cv.take<float>(1);
     J.d_ws = cv.take<char>(ws_bytes);
     J.d_u8[0] = real_is_u8 ? cv.take<unsigned char>((size_t)chunk * npix * 4) : nullptr;
@@ -154,9 +194,12 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   J.batch = batch; J.npix = npix; J.channels = channels; J.bins = bins; J.method = method;
   J.sigma_sqr = sigma_sqr; J.epsilon = epsilon; J.impl = impl; J.chunk = chunk; J.nchunks = nchunks;
   J.ws_bytes = ws_bytes;
+  J.with_grad = with_grad;
 
+  static const double kOne = 1.0;
+  PH_CUDA_OK(cudaMemcpyAsync(J.d_one, &kOne, sizeof(double), cudaMemcpyHostToDevice, ctx->s_in));
   PH_CUDA_OK(cudaMemcpyAsync(J.d_dom, bin_centers_host, sizeof(float) * bins, cudaMemcpyHostToDevice, ctx->s_in));
-  // ---- phase A: upload + forward, chunk by chunk ----
+  // ---- phase 1: upload + forward + unit-scale backward, chunk by chunk ----
   for (int k = 0; k < nchunks; ++k) {
     const int64_t b0 = (int64_t)k * chunk;
     const int64_t nb = batch - b0 < chunk ? batch - b0 : chunk;
@@ -188,6 +231,13 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
                          sigma_sqr, epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0, J.d_ws, ws_bytes,
                          impl, ctx->s_compute);
     if (rc != PH_OK) return rc;
+    if (with_grad) {
+      rc = ph_hist_backward(J.d_fake + (size_t)b0 * npix * channels, nb, npix, channels, J.d_dom, bins, method, sigma_sqr,
+                            epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0, nullptr,
+                            J.d_hreal + (size_t)b0 * hist_elems, J.d_one, 1, nullptr,
+                            J.d_gradfull + (size_t)b0 * npix * channels, J.d_ws, ws_bytes, impl, ctx->s_compute);
+      if (rc != PH_OK) return rc;
+    }
   }
   // ---- the one coupling scalar ----
   int rc = ph_hellinger_ssum(J.d_hreal, J.d_hfake, (int64_t)(batch * hist_elems), J.d_ssum, ctx->s_compute);
@@ -202,14 +252,14 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
                        int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
                        float sigma_sqr, float epsilon, int impl, double* ssum_local_host) {
   return host_hist_begin_impl(ctx, real_host, false, fake_host, batch, npix, channels, bin_centers_host, bins, method,
-                              sigma_sqr, epsilon, impl, ssum_local_host);
+                              sigma_sqr, epsilon, impl, true, ssum_local_host);
 }
 
 int ph_host_hist_begin_u8real(ph_host_ctx* ctx, const uint8_t* real_u8_host, const float* fake_host, int64_t batch,
                               int64_t npix, const float* bin_centers_host, int bins, int method, float sigma_sqr,
                               float epsilon, int impl, double* ssum_local_host) {
   return host_hist_begin_impl(ctx, real_u8_host, true, fake_host, batch, npix, 4, bin_centers_host, bins, method,
-                              sigma_sqr, epsilon, impl, ssum_local_host);
+                              sigma_sqr, epsilon, impl, true, ssum_local_host);
 }
 
 int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
@@ -225,31 +275,26 @@ int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_bat
   int rc = ph_hellinger_finish(J.d_ssum, global_batch, J.d_loss, ctx->s_compute);
   if (rc != PH_OK) return rc;
   PH_CUDA_OK(cudaMemcpyAsync(loss_host, J.d_loss, sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
-  // ---- phase B: backward; the gradient either stays on the device (the consumer — the generator's
-  //      backward — lives there) or is downloaded chunk by chunk, overlapped with the kernels ----
+  // ---- phase 2: scale the stored unit gradient by 1 / (B sqrt(S)); it either stays on the device (the consumer
+  //      — the generator's backward — lives there) or is downloaded chunk by chunk behind its scaling pass ----
+  PH_CHECK_ARG(J.with_grad || (!grad_fake_device && !grad_fake_host), "this job was started without a gradient");
+  const int64_t n_all = J.batch * J.npix * J.channels;
   if (grad_fake_device) {
-    rc = ph_hist_backward(J.d_fake, J.batch, J.npix, J.channels, J.d_dom, J.bins, J.method, J.sigma_sqr, J.epsilon,
-                          J.d_hfake, J.d_denom_f, nullptr, J.d_hreal, J.d_ssum, global_batch, nullptr, grad_fake_device,
-                          J.d_ws, J.ws_bytes, J.impl, ctx->s_compute);
+    rc = launch_grad_rescale(J.d_gradfull, grad_fake_device, n_all, J.d_ssum, global_batch, ctx->s_compute);
     if (rc != PH_OK) return rc;
   }
   if (grad_fake_host) {
     for (int k = 0; k < J.nchunks; ++k) {
       const int64_t b0 = (int64_t)k * J.chunk;
       const int64_t nb = J.batch - b0 < J.chunk ? J.batch - b0 : J.chunk;
-      const size_t n = (size_t)nb * J.npix * J.channels;
-      const int slot = k & 1;
-      if (k >= 2) PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[k - 2], 0));  // grad slot drained
-      rc = ph_hist_backward(J.d_fake + (size_t)b0 * J.npix * J.channels, nb, J.npix, J.channels, J.d_dom, J.bins,
-                            J.method, J.sigma_sqr, J.epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0,
-                            nullptr, J.d_hreal + (size_t)b0 * hist_elems, J.d_ssum, global_batch, nullptr,
-                            J.d_grad[slot], J.d_ws, J.ws_bytes, J.impl, ctx->s_compute);
+      const int64_t n = nb * J.npix * J.channels;
+      float* g = J.d_gradfull + (size_t)b0 * J.npix * J.channels;
+      rc = launch_grad_rescale(g, g, n, J.d_ssum, global_batch, ctx->s_compute);
       if (rc != PH_OK) return rc;
       PH_CUDA_OK(cudaEventRecord(ctx->ev_done[k], ctx->s_compute));
       PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_done[k], 0));
-      PH_CUDA_OK(cudaMemcpyAsync(grad_fake_host + (size_t)b0 * J.npix * J.channels, J.d_grad[slot], n * sizeof(float),
+      PH_CUDA_OK(cudaMemcpyAsync(grad_fake_host + (size_t)b0 * J.npix * J.channels, g, (size_t)n * sizeof(float),
                                  cudaMemcpyDeviceToHost, ctx->s_out));
-      PH_CUDA_OK(cudaEventRecord(ctx->ev_in[k], ctx->s_out));  // reuse ev_in[k] as "slot drained"
     }
   }
   PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
@@ -261,8 +306,8 @@ int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const float* fak
                       int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
                       float sigma_sqr, float epsilon, int impl, float* loss_host, float* grad_fake_host) {
   double ssum = 0.0;
-  int rc = ph_host_hist_begin(ctx, real_host, fake_host, batch, npix, channels, bin_centers_host, bins, method,
-                              sigma_sqr, epsilon, impl, &ssum);
+  int rc = host_hist_begin_impl(ctx, real_host, false, fake_host, batch, npix, channels, bin_centers_host, bins, method,
+                                sigma_sqr, epsilon, impl, grad_fake_host != nullptr, &ssum);
   if (rc != PH_OK) return rc;
   return ph_host_hist_finish(ctx, ssum, batch, loss_host, grad_fake_host, nullptr);
 }

@@ -82,8 +82,9 @@ def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", 
 
 def histogram_loss_begin(real_image, fake_image, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",
                          ctx=None, device=0) -> float:
-    """Phase 1 of a sharded evaluation: upload + both forward passes; returns this shard's sum of squares
-    (all-reduce it over ranks, then call `histogram_loss_finish`)."""
+    """Phase 1 of a sharded evaluation: upload, both forward passes and the backward kernels at unit scale
+    (the gradient depends on the global sum only through the factor 1 / (B sqrt(S)), applied in phase 2);
+    returns this shard's sum of squares (all-reduce it over ranks, then call `histogram_loss_finish`)."""
     fake = _np(fake_image, np.float32, "fake_image")
     real = real_image.numpy() if hasattr(real_image, "numpy") and not isinstance(real_image, np.ndarray) else np.asarray(real_image)
     dom = tf_linspace(-3.0, 3.0, int(size))
