@@ -8,6 +8,8 @@
 // of image b alone.  So phase 1 already runs the backward kernels of every chunk with S = B = 1, right behind
 // that chunk's forward kernels and under the upload of the next chunk, and phase 2 only multiplies the stored
 // gradient by 1 / (B sqrt(S)) — one pass at HBM speed — once the global S is known.
+#include <stdlib.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -161,6 +163,8 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   const size_t img_bytes = (size_t)npix * channels * sizeof(float);
   int64_t chunk = (int64_t)((8u << 20) / img_bytes);
   if (chunk < 296) chunk = 296;  // at least two images per SM, so each chunk takes the whole-image kernel path
+  static const int64_t chunk_env = getenv("PH_HOST_CHUNK") ? atoll(getenv("PH_HOST_CHUNK")) : 0;  // tuning knob
+  if (chunk_env > 0) chunk = chunk_env;
   if (chunk > batch) chunk = batch;
   if (chunk < 1) chunk = 1;
   if (ceil_div(batch, chunk) > ph_host_ctx::kMaxChunks) chunk = ceil_div(batch, ph_host_ctx::kMaxChunks);
