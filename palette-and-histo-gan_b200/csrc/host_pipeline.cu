@@ -17,7 +17,7 @@
 
 struct ph_host_ctx {
   int device = 0;
-  cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+  cudaStream_t s_in = nullptr, s_compute = nullptr, s_compute2 = nullptr, s_out = nullptr;
   // grow-only device arena
   void* arena = nullptr;
   size_t arena_bytes = 0;
@@ -25,6 +25,7 @@ struct ph_host_ctx {
   cudaEvent_t ev_in[kMaxChunks];
   cudaEvent_t ev_done[kMaxChunks];
   cudaEvent_t ev_free[2];
+  cudaEvent_t ev_join;
   bool events_ready = false;
   // state carried from ph_host_hist_begin to ph_host_hist_finish
   struct Job {
@@ -33,6 +34,7 @@ struct ph_host_ctx {
     double *d_ssum, *d_one;
     bool with_grad;
     char* d_ws;
+    char* d_ws2;
     size_t ws_bytes;
     int64_t batch, npix, chunk;
     int channels, bins, method, impl, nchunks;
@@ -118,12 +120,14 @@ int ph_host_ctx_create(int device, ph_host_ctx** out) {
   ctx->device = device;
   PH_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
   PH_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+  PH_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s_compute2, cudaStreamNonBlocking));
   PH_CUDA_OK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
   for (int i = 0; i < ph_host_ctx::kMaxChunks; ++i) {
     PH_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
     PH_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
   }
   for (int i = 0; i < 2; ++i) PH_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming));
+  PH_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   ctx->events_ready = true;
   *out = ctx;
   return PH_OK;
@@ -139,9 +143,11 @@ void ph_host_ctx_destroy(ph_host_ctx* ctx) {
       cudaEventDestroy(ctx->ev_done[i]);
     }
     for (int i = 0; i < 2; ++i) cudaEventDestroy(ctx->ev_free[i]);
+    cudaEventDestroy(ctx->ev_join);
   }
   if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->s_compute2) cudaStreamDestroy(ctx->s_compute2);
   if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if (ctx->arena) cudaFree(ctx->arena);
   delete ctx;
@@ -188,6 +194,7 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
     J.d_one = cv.take<double>(1);
     J.d_loss = cv.take<float>(1);
     J.d_ws = cv.take<char>(ws_bytes);
+    J.d_ws2 = cv.take<char>(ws_bytes);
     J.d_u8[0] = real_is_u8 ? cv.take<unsigned char>((size_t)chunk * npix * 4) : nullptr;
     J.d_u8[1] = real_is_u8 ? cv.take<unsigned char>((size_t)chunk * npix * 4) : nullptr;
     if (pass == 0) {
@@ -220,30 +227,36 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
     PH_CUDA_OK(cudaMemcpyAsync(J.d_fake + (size_t)b0 * npix * channels, fake_host + (size_t)b0 * npix * channels,
                                n * sizeof(float), cudaMemcpyHostToDevice, ctx->s_in));
     PH_CUDA_OK(cudaEventRecord(ctx->ev_in[k], ctx->s_in));
-    PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_in[k], 0));
+    // chunks alternate between two compute streams: the kernels of chunk k+1 fill the SMs that the (persistent)
+    // kernels of chunk k vacate in their tails, and the small prologue kernels run beside the large ones
+    cudaStream_t sc = slot == 0 ? ctx->s_compute : ctx->s_compute2;
+    char* ws = slot == 0 ? J.d_ws : J.d_ws2;
+    PH_CUDA_OK(cudaStreamWaitEvent(sc, ctx->ev_in[k], 0));
     if (real_is_u8) {  // blacken + normalise on the device (dataset_utils.py:66-77)
-      int rcu = ph_u8_to_float_image(J.d_u8[slot], nb * npix, 1, 1, J.d_real[slot], ctx->s_compute);
+      int rcu = ph_u8_to_float_image(J.d_u8[slot], nb * npix, 1, 1, J.d_real[slot], sc);
       if (rcu != PH_OK) return rcu;
     }
     int rc = ph_hist_forward(J.d_real[slot], nb, npix, channels, J.d_dom, bins, method, sigma_sqr, epsilon,
-                             J.d_hreal + (size_t)b0 * hist_elems, J.d_denom_r + b0, J.d_ws, ws_bytes,
+                             J.d_hreal + (size_t)b0 * hist_elems, J.d_denom_r + b0, ws, ws_bytes,
                              impl | PH_IMPL_DEDUP,  // real images are dataset sprites: contract unique colours
-                             ctx->s_compute);
+                             sc);
     if (rc != PH_OK) return rc;
-    PH_CUDA_OK(cudaEventRecord(ctx->ev_free[slot], ctx->s_compute));
+    PH_CUDA_OK(cudaEventRecord(ctx->ev_free[slot], sc));
     rc = ph_hist_forward(J.d_fake + (size_t)b0 * npix * channels, nb, npix, channels, J.d_dom, bins, method,
-                         sigma_sqr, epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0, J.d_ws, ws_bytes,
-                         impl, ctx->s_compute);
+                         sigma_sqr, epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0, ws, ws_bytes,
+                         impl, sc);
     if (rc != PH_OK) return rc;
     if (with_grad) {
       rc = ph_hist_backward(J.d_fake + (size_t)b0 * npix * channels, nb, npix, channels, J.d_dom, bins, method, sigma_sqr,
                             epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0, nullptr,
                             J.d_hreal + (size_t)b0 * hist_elems, J.d_one, 1, nullptr,
-                            J.d_gradfull + (size_t)b0 * npix * channels, J.d_ws, ws_bytes, impl, ctx->s_compute);
+                            J.d_gradfull + (size_t)b0 * npix * channels, ws, ws_bytes, impl, sc);
       if (rc != PH_OK) return rc;
     }
   }
   // ---- the one coupling scalar ----
+  PH_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->s_compute2));
+  PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_join, 0));
   int rc = ph_hellinger_ssum(J.d_hreal, J.d_hfake, (int64_t)(batch * hist_elems), J.d_ssum, ctx->s_compute);
   if (rc != PH_OK) return rc;
   PH_CUDA_OK(cudaMemcpyAsync(ssum_local_host, J.d_ssum, sizeof(double), cudaMemcpyDeviceToHost, ctx->s_compute));
