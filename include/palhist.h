@@ -170,6 +170,13 @@ PH_API int ph_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npi
                        int64_t palette_batch, int palette_rows, int channels, int32_t* out,
                        void* stream);
 
+/* pix2pix_model.py:283-287 (`generate`: argmax over the softmax channels, int32, first maximum) fused with
+ * io_utils.py:96-103 `indexed_to_rgba` (:356, :446-447): probabilities (batch,npix,depth) float32 ->
+ * indexed (batch,npix) int32 and/or rgba (batch,npix,4) int32 = palette[b or 0, argmax, :]; either output may
+ * be NULL.  An arg-max >= palette_rows gives a row of zeros like ph_indexed_to_rgba. */
+PH_API int ph_argmax_indexed(const float* probabilities, int64_t batch, int64_t npix, int depth, const int32_t* palette,
+                      int64_t palette_batch, int palette_rows, int32_t* indexed, int32_t* rgba, void* stream);
+
 /* dataset_utils.py:138-151 glue, batched: shared palette of source||target (rows interleaved
  * src px0, tgt px0, src px1, ... as the channel-axis concat + reshape(-1,4) produces), then both
  * index images.  source/target (batch,npix,4) int32. */

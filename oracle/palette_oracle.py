@@ -130,3 +130,22 @@ def normalize(image):  # dataset_utils.py:39-48
 
 def denormalize(image):  # dataset_utils.py:51-60
     return (np.asarray(image, np.float32) + np.float32(1.0)) * np.float32(127.5)
+
+
+def argmax_indexed(probabilities):
+    """`generate` of the indexed model (pix2pix_model.py:283-287): arg-max over the last axis as int32 with a
+    trailing singleton axis; first maximum wins, NaNs are never selected (all-NaN / all -inf row -> 0)."""
+    p = np.asarray(probabilities, dtype=np.float32)
+    clean = np.where(np.isnan(p), -np.inf, p)
+    return np.argmax(clean, axis=-1).astype(np.int32)[..., None]
+
+
+def probabilities_to_rgba(probabilities, palette):
+    """`indexed_to_rgba(generate(...), palette)` (pix2pix_model.py:356, 446-447)."""
+    idx = argmax_indexed(probabilities)
+    pal = np.asarray(palette, dtype=np.int32)
+    if idx.ndim == 4 and pal.ndim == 3:
+        return np.stack([indexed_to_rgba(idx[b], pal[b]) for b in range(idx.shape[0])])
+    if idx.ndim == 4:
+        return np.stack([indexed_to_rgba(idx[b], pal) for b in range(idx.shape[0])])
+    return indexed_to_rgba(idx, pal)

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "ph_one_hot": (_int, [_p, _i64, _int, _p, _p]),
     "ph_u8_to_float_image": (_int, [_p, _i64, _int, _int, _p, _p]),
     "ph_indexed_to_rgba": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _p]),
+    "ph_argmax_indexed": (_int, [_p, _i64, _i64, _int, _p, _i64, _int, _p, _p, _p]),
     "ph_load_indexed_images": (_int, [_p, _p, _i64, _i64, _int, _p, _p, _p, _p, _p]),
     "ph_host_ctx_create": (_int, [_int, C.POINTER(_p)]),
     "ph_host_ctx_destroy": (None, [_p]),

@@ -256,6 +256,21 @@ int ph_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npix, cons
   return PH_OK;
 }
 
+int ph_argmax_indexed(const float* probabilities, int64_t batch, int64_t npix, int depth, const int32_t* palette,
+                      int64_t palette_batch, int palette_rows, int32_t* indexed, int32_t* rgba, void* stream) {
+  PH_CHECK_ARG(probabilities && (indexed || rgba), "NULL pointer argument");
+  PH_CHECK_ARG(batch >= 0 && npix >= 0 && depth > 0, "bad shape");
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(probabilities) & 15) == 0, "probabilities must be 16-byte aligned");
+  if (rgba) {
+    PH_CHECK_ARG(palette != nullptr && palette_rows > 0, "rgba output needs a palette");
+    PH_CHECK_ARG(palette_batch == 1 || palette_batch == batch, "palette_batch must be 1 or batch");
+    PH_CHECK_ARG((reinterpret_cast<uintptr_t>(palette) & 15) == 0 && (reinterpret_cast<uintptr_t>(rgba) & 15) == 0,
+                 "RGBA palette / rgba must be 16-byte aligned");
+  }
+  return launch_argmax_indexed(probabilities, batch, npix, depth, palette, palette_batch, palette_rows, indexed, rgba,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int ph_load_indexed_images(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
                            int ordering, int32_t* source_indexed, int32_t* target_indexed,
                            int32_t* palette, int32_t* ncolors, void* stream) {

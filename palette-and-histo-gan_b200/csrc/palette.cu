@@ -349,6 +349,92 @@ __global__ void __launch_bounds__(256) indexed_to_rgba_kernel(
 }
 
 // =============================================================================================
+// Indexed-model inference (pix2pix_model.py:283-287 `generate`: argmax over the 256 softmax channels, int32;
+// :356 / :446-447 `indexed_to_rgba` of the result) in one pass: 1 KiB read per pixel, 4 + 16 B written — the
+// HBM-bound twin of the one-hot writer.  One warp per pixel row (two coalesced 512 B loads when depth is a
+// multiple of 128), running first-maximum in index order per lane (strict >: ties keep the earlier index and
+// a NaN is never selected, as in the reference's CPU arg-max reducer; a row without any value > -inf gives 0),
+// then a warp arg-max that prefers the smaller index on equal values.  Each warp handles 32 consecutive pixels and lane p keeps pixel p's
+// result, so indices and colours leave as coalesced 128 B / 512 B stores.
+// =============================================================================================
+__device__ __forceinline__ void argmax_step(float v, int i, float& best, int& bi) {
+  if (v > best) { best = v; bi = i; }
+}
+__device__ __forceinline__ int warp_argmax(float best, int bi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (ob > best || (ob == best && (bi < 0 || oi < bi)))) { best = ob; bi = oi; }
+  }
+  return bi < 0 ? 0 : bi;
+}
+__global__ void __launch_bounds__(256) argmax_indexed_kernel(
+    const float* __restrict__ probs, int64_t npix_total, int64_t npix, int depth, const int* __restrict__ palette,
+    int64_t palette_batch, int palette_rows, int* __restrict__ indexed, int* __restrict__ rgba) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp * 32; base < npix_total; base += nwarps * 32) {
+    int mine = 0;
+    const int cnt = (int)min((int64_t)32, npix_total - base);
+    if (depth == 256) {
+      // the reference's depth (MAX_PALETTE_SIZE): four rows = eight 512 B loads in flight per warp
+      for (int k0 = 0; k0 < cnt; k0 += 4) {
+        float4 q[4][2];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float* row = probs + (base + min(k0 + r, cnt - 1)) * 256;
+          q[r][0] = __ldcs(reinterpret_cast<const float4*>(row) + lane);
+          q[r][1] = __ldcs(reinterpret_cast<const float4*>(row + 128) + lane);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float best = -INFINITY;
+          int bi = -1;
+          const int i0 = lane * 4;
+          argmax_step(q[r][0].x, i0, best, bi); argmax_step(q[r][0].y, i0 + 1, best, bi);
+          argmax_step(q[r][0].z, i0 + 2, best, bi); argmax_step(q[r][0].w, i0 + 3, best, bi);
+          argmax_step(q[r][1].x, i0 + 128, best, bi); argmax_step(q[r][1].y, i0 + 129, best, bi);
+          argmax_step(q[r][1].z, i0 + 130, best, bi); argmax_step(q[r][1].w, i0 + 131, best, bi);
+          const int win = warp_argmax(best, bi);
+          if (lane == k0 + r) mine = win;
+        }
+      }
+    } else {
+      const bool vec = (depth & 127) == 0;
+      for (int k = 0; k < cnt; ++k) {
+        const float* row = probs + (base + k) * depth;
+        float best = -INFINITY;
+        int bi = -1;
+        if (vec) {
+          for (int c0 = 0; c0 < depth; c0 += 128) {
+            const float4 q = __ldcs(reinterpret_cast<const float4*>(row + c0) + lane);
+            const int i0 = c0 + lane * 4;
+            argmax_step(q.x, i0, best, bi); argmax_step(q.y, i0 + 1, best, bi);
+            argmax_step(q.z, i0 + 2, best, bi); argmax_step(q.w, i0 + 3, best, bi);
+          }
+        } else {
+          for (int i = lane; i < depth; i += 32) argmax_step(__ldcs(row + i), i, best, bi);
+        }
+        const int win = warp_argmax(best, bi);
+        if (lane == k) mine = win;
+      }
+    }
+    if (lane < cnt) {
+      const int64_t px = base + lane;
+      if (indexed) indexed[px] = mine;
+      if (rgba) {
+        const int64_t b = px / npix;
+        const int4* pal = reinterpret_cast<const int4*>(palette) + (palette_batch == 1 ? 0 : b) * (int64_t)palette_rows;
+        const int4 c = mine < palette_rows ? __ldg(pal + mine) : make_int4(0, 0, 0, 0);
+        reinterpret_cast<int4*>(rgba)[px] = c;
+      }
+    }
+  }
+}
+
+// =============================================================================================
 // Loader-side pixel prep (dataset_utils.py:66-77 after decode_png): uint8 RGBA -> float32 with
 // blacken_transparent_pixels (:11-20, alpha == 0 -> the whole pixel becomes 0) and normalize
 // (:39-48, x/127.5 - 1) in one pass.  4 B in, 16 B out per pixel; lets the host ship sprites as the
@@ -434,6 +520,19 @@ int launch_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot,
   if (grid > cap) grid = cap;
   one_hot_kernel<<<(unsigned)grid, 256, 0, st>>>(indexed, n, depth, one_hot);
   PH_LAUNCH_OK("one_hot_kernel");
+  return PH_OK;
+}
+
+int launch_argmax_indexed(const float* probs, int64_t batch, int64_t npix, int depth, const int32_t* palette,
+                          int64_t palette_batch, int palette_rows, int32_t* indexed, int32_t* rgba, cudaStream_t st) {
+  const int64_t total = batch * npix;
+  if (total == 0) return PH_OK;
+  int64_t grid = ceil_div(ceil_div(total, 32), 8);  // 8 warps per CTA, 32 pixels per warp and round
+  const int64_t cap = (int64_t)cached_sm_count() * 8;
+  if (grid > cap) grid = cap;
+  argmax_indexed_kernel<<<(unsigned)grid, 256, 0, st>>>(probs, total, npix, depth, palette, palette_batch, palette_rows,
+                                                        indexed, rgba);
+  PH_LAUNCH_OK("argmax_indexed_kernel");
   return PH_OK;
 }
 

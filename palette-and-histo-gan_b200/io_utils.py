@@ -161,6 +161,39 @@ def indexed_to_rgba(indexed_image, palette):
     return to_caller_framework(out if batched else out[0], indexed_image)
 
 
+def probabilities_to_indexed(probabilities, palette=None):
+    """Inference ops of the indexed model in one pass: `tf.expand_dims(tf.argmax(probs, -1, "int32"), -1)`
+    (pix2pix_model.py:283-287) and, when `palette` is given, `indexed_to_rgba` of the result (:356, :446-447).
+    probabilities (H,W,D) or (B,H,W,D) float32; palette (256,4) or (B,256,4) int32.
+    Returns indexed (…,1) int32, or (indexed, rgba (…,4) int32) with a palette."""
+    pr = require_cuda(from_any(probabilities, name="probabilities"), torch.float32, name="probabilities")
+    batched = pr.dim() == 4
+    if not batched:
+        pr = pr.unsqueeze(0)
+    if pr.dim() != 4:
+        raise ValueError(f"probabilities must be (H,W,D) or (B,H,W,D), got {tuple(pr.shape)}")
+    b, h, w, depth = pr.shape
+    idx = torch.empty((b, h, w, 1), dtype=torch.int32, device=pr.device)
+    pal = rgba = None
+    pal_b = rows = 0
+    if palette is not None:
+        pal = require_cuda(from_any(palette, name="palette"), torch.int32, name="palette")
+        if pal.dim() == 2:
+            pal = pal.unsqueeze(0)
+        if pal.shape[0] not in (1, b) or pal.shape[2] != 4:
+            raise ValueError("palette must be (256,4) or (B,256,4) with B matching the image batch")
+        pal_b, rows = pal.shape[0], pal.shape[1]
+        rgba = torch.empty((b, h, w, 4), dtype=torch.int32, device=pr.device)
+    if b and h * w:
+        with torch.cuda.device(pr.device):
+            _lib.call("ph_argmax_indexed", ptr(pr), b, h * w, depth, ptr(pal) if pal is not None else None, pal_b, rows,
+                      ptr(idx), ptr(rgba) if rgba is not None else None, stream_ptr(pr.device))
+    idx = to_caller_framework(idx if batched else idx[0], probabilities)
+    if rgba is None:
+        return idx
+    return idx, to_caller_framework(rgba if batched else rgba[0], probabilities)
+
+
 def one_hot(indices, depth=MAX_PALETTE_SIZE):
     """`tf.reshape(tf.one_hot(idx, depth, axis=-1), [B,H,W,-1])` of pix2pix_model.py:300-301:
     (…,1) or (…) int32 -> (…,depth) float32; an index outside [0,depth) gives an all-zero row."""
@@ -174,4 +207,5 @@ def one_hot(indices, depth=MAX_PALETTE_SIZE):
 
 
 __all__ = ["extract_palette", "rgba_to_single_int", "rgba_to_indexed", "indexed_to_rgba", "one_hot",
+           "probabilities_to_indexed",
            "PaletteOverflowError", "MAX_PALETTE_SIZE", "INVALID_INDEX_COLOR"]

@@ -187,3 +187,37 @@ def test_fused_loader_filler_colour_and_batching(P, cuda):
     # un-batched call keeps the reference shapes
     s1, t1, p1 = P.dataset_utils.load_indexed_images(dev_i32(src[0], cuda), dev_i32(tgt[0], cuda), "grayness")
     assert tuple(s1.shape) == (16, 16, 1) and tuple(p1.shape) == (256, 4)
+
+
+def test_probabilities_to_indexed_and_rgba(P, cuda, sprites):
+    """f3 of SURVEY.md §8f: argmax over the softmax channels + palette gather in one kernel, bit-exact."""
+    rng = np.random.default_rng(5)
+    src, tgt = sprites["front"][:6], sprites["right"][:6]
+    _, t_idx, pal = P.dataset_utils.load_indexed_images(dev_i32(src, cuda), dev_i32(tgt, cuda), "grayness")
+    # probabilities whose arg-max is the target index, with exact ties, NaNs and -inf sprinkled in
+    probs = rng.random((6, 64, 64, 256), dtype=np.float32) * 0.5
+    ti = t_idx.cpu().numpy()[..., 0]
+    np.put_along_axis(probs, ti[..., None].astype(np.int64), 0.75, axis=-1)
+    probs[0, 0, :, 200] = 0.75          # tie with a later (or earlier) channel: first maximum wins
+    probs[0, 1, :, 3] = np.nan          # NaN is never selected
+    probs[0, 2, :, :] = np.nan          # all-NaN row -> 0
+    probs[0, 3, :, :] = -np.inf         # all -inf row -> 0
+    probs[0, 4, :, 0] = np.nan
+    want_idx = po.argmax_indexed(probs)
+    want_rgba = po.probabilities_to_rgba(probs, pal.cpu().numpy())
+    got_idx, got_rgba = P.io_utils.probabilities_to_indexed(torch.from_numpy(probs).to(cuda), pal)
+    assert got_idx.dtype == torch.int32 and tuple(got_idx.shape) == (6, 64, 64, 1)
+    assert np.array_equal(got_idx.cpu().numpy(), want_idx)
+    assert np.array_equal(got_rgba.cpu().numpy(), want_rgba)
+    # on clean rows the round trip reproduces the target sprite
+    assert np.array_equal(got_rgba.cpu().numpy()[1:], tgt[1:].astype(np.int32))
+    # index-only call, single image, shared palette, depth that is not a multiple of 128
+    only = P.io_utils.probabilities_to_indexed(torch.from_numpy(probs[1]).to(cuda))
+    assert np.array_equal(only.cpu().numpy(), want_idx[1])
+    odd = rng.standard_normal((2, 5, 7, 37)).astype(np.float32)
+    odd[0, 0, 0, 5] = odd[0, 0, 0].max() + 1.0
+    odd[0, 0, 0, 30] = odd[0, 0, 0, 5]
+    pal1 = pal[0]
+    gi, gr = P.io_utils.probabilities_to_indexed(torch.from_numpy(odd).to(cuda), pal1)
+    assert np.array_equal(gi.cpu().numpy(), po.argmax_indexed(odd))
+    assert np.array_equal(gr.cpu().numpy(), po.probabilities_to_rgba(odd, pal1.cpu().numpy()))

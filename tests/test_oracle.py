@@ -157,3 +157,13 @@ def test_rbf_method_and_unknown_method():
     assert ho.rel_l2(res["grad"], grad.numpy()) < 1e-10
     with pytest.raises(ValueError):
         ho.rgbuv_histogram_f64(img, 16, method="thresholding")
+
+
+def test_argmax_indexed_semantics():
+    """Indexed-model inference ops (pix2pix_model.py:283-287, 356): first maximum, NaN never selected."""
+    p = np.array([[0.1, 0.7, 0.7, 0.2], [np.nan, 0.3, 0.1, 0.3], [np.nan] * 4, [-np.inf] * 4], np.float32)[None]
+    idx = po.argmax_indexed(p)
+    assert idx.dtype == np.int32 and idx.shape == (1, 4, 1)
+    assert idx[0, :, 0].tolist() == [1, 1, 0, 0]
+    pal = np.arange(16, dtype=np.int32).reshape(4, 4)
+    assert np.array_equal(po.probabilities_to_rgba(p, pal)[0], pal[[1, 1, 0, 0]])
