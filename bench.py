@@ -373,6 +373,11 @@ def run_ours(args, rank, world, local_rank):
         clocks = sampler.stop(t0, t1)
         palette = bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostapi)
 
+    # ---- the caller (cfgD): pix2pix "histogram" model step, global batch 512 ----
+    generator_step = None
+    if not args.no_generator_step:
+        generator_step = bench_generator_step(torch, dev, world, rank, distributed, barrier)
+
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -396,7 +401,7 @@ def run_ours(args, rank, world, local_rank):
                        "real_images": "palette sprites, contracted over their unique colours (PH_IMPL_DEDUP, exact); "
                                       "fake images dense"},
             "loss": loss_val, "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "palette": palette,
+            "clocks": clocks, "palette": palette, "generator_step": generator_step,
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
@@ -404,6 +409,55 @@ def run_ours(args, rank, world, local_rank):
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_generator_step(torch, dev, world, rank, distributed, barrier):
+    """cfgD: one optimisation step of the side2side "histogram" model (U-Net generator + PatchGAN through torch /
+    cuDNN, generator loss = BCE + 30 L1 + 1 Hellinger histogram loss through the new kernels), global batch 512
+    sharded over the ranks with DistributedDataParallel.  The networks are library code: reported for context
+    (what share of a real training step the hot path is), not as a kernel result."""
+    import torch.distributed as dist
+    from palette_and_histo_gan_b200 import generator_step as gs
+    from palette_and_histo_gan_b200 import histogram as H
+
+    gb = 512
+    lo, hi = shard_bounds(gb, world, rank)
+    real_np, _ = make_hist_inputs(gb, 48)
+    src_np, _ = make_hist_inputs(gb, 49)
+    real = torch.from_numpy(real_np[lo:hi]).to(dev)
+    src = torch.from_numpy(src_np[lo:hi]).to(dev)
+    step = gs.Pix2PixHistogramStep(dev, distributed=distributed)
+    for _ in range(3):
+        step.train_step(src, real)
+    n = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        out = step.train_step(src, real)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+    # the histogram term alone on the same shard (forward of both images + Hellinger + backward)
+    fake = step.generator(src).detach().requires_grad_(True)
+    for _ in range(2):
+        H.histogram_loss(real, fake, group=True if distributed else None).backward()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(n):
+        fake.grad = None
+        H.histogram_loss(real, fake, group=True if distributed else None).backward()
+    h1.record()
+    barrier()
+    hms = torch.tensor([h0.elapsed_time(h1) / n], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(hms, op=dist.ReduceOp.MAX)
+    return {"workload": "cfgD: Pix2PixHistogramModel.train_step, global batch 512 of 64x64 RGBA, U-Net 29.3 M parameters + "
+                        "PatchGAN (torch/cuDNN), Adam, lambda_l1 30, lambda_histogram 1",
+            "images_per_s": gb / (float(ms) * 1e-3), "ms_per_step": float(ms), "per_gpu_batch": hi - lo,
+            "histogram_loss_ms": float(hms), "histogram_loss_share": float(hms) / float(ms),
+            "losses": {k: float(v) for k, v in out.items()}}
 
 
 def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostapi):
@@ -515,6 +569,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--engine", choices=["auto", "simt", "tc"], default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-generator-step", action="store_true", help="skip the cfgD caller measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
