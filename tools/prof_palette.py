@@ -10,5 +10,6 @@ for _ in range(3):
     s_idx, t_idx, pal = dataset_utils.load_indexed_images(src, tgt, "grayness", check=False)
     oh = io_utils.one_hot(t_idx)
     idx2, oh2 = io_utils.rgba_to_indexed(tgt, pal, with_one_hot=True)
+    idx3, rgba3 = io_utils.probabilities_to_indexed(oh, pal)
 torch.cuda.synchronize()
 print("ok")
