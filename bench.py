@@ -381,9 +381,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, times = cpu_hist_images_per_s(32, 6)
+        v, cores, times = cpu_hist_images_per_s(32, 24)
         cpu_baseline = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"6 x 32 image pairs (cfgA shape), torch-CPU op-for-op port of histogram.py with "
+                        "sample": f"24 x 32 image pairs (cfgA shape), torch-CPU op-for-op port of histogram.py with "
                                   f"autograd, {sum(times):.1f} s; TensorFlow is not installable in this image",
                         "palette_gpix_per_s": cpu_palette_gpix_per_s(64)}
 
@@ -391,7 +391,7 @@ def run_ours(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core emulation when engine=tc, fp32 FFMA when simt)",
+            "vs_baseline": None, "dtype": "f32 (tcgen05 kind::f16 with fp16 hi+lo operand split = fp32-accurate 3-product emulation, fp32 accumulate, when engine=tc; fp32 FFMA when simt)",
             "data": "synthetic",
             "config": {"workload": "cfgC: histogram loss fwd(real)+fwd(fake)+Hellinger+bwd, 64x64 RGBA, 64 bins",
                        "global_batch": GLOBAL_BATCH, "per_gpu_batch": local_b, "bins": BINS,
