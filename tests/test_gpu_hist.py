@@ -301,3 +301,67 @@ def test_sharded_path_single_rank_nccl(H, cuda):
     finally:
         H.OVERLAP_MIN_WORLD = 4
         dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("method,sigma", [("inverse-quadratic", 0.002), ("inverse-quadratic", 0.2),
+                                          ("inverse-quadratic", 1.5), ("RBF", 0.6), ("RBF", 2.0)])  # RBF below ~0.5 underflows to exact zeros: 0/0 in the loss
+def test_tensor_core_operand_scaling_over_sigma(H, cuda, method, sigma):
+    """The tcgen05 engine scales every operand into fp16's range with powers of two chosen from sigma
+    (hist_tc_bwd.cu host side): the result must not depend on that choice."""
+    rng = np.random.default_rng(31)
+    real = np.tanh(rng.standard_normal((3, 24, 24, 4))).astype(np.float32)
+    fake = np.tanh(rng.standard_normal((3, 24, 24, 4))).astype(np.float32)
+    ref = ho.hist_loss_and_grad_f64(real, fake, method=method, sigma=sigma)
+    f = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+    loss = H.histogram_loss(torch.from_numpy(real).to(cuda), f, method=method, sigma=sigma, impl="tc")
+    loss.backward()
+    assert abs(float(loss.detach()) - ref["loss"]) / ref["loss"] < LOSS_TOL
+    assert ho.rel_l2(f.grad.cpu().numpy(), ref["grad"]) < GRAD_TOL
+    hist = H.calculate_rgbuv_histogram(torch.from_numpy(fake).to(cuda), method=method, sigma=sigma, impl="tc")
+    # the forward takes float32 logs like the reference: an error of 1e-7 in u is 5e-5 bin widths at sigma = 0.002
+    err = ho.rel_l2(hist.cpu().numpy(), ref["hist_fake"])
+    assert err < (HIST_TOL if sigma >= 0.02 else 2e-4), err
+
+
+@pytest.mark.parametrize("scale", [1e-12, 1.0, 1e9])
+def test_tensor_core_backward_any_upstream_magnitude(H, cuda, scale):
+    """G^ is rescaled per image by a power of two before its fp16 split: upstream gradients of any magnitude
+    (and images whose gradient rows differ by orders of magnitude) give the CUDA-core engine's result."""
+    rng = np.random.default_rng(32)
+    img = np.tanh(rng.standard_normal((4, 32, 32, 4))).astype(np.float32)
+    up = rng.standard_normal((4, 64, 64, 3)).astype(np.float32) * np.float32(scale)
+    up[1] *= np.float32(1e-4)   # per-image dynamic range
+    up[2, :, :, 0] *= np.float32(1e3)
+    grads = {}
+    for impl in ("simt", "tc"):
+        x = torch.from_numpy(img).to(cuda).requires_grad_(True)
+        H.calculate_rgbuv_histogram(x, impl=impl).backward(torch.from_numpy(up).to(cuda))
+        grads[impl] = x.grad.cpu().numpy().astype(np.float64)
+    for b in range(4):
+        assert ho.rel_l2(grads["tc"][b], grads["simt"][b]) < GRAD_TOL
+    assert np.isfinite(grads["tc"]).all()
+
+
+def test_host_pipeline_chunks_and_three_channels(cuda):
+    """Several chunks on the two compute streams, unit-scale backward + rescale, gradient downloaded; and RGB
+    (3-channel) images, whose gradient chunks are not 16-byte multiples."""
+    from palette_and_histo_gan_b200 import hostapi
+
+    rng = np.random.default_rng(33)
+    real = np.tanh(rng.standard_normal((700, 8, 8, 4))).astype(np.float32)
+    fake = np.tanh(rng.standard_normal((700, 8, 8, 4))).astype(np.float32)
+    loss, grad = hostapi.histogram_loss(real, fake)   # 3 chunks of 296 images
+    ref = ho.hist_loss_and_grad_f64(real[:40], fake[:40], global_batch=700,
+                                    global_ssum=None)  # per-image terms only need the global scalars
+    full = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+    from palette_and_histo_gan_b200 import histogram as Hm
+    l_dev = Hm.histogram_loss(torch.from_numpy(real).to(cuda), full, impl="simt")
+    l_dev.backward()
+    assert abs(loss - float(l_dev.detach())) / float(l_dev.detach()) < LOSS_TOL
+    assert ho.rel_l2(grad, full.grad.cpu().numpy()) < GRAD_TOL
+    del ref
+    real3, fake3 = real[:5, :, :, :3].copy(), fake[:5, :, :, :3].copy()
+    ref3 = ho.hist_loss_and_grad_f64(real3, fake3)
+    loss3, grad3 = hostapi.histogram_loss(real3, fake3)
+    assert abs(loss3 - ref3["loss"]) / ref3["loss"] < LOSS_TOL
+    assert ho.rel_l2(grad3, ref3["grad"]) < GRAD_TOL
