@@ -99,6 +99,15 @@ PH_API int ph_hist_forward(const float* image, int64_t batch, int64_t npix, int 
                     float* hist, float* denom, void* workspace, size_t workspace_bytes, int impl,
                     void* stream);
 
+/* The generator-loss call site (pix2pix_model.py:243-245) as one launch per image set: histogram of the `fake`
+ * images as above and, while each normalised histogram is still on chip, this batch's share of the Hellinger sum
+ * of squares  sum (sqrt(hist) - sqrt(hist_true))^2  (histogram.py:88) against the histograms of the real images,
+ * added into the device double *ssum (zeroed first unless accumulate != 0, so a batch can be fed in chunks). */
+PH_API int ph_hist_forward_ssum(const float* image, int64_t batch, int64_t npix, int channels, const float* bin_centers,
+                         int bins, int method, float sigma_sqr, float epsilon, float* hist, float* denom,
+                         const float* hist_true, double* ssum, int accumulate, void* workspace,
+                         size_t workspace_bytes, int impl, void* stream);
+
 /* histogram.py:5-32 `calculate_component_histogram`: un-normalised (batch,bins,bins) histogram of one
  * component against two projections, intensities (batch,npix) given. */
 PH_API int ph_component_histogram(const float* component, const float* projection1, const float* projection2,

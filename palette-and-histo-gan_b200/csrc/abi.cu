@@ -86,30 +86,52 @@ size_t ph_hist_workspace_bytes(int64_t batch, int64_t npix, int bins, int impl) 
   return s;
 }
 
-int ph_hist_forward(const float* image, int64_t batch, int64_t npix, int channels,
-                    const float* bin_centers, int bins, int method, float sigma_sqr, float epsilon,
-                    float* hist, float* denom, void* workspace, size_t workspace_bytes, int impl,
-                    void* stream) {
+static int hist_forward_impl(const float* image, int64_t batch, int64_t npix, int channels, const float* bin_centers,
+                             int bins, int method, float sigma_sqr, float epsilon, float* hist, float* denom,
+                             const float* hist_true, double* ssum, int accumulate, void* workspace,
+                             size_t workspace_bytes, int impl, void* stream) {
   int rc = check_hist_args(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr);
   if (rc != PH_OK) return rc;
   PH_CHECK_ARG(hist != nullptr && denom != nullptr, "hist / denom must not be NULL");
   PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
                "bad impl %d", impl);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ssum != nullptr && !accumulate) PH_CUDA_OK(cudaMemsetAsync(ssum, 0, sizeof(double), st));
   if (batch == 0) return PH_OK;
   const int eng = resolve_impl(impl, npix, bins, method);
   PH_CHECK_ARG(workspace != nullptr && workspace_bytes >= ph_hist_workspace_bytes(batch, npix, bins, eng),
                "workspace too small: %zu < %zu", workspace_bytes, ph_hist_workspace_bytes(batch, npix, bins, eng));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (eng == PH_IMPL_TC) {
     if (!tc_supported(npix, bins, method)) {
       set_error("tensor-core engine does not cover npix=%lld bins=%d method=%d", (long long)npix, bins, method);
       return PH_ERR_UNSUPPORTED;
     }
     return tc_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist,
-                           denom, workspace, (impl & PH_IMPL_DEDUP) != 0, st);
+                           denom, workspace, (impl & PH_IMPL_DEDUP) != 0, hist_true, ssum, st);
   }
-  return simt_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist,
-                           denom, workspace, st);
+  rc = simt_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist, denom,
+                         workspace, st);
+  if (rc != PH_OK || ssum == nullptr) return rc;
+  return launch_hellinger_ssum_accumulate(hist_true, hist, batch * (int64_t)bins * bins * 3, ssum, st);
+}
+
+int ph_hist_forward(const float* image, int64_t batch, int64_t npix, int channels,
+                    const float* bin_centers, int bins, int method, float sigma_sqr, float epsilon,
+                    float* hist, float* denom, void* workspace, size_t workspace_bytes, int impl,
+                    void* stream) {
+  return hist_forward_impl(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist, denom,
+                           nullptr, nullptr, 0, workspace, workspace_bytes, impl, stream);
+}
+
+int ph_hist_forward_ssum(const float* image, int64_t batch, int64_t npix, int channels, const float* bin_centers,
+                         int bins, int method, float sigma_sqr, float epsilon, float* hist, float* denom,
+                         const float* hist_true, double* ssum, int accumulate, void* workspace,
+                         size_t workspace_bytes, int impl, void* stream) {
+  PH_CHECK_ARG(hist_true != nullptr && ssum != nullptr, "hist_true / ssum must not be NULL");
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(hist_true) & 15) == 0 && (reinterpret_cast<uintptr_t>(hist) & 15) == 0,
+               "histogram pointers must be 16-byte aligned");
+  return hist_forward_impl(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist, denom,
+                           hist_true, ssum, accumulate, workspace, workspace_bytes, impl, stream);
 }
 
 int ph_component_histogram(const float* component, const float* projection1, const float* projection2,

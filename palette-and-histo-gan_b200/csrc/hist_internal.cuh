@@ -39,7 +39,8 @@ size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins);
 size_t tc_bwd_workspace_bytes(int64_t batch);  // hist_tc_bwd.cu: fp16 G^ operand tiles + per-image scales
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                     int bins, int method, float sigma_sqr, float eps, float* hist, float* denom,
-                    void* workspace, bool dedup, cudaStream_t st);
+                    void* workspace, bool dedup, const float* hist_true, double* ssum, cudaStream_t st);
+int launch_hellinger_ssum_accumulate(const float* ht, const float* hp, int64_t n, double* ssum, cudaStream_t st);
 int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                      int bins, int method, float sigma_sqr, float eps, const float* hist_pred,
                      const float* denom, const float* grad_hist, const float* hist_true,

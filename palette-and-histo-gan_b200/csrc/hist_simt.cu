@@ -672,6 +672,14 @@ int launch_hellinger_ssum(const float* ht, const float* hp, int64_t n, double* s
   return PH_OK;
 }
 
+int launch_hellinger_ssum_accumulate(const float* ht, const float* hp, int64_t n, double* ssum, cudaStream_t st) {
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(ht) & 15) == 0 && (reinterpret_cast<uintptr_t>(hp) & 15) == 0,
+               "histogram pointers must be 16-byte aligned");
+  hellinger_ssum_kernel<<<reduce_grid(n / 4 + 1), 256, 0, st>>>(ht, hp, n, ssum);  // adds into *ssum
+  PH_LAUNCH_OK("hellinger_ssum_kernel");
+  return PH_OK;
+}
+
 int launch_hellinger_finish(const double* ssum, int64_t global_batch, float* loss, cudaStream_t st) {
   hellinger_finish_kernel<<<1, 1, 0, st>>>(ssum, (double)global_batch, loss);
   PH_LAUNCH_OK("hellinger_finish_kernel");

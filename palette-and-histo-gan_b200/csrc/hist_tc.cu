@@ -73,6 +73,8 @@ struct Smem {
   PxSlot px[PR];
   float dom[BINS];
   float red[PROD_WARPS];
+  double red2[PROD_WARPS];
+  int last_flag;
   alignas(8) uint64_t px_full[PR], px_empty[PR], ab_full[NS], ab_empty[NS], d_full, d_empty;
   uint32_t tmem_base;
 };
@@ -83,6 +85,9 @@ struct Params {
   float* partial;  // (B - n_whole, splits, 3, 64, 64) raw sums of the sliced ("tail") images
   float* hist;     // (B, 64, 64, 3) normalised, written directly for whole-image items
   float* denom;    // (B)
+  const float* hist_true;  // optional (B, 64, 64, 3): accumulate the Hellinger sum of squares against it into *ssum
+  double* ssum;            // (histogram.py:88) while the normalised histogram is still on chip, or NULL
+  int* tail_counter;       // (B - n_whole): slices of a tail image that have delivered their partial sums
   const float4* ulist;  // optional (B, DEDUP_MAX): unique colours (r,g,b,count) of each image, or NULL
   const int* nunique;   // optional (B): number of unique colours, < 0 = image not de-duplicated
   int64_t npix;
@@ -152,7 +157,7 @@ __device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 wa2, f32x2 w
   }
 }
 
-template <int METHOD>
+template <int METHOD, bool FUSE_SSUM>
 __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
   // no-swizzle operand tiles need only 16 B alignment; keeping the pointer derived from the
   // __shared__ symbol (no integer round trip) lets ptxas emit LDS/STS instead of generic LD/ST
@@ -317,10 +322,37 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         }
         if (kb + 1 != nkb) { named_bar_sync(5, PROD_WARPS * 32); continue; }  // acc is read-modified by the next chain
 
-        // ---- item epilogue: all 16 warps, normalise (whole image) or emit the raw partial ----
+        // ---- item epilogue: all 16 warps.  A whole image is normalised here; a slice of a tail image delivers
+        //      its raw sums, and the CTA that delivers the last slice adds them up (in slice order: deterministic)
+        //      and normalises — no second kernel, no partials left for the host side to combine ----
         named_bar_sync(5, PROD_WARPS * 32);
         const int t = tid;  // 0..511
-        if (ir.whole) {
+        bool finish = ir.whole;
+        float dscale = p.inv_scale;  // raw sum -> true scale of the normaliser D
+        if (!ir.whole) {
+          float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
+          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
+            dst[e] = S.acc[c][j][i] * p.inv_scale;
+          }
+          __threadfence();
+          named_bar_sync(5, PROD_WARPS * 32);
+          if (t == 0) S.last_flag = atomicAdd(p.tail_counter + (b - p.n_whole), 1) == p.splits - 1;
+          named_bar_sync(5, PROD_WARPS * 32);
+          finish = S.last_flag != 0;
+          if (finish) {
+            __threadfence();
+            const float* src = p.partial + (b - p.n_whole) * (int64_t)p.splits * (3 * BINS * BINS);
+            for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+              float v = 0.f;
+              for (int sidx = 0; sidx < p.splits; ++sidx) v += __ldcg(src + (int64_t)sidx * (3 * BINS * BINS) + e);
+              S.acc[e >> 12][e & 63][(e >> 6) & 63] = v;
+            }
+            dscale = 1.0f;
+            named_bar_sync(5, PROD_WARPS * 32);
+          }
+        }
+        if (finish) {
           float s = 0.f;
           for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
           s = warp_sum(s);
@@ -329,18 +361,44 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
           float d = 0.f;
 #pragma unroll
           for (int k = 0; k < PROD_WARPS; ++k) d += S.red[k];
-          if (t == 0) p.denom[b] = d * p.inv_scale;
+          if (t == 0) p.denom[b] = d * dscale;
           const float inv_d = 1.0f / d;
           float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
-          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
-            const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-            dst[e] = S.acc[c][j][i] * inv_d;
-          }
-        } else {
-          float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
-          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
-            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
-            dst[e] = S.acc[c][j][i] * p.inv_scale;
+          if (!FUSE_SSUM) {
+            for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+              const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
+              dst[e] = S.acc[c][j][i] * inv_d;
+            }
+          } else {
+            // fused Hellinger partial: sum (sqrt(Hp) - sqrt(Ht))^2 of this image (histogram.py:88) while Hp is
+            // on chip; the real image's histogram arrives in two batches of 12 independent loads per thread
+            constexpr int HALF = 3 * BINS * BINS / (PROD_WARPS * 32) / 2;  // 12
+            const float* ht = p.hist_true + b * (int64_t)(3 * BINS * BINS);
+            float part = 0.f;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              float htv[HALF];
+#pragma unroll
+              for (int k = 0; k < HALF; ++k) htv[k] = __ldg(ht + t + (half * HALF + k) * (PROD_WARPS * 32));
+#pragma unroll
+              for (int k = 0; k < HALF; ++k) {
+                const int e = t + (half * HALF + k) * (PROD_WARPS * 32);
+                const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
+                const float h = S.acc[c][j][i] * inv_d;
+                dst[e] = h;
+                const float df = fast_sqrt(h) - fast_sqrt(htv[k]);
+                part = fmaf(df, df, part);
+              }
+            }
+            double dpart = warp_sum((double)part);
+            if (lane == 0) S.red2[warp] = dpart;
+            named_bar_sync(5, PROD_WARPS * 32);
+            if (t == 0) {
+              double tot = 0.0;
+#pragma unroll
+              for (int k = 0; k < PROD_WARPS; ++k) tot += S.red2[k];
+              atomicAdd(p.ssum, tot);
+            }
           }
         }
         named_bar_sync(5, PROD_WARPS * 32);
@@ -525,19 +583,16 @@ static FwdPlan tc_fwd_plan(int64_t batch, int64_t npix, bool dedup) {
 size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins) {
   if (bins != 64) return 0;
   const FwdPlan pl = tc_fwd_plan(batch, npix, false);
-  size_t fwd = (size_t)(batch - pl.n_whole) * pl.splits * 3 * bins * bins * sizeof(float);
+  size_t fwd = align_up((size_t)(batch - pl.n_whole) * pl.splits * 3 * bins * bins * sizeof(float), 256) +
+               align_up((size_t)(batch - pl.n_whole) * sizeof(int), 256);  // slice partials + arrival counters
   if (tc_fwd_plan(batch, npix, true).n_whole == batch && dedup_bytes(batch) > fwd) fwd = dedup_bytes(batch);
   const size_t bwd = tc_bwd_workspace_bytes(batch);
   return align_up(fwd > bwd ? fwd : bwd, 256) + 256;
 }
 
-// defined in hist_simt.cu
-void launch_finalize(const float* partial, int splits, int nch, int bins, int normalise, float* hist,
-                     float* denom, int64_t batch, cudaStream_t st);
-
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int bins,
                     int method, float sigma_sqr, float eps, float* hist, float* denom, void* workspace, bool dedup,
-                    cudaStream_t st) {
+                    const float* hist_true, double* ssum, cudaStream_t st) {
   using namespace fwdtc;
   PH_CHECK_ARG(bins == BINS, "tensor-core forward is specialised for 64 bins");
   Params p{};
@@ -546,6 +601,8 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.partial = static_cast<float*>(workspace);
   p.hist = hist;
   p.denom = denom;
+  p.hist_true = hist_true;
+  p.ssum = ssum;
   p.npix = npix;
   p.channels = channels;
   const FwdPlan pl = tc_fwd_plan(batch, npix, dedup);
@@ -579,24 +636,22 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     p.ulist = ulist;
     p.nunique = nunique;
   }
+  if (p.n_whole < batch) {
+    const size_t part_bytes = align_up((size_t)(batch - p.n_whole) * p.splits * 3 * BINS * BINS * sizeof(float), 256);
+    p.tail_counter = reinterpret_cast<int*>(static_cast<char*>(workspace) + part_bytes);
+    PH_CUDA_OK(cudaMemsetAsync(p.tail_counter, 0, (size_t)(batch - p.n_whole) * sizeof(int), st));
+  }
   const size_t smem = sizeof(Smem);
   int grid = cached_sm_count();
   if (grid > p.items) grid = (int)p.items;
-  if (method == PH_METHOD_INVERSE_QUADRATIC) {
-    PH_CUDA_OK(cudaFuncSetAttribute(hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC><<<grid, THREADS, smem, st>>>(p);
-  } else {
-    PH_CUDA_OK(cudaFuncSetAttribute(hist_fwd_tc_kernel<PH_METHOD_RBF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    hist_fwd_tc_kernel<PH_METHOD_RBF><<<grid, THREADS, smem, st>>>(p);
-  }
+  void (*kern)(Params) = nullptr;
+  if (method == PH_METHOD_INVERSE_QUADRATIC)
+    kern = ssum ? hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
+  else
+    kern = ssum ? hist_fwd_tc_kernel<PH_METHOD_RBF, true> : hist_fwd_tc_kernel<PH_METHOD_RBF, false>;
+  PH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, THREADS, smem, st>>>(p);
   PH_LAUNCH_OK("hist_fwd_tc_kernel");
-  if (p.n_whole < batch) {
-    launch_finalize(p.partial, p.splits, 3, bins, 1, hist + p.n_whole * (int64_t)(3 * bins * bins), denom + p.n_whole,
-                    batch - p.n_whole, st);
-    PH_LAUNCH_OK("hist_finalize_kernel");
-  }
   return PH_OK;
 }
 

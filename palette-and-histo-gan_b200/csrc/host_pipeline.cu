@@ -31,7 +31,7 @@ struct ph_host_ctx {
   struct Job {
     unsigned char* d_u8[2];
     float *d_fake, *d_real[2], *d_hreal, *d_hfake, *d_denom_r, *d_denom_f, *d_gradfull, *d_dom, *d_loss;
-    double *d_ssum, *d_one;
+    double *d_ssum, *d_ssum2, *d_one;
     bool with_grad;
     char* d_ws;
     char* d_ws2;
@@ -192,6 +192,7 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
     J.d_dom = cv.take<float>((size_t)bins);
     J.d_ssum = cv.take<double>(1);
     J.d_one = cv.take<double>(1);
+    J.d_ssum2 = cv.take<double>(2);  // per compute stream
     J.d_loss = cv.take<float>(1);
     J.d_ws = cv.take<char>(ws_bytes);
     J.d_ws2 = cv.take<char>(ws_bytes);
@@ -242,9 +243,10 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
                              sc);
     if (rc != PH_OK) return rc;
     PH_CUDA_OK(cudaEventRecord(ctx->ev_free[slot], sc));
-    rc = ph_hist_forward(J.d_fake + (size_t)b0 * npix * channels, nb, npix, channels, J.d_dom, bins, method,
-                         sigma_sqr, epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0, ws, ws_bytes,
-                         impl, sc);
+    // forward of the fake chunk fused with its share of the Hellinger sum (added into d_ssum[slot])
+    rc = ph_hist_forward_ssum(J.d_fake + (size_t)b0 * npix * channels, nb, npix, channels, J.d_dom, bins, method,
+                              sigma_sqr, epsilon, J.d_hfake + (size_t)b0 * hist_elems, J.d_denom_f + b0,
+                              J.d_hreal + (size_t)b0 * hist_elems, J.d_ssum2 + slot, k >= 2, ws, ws_bytes, impl, sc);
     if (rc != PH_OK) return rc;
     if (with_grad) {
       rc = ph_hist_backward(J.d_fake + (size_t)b0 * npix * channels, nb, npix, channels, J.d_dom, bins, method, sigma_sqr,
@@ -257,10 +259,11 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   // ---- the one coupling scalar ----
   PH_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->s_compute2));
   PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_join, 0));
-  int rc = ph_hellinger_ssum(J.d_hreal, J.d_hfake, (int64_t)(batch * hist_elems), J.d_ssum, ctx->s_compute);
-  if (rc != PH_OK) return rc;
-  PH_CUDA_OK(cudaMemcpyAsync(ssum_local_host, J.d_ssum, sizeof(double), cudaMemcpyDeviceToHost, ctx->s_compute));
+  double parts[2] = {0.0, 0.0};
+  PH_CUDA_OK(cudaMemcpyAsync(parts, J.d_ssum2, sizeof(double) * (nchunks > 1 ? 2 : 1), cudaMemcpyDeviceToHost,
+                             ctx->s_compute));
   PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+  *ssum_local_host = parts[0] + parts[1];
   ctx->job_valid = true;
   return PH_OK;
 }

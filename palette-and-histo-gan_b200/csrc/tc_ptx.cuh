@@ -336,6 +336,11 @@ __device__ __forceinline__ void split_f16x2(f32x2 w, f32x2 /*mone2*/, uint32_t& 
       : "f"(w0), "f"(w1));
   lo = cvt_f16x2(l0, l1);
 }
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float fast_ex2(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

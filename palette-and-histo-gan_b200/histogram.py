@@ -103,6 +103,22 @@ def _backward(image, dom, method_id, sigma_sqr, impl, hist_pred, denom, *, grad_
     return grad
 
 
+def _forward_ssum(image, dom, method_id, sigma_sqr, impl, hist_true):
+    """Forward of the `fake` images fused with their share of the Hellinger sum of squares against `hist_true`
+    (one launch, the normalised histogram is read from shared memory): -> (hist, denom, ssum (1,) float64)."""
+    b, npix, ch = _check_image(image)
+    bins = dom.numel()
+    hist = torch.empty((b, bins, bins, 3), dtype=torch.float32, device=image.device)
+    denom = torch.empty((b,), dtype=torch.float32, device=image.device)
+    ssum = torch.empty((1,), dtype=torch.float64, device=image.device)
+    ws, ws_bytes = _workspace(max(b, 1), npix, bins, impl, image.device)
+    with torch.cuda.device(image.device):
+        _lib.call("ph_hist_forward_ssum", ptr(image), b, npix, ch, ptr(dom), bins, method_id, sigma_sqr, EPSILON,
+                  ptr(hist), ptr(denom), ptr(hist_true), ptr(ssum), 0, ptr(ws), ws_bytes, impl,
+                  stream_ptr(image.device))
+    return hist, denom, ssum
+
+
 def _ssum(y_true, y_pred):
     out = torch.empty((1,), dtype=torch.float64, device=y_true.device)
     with torch.cuda.device(y_true.device):
@@ -181,8 +197,7 @@ class _HistogramLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, real, fake, dom, method_id, sigma_sqr, impl, group, global_batch, dedup_real):
         hist_real, _ = _forward(real, dom, method_id, sigma_sqr, impl | (DEDUP_FLAG if dedup_real else 0))
-        hist_fake, denom_fake = _forward(fake, dom, method_id, sigma_sqr, impl)
-        ssum = _ssum(hist_real, hist_fake)
+        hist_fake, denom_fake, ssum = _forward_ssum(fake, dom, method_id, sigma_sqr, impl, hist_real)
         sharded = group is not None and group is not False
         overlap = False
         if sharded and ctx.needs_input_grad[1]:

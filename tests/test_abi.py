@@ -32,7 +32,7 @@ def pkg():
 
 def test_header_declares_expected_surface():
     syms = declared_symbols()
-    for name in ("ph_hist_forward", "ph_hist_backward", "ph_hellinger_ssum", "ph_extract_palette",
+    for name in ("ph_hist_forward", "ph_hist_forward_ssum", "ph_hist_backward", "ph_hellinger_ssum", "ph_extract_palette",
                  "ph_rgba_to_indexed", "ph_one_hot", "ph_indexed_to_rgba", "ph_argmax_indexed", "ph_load_indexed_images",
                  "ph_host_hist_loss", "ph_host_load_indexed_images"):
         assert name in syms
