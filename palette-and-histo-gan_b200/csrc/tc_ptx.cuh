@@ -148,7 +148,8 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_noswizzle(uint32_t smem_add
   return d;         // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
 }
 
-// kind::tf32 instruction descriptor: fp32 accumulate, tf32 A and B, both K-major, dense.
+// kind::tf32 instruction descriptor: fp32 accumulate, tf32 A and B, both K-major, dense.  (The tf32 wrappers below
+// are what the first version of the kernels used; tools/mma_bench.cu still times them against kind::f16.)
 __host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
   return (1u << 4)                    // c_format = F32
          | (2u << 7)                  // a_format = TF32

@@ -8,9 +8,8 @@ from oracle import histogram_oracle as ho
 
 def split_f16(x32, scale):
     xs = (x32.astype(np.float32) * np.float32(scale)).astype(np.float32)
-    hi_f = (xs.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
-    hi = hi_f.astype(np.float16)
-    lo = (xs - hi.astype(np.float32)).astype(np.float16)
+    hi = xs.astype(np.float16)                                  # cvt.rn.f16x2.f32
+    lo = (xs - hi.astype(np.float32)).astype(np.float16)        # FHFMA (exact difference) + cvt.rn
     return hi.astype(np.float64) / scale, lo.astype(np.float64) / scale
 
 def split_tf32(x32, scale=1.0):
