@@ -9,5 +9,9 @@ this image (no TF wheel, no network) and ships neither tests nor golden vectors,
 is a restatement checked only against (a) the survey-time known-answer values recorded in
 SURVEY.md §4, (b) an independent torch-autograd restatement (`oracle/torch_port.py`), (c) central
 finite differences for the analytic gradient, and (d) the self-consistency identities the
-reference's own call sites rely on (round trips, sum-to-one, symmetry).
+reference's own call sites rely on (round trips, sum-to-one, symmetry), and — the strongest pin —
+(e) the outputs of the reference's OWN source files (histogram.py, io_utils.py, dataset_utils.py, imported
+unmodified) executed over a minimal TensorFlow-op shim (`oracle/ref_shim.py`, `oracle/run_reference.py`,
+fixture `tests/golden/reference_run.npz`).  That pins the restatement to the reference's code; the semantics of
+the individual TensorFlow ops remain an assumption until a run of real TensorFlow is possible.
 """

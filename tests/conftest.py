@@ -31,6 +31,12 @@ def hist_golden():
 
 
 @pytest.fixture(scope="session")
+def reference_run():
+    """Outputs of the reference's own source files executed over oracle/ref_shim.py (oracle/run_reference.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "reference_run.npz")))
+
+
+@pytest.fixture(scope="session")
 def cuda():
     import torch
 

@@ -365,3 +365,26 @@ def test_host_pipeline_chunks_and_three_channels(cuda):
     loss3, grad3 = hostapi.histogram_loss(real3, fake3)
     assert abs(loss3 - ref3["loss"]) / ref3["loss"] < LOSS_TOL
     assert ho.rel_l2(grad3, ref3["grad"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("impl", impls())
+def test_against_the_reference_source_run(H, cuda, reference_run, hist_golden, impl):
+    """The CUDA path against the outputs of the reference's own histogram.py (executed over oracle/ref_shim.py,
+    float32): the distance to that run is the reference's own float32 noise, not more."""
+    R = reference_run
+    real = torch.from_numpy(hist_golden["real"]).to(cuda)
+    fake = torch.from_numpy(hist_golden["fake"]).to(cuda).requires_grad_(True)
+    h_real = H.calculate_rgbuv_histogram(real, impl=impl).cpu().numpy()
+    assert ho.rel_l2(h_real, R["hist_real"]) < HIST_TOL
+    loss = H.hellinger_loss(torch.from_numpy(R["hist_real"]).to(cuda),
+                            H.calculate_rgbuv_histogram(fake, impl=impl))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(R["loss"].reshape(-1)[0])) / float(R["loss"].reshape(-1)[0]) < LOSS_TOL
+    # the reference's float32 autodiff is itself 3e-5 from float64 on these near-black sprites
+    assert ho.rel_l2(fake.grad.cpu().numpy(), R["grad"]) < 5e-5
+    dense = torch.from_numpy(R["dense_input"]).to(cuda)
+    assert ho.rel_l2(H.calculate_rgbuv_histogram(dense, size=32, impl=impl).cpu().numpy(), R["dense_hist_32_iq"]) < HIST_TOL
+    rbf = H.calculate_rgbuv_histogram(dense, size=64, method="RBF", sigma=0.5, impl=impl).cpu().numpy()
+    assert ho.rel_l2(rbf, R["dense_hist_64_rbf"]) < HIST_TOL
+    assert abs(float(H.l1_loss(torch.from_numpy(R["hist_real"]).to(cuda), torch.from_numpy(R["hist_fake"]).to(cuda)))
+               - float(R["l1"])) < 1e-9

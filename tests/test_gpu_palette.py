@@ -221,3 +221,23 @@ def test_probabilities_to_indexed_and_rgba(P, cuda, sprites):
     gi, gr = P.io_utils.probabilities_to_indexed(torch.from_numpy(odd).to(cuda), pal1)
     assert np.array_equal(gi.cpu().numpy(), po.argmax_indexed(odd))
     assert np.array_equal(gr.cpu().numpy(), po.probabilities_to_rgba(odd, pal1.cpu().numpy()))
+
+
+@pytest.mark.parametrize("ordering", ["grayness", "top2bottom", "bottom2top"])
+def test_against_the_reference_source_run(P, cuda, reference_run, ordering):
+    """Bit-exact against the outputs of the reference's own dataset_utils.load_indexed_images / io_utils.py
+    (executed over oracle/ref_shim.py on the dataset's PNG files)."""
+    R = reference_run
+    src, tgt = dev_i32(R["loader_source"], cuda), dev_i32(R["loader_target"], cuda)
+    s_idx, t_idx, pal = P.dataset_utils.load_indexed_images(src, tgt, ordering)
+    assert np.array_equal(pal.cpu().numpy(), R[f"palette_{ordering}"])
+    assert np.array_equal(s_idx.cpu().numpy(), R[f"src_idx_{ordering}"])
+    assert np.array_equal(t_idx.cpu().numpy(), R[f"tgt_idx_{ordering}"])
+    if ordering == "grayness":
+        n = R["roundtrip_rgba"].shape[0]
+        assert np.array_equal(P.io_utils.indexed_to_rgba(t_idx[:n], pal[:n]).cpu().numpy(), R["roundtrip_rgba"])
+        oh = P.io_utils.one_hot(t_idx[:2]).cpu().numpy()[:, ::8, ::8]
+        assert np.array_equal(oh.reshape(R["one_hot_rows"].shape), R["one_hot_rows"])
+        # the uint8 loader prep (blacken + normalise) against the reference's normalize()
+        u8 = torch.from_numpy(R["loader_target"][:n]).to(cuda)
+        assert np.array_equal(P.dataset_utils.load_image(u8).cpu().numpy(), R["normalized"])
