@@ -36,7 +36,8 @@ struct ph_host_ctx {
     char* d_ws;
     char* d_ws2;
     size_t ws_bytes;
-    int64_t batch, npix, chunk;
+    int64_t batch, npix, chunk;  // chunk = the largest chunk (staging buffers)
+    int64_t start[kMaxChunks + 1];  // chunk k covers images [start[k], start[k+1])
     int channels, bins, method, impl, nchunks;
     float sigma_sqr, epsilon;
   } job;
@@ -165,20 +166,37 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   PH_CUDA_OK(cudaSetDevice(ctx->device));
   ctx->job_valid = false;
 
-  // chunking: at least 8 MiB per copy, at most kMaxChunks chunks
+  // chunking: at least two images per SM per chunk (each chunk then takes the whole-image kernel path) and at
+  // least 8 MiB per copy.  (Measured at cfgC: uniform 296-image chunks 520 k pairs/s; 148: 441 k; 592: 478 k; a
+  // small first chunk followed by larger ones: 486 k.)
   const size_t img_bytes = (size_t)npix * channels * sizeof(float);
-  int64_t chunk = (int64_t)((8u << 20) / img_bytes);
-  if (chunk < 296) chunk = 296;  // at least two images per SM, so each chunk takes the whole-image kernel path
+  int64_t base = (int64_t)((8u << 20) / img_bytes);
+  if (base < 296) base = 296;
   static const int64_t chunk_env = getenv("PH_HOST_CHUNK") ? atoll(getenv("PH_HOST_CHUNK")) : 0;  // tuning knob
-  if (chunk_env > 0) chunk = chunk_env;
-  if (chunk > batch) chunk = batch;
-  if (chunk < 1) chunk = 1;
-  if (ceil_div(batch, chunk) > ph_host_ctx::kMaxChunks) chunk = ceil_div(batch, ph_host_ctx::kMaxChunks);
-  const int nchunks = (int)ceil_div(batch, chunk);
-  const size_t hist_elems = (size_t)bins * bins * 3;
-  const size_t ws_bytes = ph_hist_workspace_bytes(chunk, npix, bins, impl);
-
   ph_host_ctx::Job& J = ctx->job;
+  int nchunks = 0;
+  int64_t chunk = 0;
+  {
+    int64_t pos = 0;
+    J.start[0] = 0;
+    while (pos < batch) {
+      int64_t sz = chunk_env > 0 ? chunk_env : base;
+      const int64_t left = batch - pos;
+      const int slots_left = ph_host_ctx::kMaxChunks - nchunks;
+      if (slots_left * sz < left) sz = ceil_div(left, slots_left);  // huge batches: stay within kMaxChunks
+      if (sz > left || left - sz < base / 2) sz = left;               // no tiny last chunk
+      pos += sz;
+      J.start[++nchunks] = pos;
+      if (sz > chunk) chunk = sz;
+    }
+  }
+  const size_t hist_elems = (size_t)bins * bins * 3;
+  size_t ws_bytes = 0;  // the workspace depends on how a chunk splits into whole and sliced images: take the largest
+  for (int k = 0; k < nchunks; ++k) {
+    const size_t w = ph_hist_workspace_bytes(J.start[k + 1] - J.start[k], npix, bins, impl);
+    if (w > ws_bytes) ws_bytes = w;
+  }
+
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass == 0 ? nullptr : ctx->arena);
     J.d_fake = cv.take<float>((size_t)batch * npix * channels);
@@ -213,8 +231,8 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   PH_CUDA_OK(cudaMemcpyAsync(J.d_dom, bin_centers_host, sizeof(float) * bins, cudaMemcpyHostToDevice, ctx->s_in));
   // ---- phase 1: upload + forward + unit-scale backward, chunk by chunk ----
   for (int k = 0; k < nchunks; ++k) {
-    const int64_t b0 = (int64_t)k * chunk;
-    const int64_t nb = batch - b0 < chunk ? batch - b0 : chunk;
+    const int64_t b0 = J.start[k];
+    const int64_t nb = J.start[k + 1] - b0;
     const size_t n = (size_t)nb * npix * channels;
     const int slot = k & 1;
     if (k >= 2) PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_free[slot], 0));
@@ -305,8 +323,8 @@ int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_bat
   }
   if (grad_fake_host) {
     for (int k = 0; k < J.nchunks; ++k) {
-      const int64_t b0 = (int64_t)k * J.chunk;
-      const int64_t nb = J.batch - b0 < J.chunk ? J.batch - b0 : J.chunk;
+      const int64_t b0 = J.start[k];
+      const int64_t nb = J.start[k + 1] - b0;
       const int64_t n = nb * J.npix * J.channels;
       float* g = J.d_gradfull + (size_t)b0 * J.npix * J.channels;
       rc = launch_grad_rescale(g, g, n, J.d_ssum, global_batch, ctx->s_compute);
