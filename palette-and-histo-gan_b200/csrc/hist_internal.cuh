@@ -36,7 +36,7 @@ int launch_diff_reduce(const float* a, const float* b, int64_t n, int kind, floa
 // ---- hist_tc.cu (tcgen05 engine) --------------------------------------------------------------
 bool tc_supported(int64_t npix, int bins, int method);
 size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins);
-size_t tc_bwd_workspace_bytes(int64_t batch);  // hist_tc_bwd.cu: fp16 G^ operand tiles + per-image scales
+size_t tc_bwd_workspace_bytes(int64_t batch, int bins);  // hist_tc_bwd.cu: G^ operand tiles, scales (+ float G^ when bins > 64)
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                     int bins, int method, float sigma_sqr, float eps, float* hist, float* denom,
                     void* workspace, bool dedup, const float* hist_true, double* ssum, cudaStream_t st);

@@ -71,7 +71,7 @@ struct Smem {
                                                     // floats so both the bin-major drain and the j-major
                                                     // write-out are free of bank conflicts
   PxSlot px[PR];
-  float dom[BINS];
+  float dom[2][BINS];  // [u side, v side]
   float red[PROD_WARPS];
   double red2[PROD_WARPS];
   int last_flag;
@@ -81,7 +81,10 @@ struct Smem {
 
 struct Params {
   const float* image;
-  const float* dom;
+  const float* dom_u;  // 64 bin centres of the u side (rows i of the histogram block)
+  const float* dom_v;  // 64 bin centres of the v side (columns j)
+  float* raw_out;      // optional (B, 3, 64, 64): emit the un-normalised block sums instead of H/D (histograms with
+                       // more than 64 bins are assembled from 64 x 64 blocks, one launch per block)
   float* partial;  // (B - n_whole, splits, 3, 64, 64) raw sums of the sliced ("tail") images
   float* hist;     // (B, 64, 64, 3) normalised, written directly for whole-image items
   float* denom;    // (B)
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     mbar_init(&S.d_empty, PROD_WARPS);
     fence_mbar_init();
   }
-  if (tid < BINS) S.dom[tid] = p.dom[tid];
+  if (tid < BINS) { S.dom[0][tid] = p.dom_u[tid]; S.dom[1][tid] = p.dom_v[tid]; }
   if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     const int side = warp >> 3;                 // 0: A (u side, x intensity), 1: B (v side)   — warp-uniform
     const int bin = tid & 63;
     const int po = (tid >> 6) & 3;              // which 8 of the stage's 32 pixels
-    const float c_bin = S.dom[bin];
+    const float c_bin = S.dom[side][bin];
     const f32x2 negc = pack2(-c_bin, -c_bin);
     const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
     // hi row `bin`, lo row `bin + 64` (+ 8 row groups = 1024 B) of core-matrix column `po`
@@ -352,7 +355,13 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
             named_bar_sync(5, PROD_WARPS * 32);
           }
         }
-        if (finish) {
+        if (finish && p.raw_out != nullptr) {
+          float* dst = p.raw_out + b * (int64_t)(3 * BINS * BINS);
+          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
+            dst[e] = S.acc[c][j][i] * dscale;
+          }
+        } else if (finish) {
           float s = 0.f;
           for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
           s = warp_sum(s);
@@ -542,7 +551,7 @@ __global__ void __launch_bounds__(256) hist_dedup_kernel(const float* __restrict
 // =============================================================================================
 bool tc_supported(int64_t npix, int bins, int method) {
   (void)method;
-  return bins == 64 && npix >= 1;
+  return bins >= 64 && bins <= 1024 && bins % 64 == 0 && npix >= 1;
 }
 
 // Pixel slices per image: 1 (whole image per CTA, normalisation fused) once the batch fills the SMs,
@@ -580,29 +589,55 @@ static FwdPlan tc_fwd_plan(int64_t batch, int64_t npix, bool dedup) {
   return pl;
 }
 
+static size_t tail_bytes(const FwdPlan& pl, int64_t batch) {
+  const int64_t n_tail = batch - pl.n_whole;
+  if (n_tail == 0) return 0;
+  return align_up((size_t)n_tail * pl.splits * 3 * 64 * 64 * sizeof(float), 256) + align_up((size_t)n_tail * sizeof(int), 256);
+}
+
 size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins) {
-  if (bins != 64) return 0;
-  const FwdPlan pl = tc_fwd_plan(batch, npix, false);
-  size_t fwd = align_up((size_t)(batch - pl.n_whole) * pl.splits * 3 * bins * bins * sizeof(float), 256) +
-               align_up((size_t)(batch - pl.n_whole) * sizeof(int), 256);  // slice partials + arrival counters
-  if (tc_fwd_plan(batch, npix, true).n_whole == batch && dedup_bytes(batch) > fwd) fwd = dedup_bytes(batch);
-  const size_t bwd = tc_bwd_workspace_bytes(batch);
+  if (bins < 64 || bins % 64 != 0) return 0;
+  const int64_t nb = bins / 64;
+  // forward: [unique-colour lists] [slice partials + arrival counters] [raw 64 x 64 blocks when bins > 64]
+  size_t fwd = tail_bytes(tc_fwd_plan(batch, npix, false), batch);
+  if (tc_fwd_plan(batch, npix, true).n_whole == batch) fwd += dedup_bytes(batch);
+  if (nb > 1) fwd += align_up((size_t)batch * nb * nb * 3 * 64 * 64 * sizeof(float), 256);
+  const size_t bwd = tc_bwd_workspace_bytes(batch, bins);
   return align_up(fwd > bwd ? fwd : bwd, 256) + 256;
+}
+
+// out[b, I, J, c] = raw[block(I/64, J/64)][b][c][I%64][J%64] / D_b,  D_b = sum of every block of image b
+__global__ void __launch_bounds__(256) hist_block_finalize_kernel(const float* __restrict__ raw, int64_t batch, int nb,
+                                                                  float* __restrict__ hist, float* __restrict__ denom) {
+  __shared__ double scratch[32];
+  const int64_t b = blockIdx.x;
+  const int bins = nb * 64;
+  const int64_t blk_stride = batch * (int64_t)(3 * 64 * 64);
+  const float* mine = raw + b * (int64_t)(3 * 64 * 64);
+  double acc = 0.0;
+  for (int blk = 0; blk < nb * nb; ++blk)
+    for (int e = threadIdx.x; e < 3 * 64 * 64; e += 256) acc += (double)__ldg(mine + blk * blk_stride + e);
+  const float d = (float)block_sum(acc, scratch);
+  if (threadIdx.x == 0) denom[b] = d;
+  const float inv_d = 1.0f / d;
+  float* out = hist + b * (int64_t)bins * bins * 3;
+  for (int e = threadIdx.x; e < bins * bins * 3; e += 256) {
+    const int c = e % 3, ij = e / 3, i_full = ij / bins, j_full = ij - i_full * bins;
+    const int blk = (i_full >> 6) * nb + (j_full >> 6);
+    out[e] = __ldg(mine + blk * blk_stride + c * 4096 + (i_full & 63) * 64 + (j_full & 63)) * inv_d;
+  }
 }
 
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int bins,
                     int method, float sigma_sqr, float eps, float* hist, float* denom, void* workspace, bool dedup,
                     const float* hist_true, double* ssum, cudaStream_t st) {
   using namespace fwdtc;
-  PH_CHECK_ARG(bins == BINS, "tensor-core forward is specialised for 64 bins");
+  PH_CHECK_ARG(bins >= BINS && bins % BINS == 0, "tensor-core forward needs a multiple of 64 bins");
+  const int nb = bins / BINS;
   Params p{};
   p.image = image;
-  p.dom = dom;
-  p.partial = static_cast<float*>(workspace);
   p.hist = hist;
   p.denom = denom;
-  p.hist_true = hist_true;
-  p.ssum = ssum;
   p.npix = npix;
   p.channels = channels;
   const FwdPlan pl = tc_fwd_plan(batch, npix, dedup);
@@ -619,39 +654,56 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     p.wb = 14.0f;
   }
   p.iy_scale = 1.0f;
+  char* ws = static_cast<char*>(workspace);
+  size_t off = 0;
   if (dedup && p.n_whole == batch) {
     // multiplicities reach npix: keep count * Iy * 2^14 K below fp16's maximum
     int e = 0;
     while (((int64_t)1 << e) < npix) ++e;
     p.iy_scale = ldexpf(1.0f, -e);
-  }
-  p.inv_scale = 1.0f / ((double)W_SCALE * (double)W_SCALE * (double)p.iy_scale);
-  if (dedup && p.n_whole == batch) {
     // unique colours + multiplicities per image (only worth it when a CTA owns whole images)
-    float4* ulist = static_cast<float4*>(workspace);
-    int* nunique = reinterpret_cast<int*>(static_cast<char*>(workspace) +
-                                          align_up((size_t)batch * DEDUP_MAX * sizeof(float4), 256));
+    float4* ulist = reinterpret_cast<float4*>(ws);
+    int* nunique = reinterpret_cast<int*>(ws + align_up((size_t)batch * DEDUP_MAX * sizeof(float4), 256));
     hist_dedup_kernel<<<(unsigned)batch, 256, 0, st>>>(image, npix, channels, ulist, nunique);
     PH_LAUNCH_OK("hist_dedup_kernel");
     p.ulist = ulist;
     p.nunique = nunique;
+    off += dedup_bytes(batch);
   }
-  if (p.n_whole < batch) {
-    const size_t part_bytes = align_up((size_t)(batch - p.n_whole) * p.splits * 3 * BINS * BINS * sizeof(float), 256);
-    p.tail_counter = reinterpret_cast<int*>(static_cast<char*>(workspace) + part_bytes);
-    PH_CUDA_OK(cudaMemsetAsync(p.tail_counter, 0, (size_t)(batch - p.n_whole) * sizeof(int), st));
+  p.inv_scale = 1.0f / ((double)W_SCALE * (double)W_SCALE * (double)p.iy_scale);
+  const int64_t n_tail = batch - p.n_whole;
+  if (n_tail > 0) {
+    p.partial = reinterpret_cast<float*>(ws + off);
+    p.tail_counter = reinterpret_cast<int*>(ws + off + align_up((size_t)n_tail * p.splits * 3 * BINS * BINS * sizeof(float), 256));
+    off += tail_bytes(pl, batch);
   }
+  float* raw = nb > 1 ? reinterpret_cast<float*>(ws + off) : nullptr;
+  const bool fuse = ssum != nullptr && nb == 1;
+  p.hist_true = fuse ? hist_true : nullptr;
+  p.ssum = fuse ? ssum : nullptr;
   const size_t smem = sizeof(Smem);
   int grid = cached_sm_count();
   if (grid > p.items) grid = (int)p.items;
   void (*kern)(Params) = nullptr;
   if (method == PH_METHOD_INVERSE_QUADRATIC)
-    kern = ssum ? hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
+    kern = fuse ? hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
   else
-    kern = ssum ? hist_fwd_tc_kernel<PH_METHOD_RBF, true> : hist_fwd_tc_kernel<PH_METHOD_RBF, false>;
+    kern = fuse ? hist_fwd_tc_kernel<PH_METHOD_RBF, true> : hist_fwd_tc_kernel<PH_METHOD_RBF, false>;
   PH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, THREADS, smem, st>>>(p);
-  PH_LAUNCH_OK("hist_fwd_tc_kernel");
+  // one launch per 64 x 64 block of the histogram (a single one at 64 bins)
+  for (int blk = 0; blk < nb * nb; ++blk) {
+    p.dom_u = dom + (blk / nb) * BINS;
+    p.dom_v = dom + (blk % nb) * BINS;
+    p.raw_out = raw ? raw + (int64_t)blk * batch * (3 * BINS * BINS) : nullptr;
+    if (n_tail > 0) PH_CUDA_OK(cudaMemsetAsync(p.tail_counter, 0, (size_t)n_tail * sizeof(int), st));
+    kern<<<grid, THREADS, smem, st>>>(p);
+    PH_LAUNCH_OK("hist_fwd_tc_kernel");
+  }
+  if (nb > 1) {
+    hist_block_finalize_kernel<<<(unsigned)batch, 256, 0, st>>>(raw, batch, nb, hist, denom);
+    PH_LAUNCH_OK("hist_block_finalize_kernel");
+    if (ssum != nullptr) return launch_hellinger_ssum_accumulate(hist_true, hist, batch * (int64_t)bins * bins * 3, ssum, st);
+  }
   return PH_OK;
 }
 

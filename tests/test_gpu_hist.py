@@ -388,3 +388,32 @@ def test_against_the_reference_source_run(H, cuda, reference_run, hist_golden, i
     assert ho.rel_l2(rbf, R["dense_hist_64_rbf"]) < HIST_TOL
     assert abs(float(H.l1_loss(torch.from_numpy(R["hist_real"]).to(cuda), torch.from_numpy(R["hist_fake"]).to(cuda)))
                - float(R["l1"])) < 1e-9
+
+
+@pytest.mark.parametrize("shape,bins", [((2, 16, 16, 4), 128), ((2, 24, 24, 3), 256), ((150, 16, 16, 4), 128)])
+def test_block_decomposed_tensor_core_path(H, cuda, shape, bins):
+    """bins = 128 / 256 (cfgE) on the tcgen05 engine: the histogram is assembled from 64 x 64 blocks (one
+    contraction launch per block, common normaliser) and the gradient is summed over the blocks of G^."""
+    rng = np.random.default_rng(41)
+    real = np.tanh(rng.standard_normal(shape)).astype(np.float32)
+    fake = np.tanh(rng.standard_normal(shape)).astype(np.float32)
+    f = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+    loss = H.histogram_loss(torch.from_numpy(real).to(cuda), f, size=bins, impl="tc")
+    loss.backward()
+    hist = H.calculate_rgbuv_histogram(torch.from_numpy(fake).to(cuda), size=bins, impl="tc").cpu().numpy()
+    assert hist.shape == (shape[0], bins, bins, 3)
+    assert np.allclose(hist.sum(axis=(1, 2, 3)), 1.0, atol=3e-6)
+    sub = slice(0, 3)  # the float64 oracle materialises (N, bins) arrays per image: a few images are enough
+    ref = ho.hist_loss_and_grad_f64(real, fake, size=bins) if shape[0] <= 4 else None
+    if ref is not None:
+        assert ho.rel_l2(hist, ref["hist_fake"]) < HIST_TOL
+        assert abs(float(loss.detach()) - ref["loss"]) / ref["loss"] < LOSS_TOL
+        assert ho.rel_l2(f.grad.cpu().numpy(), ref["grad"]) < GRAD_TOL
+    else:
+        f2 = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+        l2 = H.histogram_loss(torch.from_numpy(real).to(cuda), f2, size=bins, impl="simt")
+        l2.backward()
+        assert abs(float(loss.detach()) - float(l2.detach())) / float(l2.detach()) < LOSS_TOL
+        assert ho.rel_l2(f.grad.cpu().numpy()[sub], f2.grad.cpu().numpy()[sub]) < GRAD_TOL
+        assert ho.rel_l2(f.grad.cpu().numpy(), f2.grad.cpu().numpy()) < GRAD_TOL
+    assert np.abs(f.grad.cpu().numpy()[..., 3:]).max() == 0.0 if shape[-1] == 4 else True
