@@ -377,6 +377,11 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_generator_step:
         generator_step = bench_generator_step(torch, dev, world, rank, distributed, barrier)
 
+    # ---- cfgE scale sweep: 256 x 256 images, 256 bins, global batch 1024 (block-decomposed tensor-core path) ----
+    scale_sweep = None
+    if not args.no_scale_sweep:
+        scale_sweep = bench_scale_sweep(torch, dev, world, rank, distributed, barrier, peaks)
+
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -400,7 +405,7 @@ def run_ours(args, rank, world, local_rank):
                        "real_images": "palette sprites, contracted over their unique colours (PH_IMPL_DEDUP, exact); "
                                       "fake images dense"},
             "loss": loss_val, "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "palette": palette, "generator_step": generator_step,
+            "clocks": clocks, "palette": palette, "generator_step": generator_step, "scale_sweep": scale_sweep,
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
@@ -408,6 +413,53 @@ def run_ours(args, rank, world, local_rank):
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_scale_sweep(torch, dev, world, rank, distributed, barrier, peaks):
+    """cfgE (BASELINE.json config 5): histogram loss fwd+bwd at 256 x 256 pixels and 256 bins, global batch 1024 sharded
+    over the ranks.  The tensor-core engine assembles the 256 x 256 histogram from sixteen 64 x 64 blocks."""
+    import torch.distributed as dist
+    from palette_and_histo_gan_b200 import histogram as H
+
+    gb, side, bins = 1024, 256, 256
+    lo, hi = shard_bounds(gb, world, rank)
+    g = torch.Generator(device=dev).manual_seed(50 + rank)
+    fake = torch.tanh(torch.randn((hi - lo, side, side, 4), device=dev, generator=g)).requires_grad_(True)
+    # sprite-like real images: few colours, mostly transparent black (as make_sprites_u8, drawn on the device)
+    pal = torch.randint(0, 256, (hi - lo, 32, 4), device=dev, generator=g)
+    idx = torch.randint(0, 32, (hi - lo, side, side), device=dev, generator=g)
+    real_u8 = torch.gather(pal, 1, idx.reshape(hi - lo, -1, 1).expand(-1, -1, 4)).reshape(hi - lo, side, side, 4)
+    opaque = torch.rand((hi - lo, side, side, 1), device=dev, generator=g) < 0.165
+    real = (torch.where(opaque, real_u8, torch.zeros_like(real_u8)).to(torch.float32) / 127.5 - 1.0).contiguous()
+    del pal, idx, real_u8, opaque
+    group = True if distributed else None
+
+    def step():
+        fake.grad = None
+        loss = H.histogram_loss(real, fake, size=bins, group=group, global_batch=gb)
+        loss.backward()
+        return loss
+
+    step()
+    n = 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tflops = 24.0 * bins * bins * side * side * gb / (float(ms) * 1e-3) / 1e12
+    out = {"workload": "cfgE: histogram loss fwd+bwd, 256x256 RGBA, 256 bins, global batch 1024",
+           "images_per_s": gb / (float(ms) * 1e-3), "ms_per_step": float(ms), "per_gpu_batch": hi - lo,
+           "algorithmic_tflops": tflops, "frac_of_f16_peak": tflops / (peaks["bf16_tflops_sustained"] * world),
+           "loss": float(loss.detach())}
+    del fake, real
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_generator_step(torch, dev, world, rank, distributed, barrier):
@@ -569,6 +621,7 @@ def main():
     ap.add_argument("--engine", choices=["auto", "simt", "tc"], default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-generator-step", action="store_true", help="skip the cfgD caller measurement")
+    ap.add_argument("--no-scale-sweep", action="store_true", help="skip the cfgE (256x256, 256 bins) measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
