@@ -58,9 +58,10 @@ enum ph_index_mode { PH_INDEX_EXACT_SUM = 0, PH_INDEX_NEAREST = 1 };
 
 /* Contraction engine for the histogram GEMMs. */
 enum ph_impl {
-  PH_IMPL_AUTO = 0, /* tensor cores when the shape allows, else SIMT */
+  PH_IMPL_AUTO = 0, /* tensor cores when the bin count is a multiple of 64 (64 ... 1024), else SIMT */
   PH_IMPL_SIMT = 1, /* fp32 CUDA-core contraction (any bin count) */
-  PH_IMPL_TC = 2,   /* tcgen05 3xTF32 contraction, accumulators in TMEM */
+  PH_IMPL_TC = 2,   /* tcgen05 kind::f16 contraction with fp16 hi+lo operand split (fp32-accurate), accumulators in TMEM;
+                       more than 64 bins are handled as 64 x 64 blocks */
   PH_IMPL_ENGINE_MASK = 3,
   /* flag, OR-ed into impl for ph_hist_forward: first reduce every image to its unique colours with
    * multiplicities and contract those (exact: the histogram is a sum over pixels of a function of the
