@@ -385,9 +385,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, times = cpu_hist_images_per_s(32, 24)
+        v, cores, times = cpu_hist_images_per_s(32, 40)
         cpu_baseline = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                        "sample": f"24 x 32 image pairs (cfgA shape), torch-CPU op-for-op port of histogram.py with "
+                        "sample": f"40 x 32 image pairs (cfgA shape), torch-CPU op-for-op port of histogram.py with "
                                   f"autograd, {sum(times):.1f} s; TensorFlow is not installable in this image",
                         "palette_gpix_per_s": cpu_palette_gpix_per_s(64)}
 
