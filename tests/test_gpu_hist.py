@@ -50,9 +50,10 @@ def test_loss_and_gradient_match_golden(H, cuda, hist_golden, impl):
     assert abs(float(loss) - float(hist_golden["loss"])) / float(hist_golden["loss"]) < LOSS_TOL
     g = fake.grad.cpu().numpy()
     assert np.abs(g[..., 3]).max() == 0.0  # alpha gets exactly zero gradient (histogram.py:61)
-    # perturbed sprites contain near-black pixels where d/dx log(x+eps) ~ 1/(x+eps) amplifies rounding:
-    # the reference's own float32 autodiff is 3e-5 from float64 here (measured with oracle/torch_port.py)
-    assert ho.rel_l2(g, hist_golden["grad"]) < 5e-5
+    # perturbed sprites contain near-black pixels where d/dx log(x+eps) ~ 1/(x+eps) amplifies rounding: the
+    # reference's own float32 autodiff is 2.8e-5 from float64 here (tests/golden/reference_run.npz); the CUDA path
+    # takes its logs in float64 and stays inside the 1e-5 bar (measured: CUDA cores 4e-7, tensor cores 2e-6)
+    assert ho.rel_l2(g, hist_golden["grad"]) < GRAD_TOL
 
 
 @pytest.mark.parametrize("impl", impls())
