@@ -99,18 +99,16 @@ def matmul(a, b):
 
 
 def unique_with_counts_v2(x, axis):
+    """Unique rows in order of FIRST OCCURRENCE, the index of each input row among them, and the counts."""
     assert list(axis) == [0]
     rows = T(x)
-    seen, order, inverse, counts = {}, [], [], []
-    for i in range(rows.shape[0]):
-        key = tuple(int(v) for v in rows[i].reshape(-1))
-        if key not in seen:
-            seen[key] = len(order)
-            order.append(i)
-            counts.append(0)
-        inverse.append(seen[key])
-        counts[seen[key]] += 1
-    return rows[torch.tensor(order, dtype=torch.long)], T(np.asarray(inverse, np.int32)), T(np.asarray(counts, np.int32))
+    a = rows.numpy().reshape(rows.shape[0], -1)
+    _, first, inverse, counts = np.unique(a, axis=0, return_index=True, return_inverse=True, return_counts=True)
+    order = np.argsort(first, kind="stable")          # sorted-unique position -> rank by first occurrence
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    uniq = rows[torch.from_numpy(first[order].astype(np.int64))]
+    return uniq, T(rank[np.asarray(inverse).reshape(-1)].astype(np.int32)), T(counts[order].astype(np.int32))
 
 
 def scatter_nd(indices, updates, shape):

@@ -2,6 +2,8 @@
 golden fixtures, torch autograd, finite differences, and the identities the reference's call sites rely on.
 PARITY UNPINNED against TensorFlow itself (not installable in this image); the strongest pin available is the
 run of the reference's own source files over a TensorFlow-op shim (tests at the end of this file)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -230,3 +232,49 @@ def test_torch_port_is_the_reference_source_op_for_op(reference_run, hist_golden
     loss, grad = tp.hist_loss_fwd_bwd(torch.from_numpy(hist_golden["real"]), torch.from_numpy(hist_golden["fake"]), 64)
     assert abs(float(loss) - float(reference_run["loss"].reshape(-1)[0])) / float(loss) < 1e-6
     assert ho.rel_l2(grad.numpy(), reference_run["grad"]) < 1e-6
+
+
+def test_tf_shim_op_semantics():
+    """The TensorFlow-op behaviours oracle/ref_shim.py assumes (documented TF semantics), stated as executable
+    checks so that a reader can see exactly what the reference-source run rests on."""
+    import torch
+    from oracle import ref_shim
+
+    tf = ref_shim.build()
+    # linspace: exact end points, start + delta * k in float32 in between (the formula histogram_oracle restates)
+    assert np.array_equal(tf.linspace(-3.0, 3.0, num=64).numpy(), ho.tf_linspace_f32(-3.0, 3.0, 64))
+    # UniqueWithCountsV2(axis=[0]): rows in order of first occurrence
+    rows = ref_shim.T(np.array([[3, 3], [1, 1], [3, 3], [2, 2], [1, 1]], np.int32))
+    uniq, inv, cnt = tf.raw_ops.UniqueWithCountsV2(x=rows, axis=[0])
+    assert uniq.numpy().tolist() == [[3, 3], [1, 1], [2, 2]] and inv.numpy().tolist() == [0, 1, 0, 2, 1]
+    assert cnt.numpy().tolist() == [2, 2, 1]
+    # scatter_nd accumulates duplicates and leaves zeros elsewhere; where() lists coordinates row-major
+    out = tf.scatter_nd(ref_shim.T(np.array([[1], [3], [1]], np.int32)), ref_shim.T(np.array([5, 7, 2], np.int32)), [5])
+    assert out.numpy().tolist() == [0, 7, 0, 7, 0]
+    assert tf.where(ref_shim.T(np.array([[0, 1], [1, 1]], np.int32)) == 1).numpy().tolist() == [[0, 1], [1, 0], [1, 1]]
+    # stable ascending argsort, one_hot out of range, repeat with a negative count
+    assert tf.argsort(ref_shim.T(np.array([2.0, 1.0, 2.0, 1.0], np.float32)), direction="ASCENDING", stable=True).numpy().tolist() == [1, 3, 0, 2]
+    assert tf.one_hot(ref_shim.T(np.array([0, 2, 5, -1], np.int32)), 3).numpy().tolist() == [[1, 0, 0], [0, 0, 1], [0, 0, 0], [0, 0, 0]]
+    with pytest.raises((ValueError, RuntimeError)):
+        tf.repeat([[255, 0, 220, 255]], [-3], axis=0)
+    # python scalars are weakly typed: float32 stays float32; pow(sigma, 2) is the float32 square
+    x = ref_shim.T(np.array([0.25], np.float32))
+    assert (x * 0.5 + 0.5).dtype == torch.float32
+    assert np.float32(tf.pow(0.02, 2).numpy()) == ho.sigma_sqr_f32(0.02)
+    # x[::-1] reverses the first axis (io_utils.py:48)
+    assert ref_shim.T(np.arange(6, dtype=np.int32).reshape(3, 2))[::-1].numpy().tolist() == [[4, 5], [2, 3], [0, 1]]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/datasets"), reason="build container only: needs the reference")
+def test_reference_run_fixture_is_reproducible(tmp_path, monkeypatch, reference_run):
+    """Re-running the reference's own source over the shim reproduces the committed fixture bit for bit."""
+    import shutil
+    from oracle import run_reference
+
+    monkeypatch.setattr(run_reference, "OUT", str(tmp_path))
+    shutil.copy(os.path.join(os.path.dirname(__file__), "golden", "hist_golden.npz"), tmp_path / "hist_golden.npz")
+    run_reference.main()
+    fresh = dict(np.load(tmp_path / "reference_run.npz"))
+    assert set(fresh) == set(reference_run)
+    for k in fresh:
+        assert np.array_equal(fresh[k], reference_run[k]), k
