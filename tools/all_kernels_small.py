@@ -1,4 +1,4 @@
-"""Small end-to-end pass over every kernel (for `compute-sanitizer --tool memcheck python tools/sanitize_small.py`)."""
+"""Small end-to-end pass over every kernel of the library (a quick functional check on a fresh box)."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
