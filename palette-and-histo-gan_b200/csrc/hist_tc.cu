@@ -57,7 +57,7 @@ constexpr int D_COLS = 128;                // per channel: [B_hi columns | B_lo 
 constexpr int T_KB_BYTES = 16 * 128;       // 2048: one core-matrix column (8 pixels) for all 128 rows
 constexpr int TILE_BYTES = 4 * T_KB_BYTES; // 8192
 constexpr int STAGE_BYTES = 6 * TILE_BYTES;  // A and B tiles of the three channels: [c][A, B]
-constexpr float W_SCALE = 16384.0f;        // weights are generated as 2^14 K, K in (0, 1]
+constexpr float W_SCALE = 16384.0f;        // RBF weights are generated as 2^14 K, K in (0, 1] (IQ: K / w, see Params)
 static_assert(3 * D_COLS <= TMEM_COLS, "TMEM budget");
 static_assert(KB == 32, "stage = 32 pixels (shifts below)");
 
@@ -103,11 +103,13 @@ struct Params {
   int64_t px_per_split;
   int64_t items;  // n_whole + (B - n_whole) * splits
   float eps;
-  // scaled weight  2^14 K:  IQ: 1 / (wa t + wb),  RBF: 2^(wa t + wb),  t = (x - c)^2
-  float wa, wb;
+  // Coordinates and bin centres are pre-multiplied by the power of two `coord_scale` (exact), d = s (x - c), so that
+  // the inverse-quadratic weight needs one FMA and a reciprocal:  IQ: K / w = 1 / (d d + wb),  wb = w = s^2 sigma^2
+  // in [2^-14, 2^-13];  RBF: 2^14 K = 2^(wa d d + wb)
+  float wa, wb, coord_scale;
   float iy_scale;    // power of two applied to the intensity (x multiplicity) so that the A operand stays below
                      // fp16's 65504: 1 for dense images, 2^-ceil(log2 npix) for de-duplicated ones
-  float inv_scale;   // 1 / (2^14 * 2^14 * iy_scale): raw sums -> true scale
+  float inv_scale;   // 1 / (weight scale^2 * iy_scale): raw sums -> true scale
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -147,15 +149,15 @@ __device__ __forceinline__ ItemRange item_range(const Params& p, int64_t w) {
 template <int METHOD>
 __device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 wa2, f32x2 wb2) {
   const f32x2 d = add2(x, negc);
-  const f32x2 t = mul2(d, d);
-  const f32x2 e = fma2(t, wa2, wb2);
   if (METHOD == PH_METHOD_INVERSE_QUADRATIC) {
+    const f32x2 e = fma2(d, d, wb2);
     // one MUFU.RCP for the two weights (1/e0 = e1 / (e0 e1), 1/e1 = e0 / (e0 e1)): with one reciprocal per weight
     // the forward is bound by the MUFU pipe (16/clk/SM: 768 cycles per 32-pixel stage), measured 5 % slower
     const float e0 = lo_of(e), e1 = hi_of(e);
     const float r = fast_rcp(e0 * e1);
     return pack2(r * e1, r * e0);
   } else {
+    const f32x2 e = fma2(mul2(d, d), wa2, wb2);
     return pack2(fast_ex2(lo_of(e)), fast_ex2(hi_of(e)));
   }
 }
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
     mbar_init(&S.d_empty, PROD_WARPS);
     fence_mbar_init();
   }
-  if (tid < BINS) { S.dom[0][tid] = p.dom_u[tid]; S.dom[1][tid] = p.dom_v[tid]; }
+  if (tid < BINS) { S.dom[0][tid] = p.dom_u[tid] * p.coord_scale; S.dom[1][tid] = p.dom_v[tid] * p.coord_scale; }
   if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
@@ -215,7 +217,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         const float x0 = fmaf(r, 0.5f, 0.5f), x1 = fmaf(g, 0.5f, 0.5f), x2 = fmaf(bl, 0.5f, 0.5f);
         const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
         const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
-        const float d_rg = logf(e0 / e1), d_rb = logf(e0 / e2), d_gb = logf(e1 / e2);
+        const float d_rg = logf(e0 / e1) * p.coord_scale, d_rb = logf(e0 / e2) * p.coord_scale,
+                    d_gb = logf(e1 / e2) * p.coord_scale;
         mbar_wait_relaxed(&S.px_empty[slot], ((it / PR) & 1) ^ 1, 400);
         PxSlot& o = S.px[slot];
         // (u,v): R:(rg, rb)  G:(-rg, gb)  B:(-rb, -gb)   (histogram.py:72-74)
@@ -646,12 +649,20 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.px_per_split = ceil_div(ceil_div(npix, p.splits), KB) * KB;
   p.items = p.n_whole + (batch - p.n_whole) * p.splits;
   p.eps = eps;
+  double weight_scale;  // the generated weights are weight_scale * K
   if (method == PH_METHOD_INVERSE_QUADRATIC) {
-    p.wa = (float)(1.0 / ((double)sigma_sqr * W_SCALE));
-    p.wb = 1.0f / W_SCALE;
+    // s = the power of two nearest to 2^-6.75 / sigma: w = s^2 sigma^2 in [2^-14, 2^-13], weights K / w <= 2^14
+    const int k = (int)lrint(-6.75 - 0.5 * log2((double)sigma_sqr));
+    const double sc = ldexp(1.0, k), w = sc * sc * (double)sigma_sqr;
+    p.coord_scale = (float)sc;
+    p.wa = 0.f;
+    p.wb = (float)w;
+    weight_scale = 1.0 / (double)p.wb;
   } else {
+    p.coord_scale = 1.0f;
     p.wa = (float)(-1.4426950408889634 / (double)sigma_sqr);
     p.wb = 14.0f;
+    weight_scale = (double)W_SCALE;
   }
   p.iy_scale = 1.0f;
   char* ws = static_cast<char*>(workspace);
@@ -670,7 +681,7 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     p.nunique = nunique;
     off += dedup_bytes(batch);
   }
-  p.inv_scale = 1.0f / ((double)W_SCALE * (double)W_SCALE * (double)p.iy_scale);
+  p.inv_scale = (float)(1.0 / (weight_scale * weight_scale * (double)p.iy_scale));
   const int64_t n_tail = batch - p.n_whole;
   if (n_tail > 0) {
     p.partial = reinterpret_cast<float*>(ws + off);
