@@ -555,6 +555,18 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
     pal_dev = index_only()[2]
     ms_argmax = time_it(lambda: io_utils.probabilities_to_indexed(probs, pal_dev), n)
     del probs
+    # f4: augment_two (hue rotation + shared translation + normalize) on 4096 RGBA pairs —
+    # 512 MiB in, 512 MiB out: larger than L2, no flush needed for the roofline figure
+    g = torch.Generator().manual_seed(47)
+    aug_a = (torch.rand(4096, HW, HW, 4, generator=g) * 255).round().to(dev)
+    aug_b = aug_a.flip(0).contiguous()
+    aug_delta = ((torch.rand(4096, generator=g) - 0.5)).to(dev)
+    aug_tr = dataset_utils._draw_translations(4096, HW, HW, g).to(dev)
+    aug_on = (torch.rand(4096, generator=g) < 0.8).to(dev)
+    ms_aug = time_it(lambda: dataset_utils.augment_two(aug_a, aug_b, hue_delta=aug_delta, translations=aug_tr,
+                                                        apply=aug_on, should_normalize=True), n)
+    aug_gbs = 2 * aug_a.numel() * 4 * 2 / (ms_aug * 1e-3) / 1e9
+    del aug_a, aug_b
     # algorithmic bytes: one-hot writer = 4 B index read + 1024 B row write per pixel
     oh_px = PALETTE_BATCH * HW * HW
     oh_gbs = oh_px * (4 + 1024) / (ms_onehot * 1e-3) / 1e9
@@ -576,7 +588,7 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
         "workload": f"cfgB: batch {PALETTE_BATCH} source||target pairs of 64x64 int32 RGBA, grayness ordering",
         "value_with_one_hot": npx / (ms_full * 1e-3) / 1e9, "value": npx / (ms_index * 1e-3) / 1e9,
         "ms": {"extract+index+one_hot": ms_full, "extract+index": ms_index, "one_hot": ms_onehot,
-               "argmax+gather": ms_argmax},
+               "argmax+gather": ms_argmax, "augment_two(4096 pairs)": ms_aug},
         "gpu_launches_per_step": int(launches),
         "roofline": {"bound": "hbm", "kernel": "one_hot_kernel", "achieved": oh_gbs, "peak": peaks["hbm_gbs"],
                      "unit": "GB/s", "frac": oh_gbs / peaks["hbm_gbs"],
@@ -585,6 +597,10 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
                      "peak_source": peaks["source"],
                      "argmax+gather": {"achieved": am_gbs, "frac": am_gbs / peaks["hbm_gbs"],
                                        "note": "argmax_indexed_kernel: 1 024 B read + 20 B written per pixel"},
+                     "augment_two": {"achieved": aug_gbs, "frac": aug_gbs / peaks["hbm_gbs"],
+                                     "note": "augment_pair_kernel (hue rotation + translation + normalize, prob 0.8): "
+                                             "16 B read + 16 B written per pixel and image, 4096 pairs, draws resident on "
+                                             "the device"},
                      "extract+index": {"achieved": idx_gbs, "frac": idx_gbs / peaks["hbm_gbs"],
                                        "note": "36 B/px, one fused launch of 256 CTAs (one per pair) over ~2 Mpix: latency bound"}},
         "e2e": {"value": npx / e2e_s / 1e9, "unit": "Gpix/s", "h2d_bytes_per_step": int(2 * src_np.nbytes),

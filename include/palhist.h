@@ -171,6 +171,18 @@ PH_API int ph_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix,
 PH_API int ph_u8_to_float_image(const uint8_t* image_u8, int64_t npixels, int blacken, int normalize, float* image,
                          void* stream);
 
+/* dataset_utils.py:80-102 `augment_two` for a batch of RGBA float32 image pairs (batch,height,width,4), with the
+ * probability gate of :109-120 and, optionally, the `normalize` of :39-48 that follows it in `load_rgba_ds`
+ * (:220-225) fused in:  hue rotation of channels 0..2 of both images by hue_delta[b] (tf.image.adjust_hue; the
+ * caller draws delta in [-0.5, 0.5), :82), then one shared translation by translation[b] = (dx, dy) pixels
+ * (keras RandomTranslation((-0.15, 0.075), 0.125, "constant", "nearest"), :89: out[y,x] = in[round(y-dy),
+ * round(x-dx)] or 0 outside).  hue_delta (batch) and translation (batch,2) are DEVICE float32 arrays, either
+ * may be NULL (step skipped); apply (batch) device uint8 or NULL: images with apply[b] == 0 pass through
+ * unchanged; second / out_second may both be NULL (single image, :80-84 or :87-92 alone).  Not in place. */
+PH_API int ph_augment_pair(const float* first, const float* second, int64_t batch, int height, int width,
+                    const float* hue_delta, const float* translation, const uint8_t* apply, int normalize,
+                    float* out_first, float* out_second, void* stream);
+
 /* pix2pix_model.py:300-301 `tf.one_hot(idx, depth)`: indexed (n) int32 -> one_hot (n,depth) float32. */
 PH_API int ph_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, void* stream);
 

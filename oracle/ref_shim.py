@@ -23,6 +23,10 @@ per-op behaviour listed below (documented TensorFlow semantics, unverifiable her
   reduce_sum / reduce_mean, reshape, transpose(perm), stack, concat, expand_dims, squeeze, cast, shape, zeros,
   constant, equal, tf.function (identity decorator), tf.newaxis (None)
   io.read_file + image.decode_png(channels=4): the PNG decoded to RGBA uint8 (done with PIL here)
+  image.stateless_random_hue, keras.layers.RandomTranslation, random.uniform, split (augmentation,
+  dataset_utils.py:80-120): adjust_hue / nearest constant-fill translation as restated in oracle/augment_oracle.py;
+  the random draws come from a numpy generator (TensorFlow's Philox streams are not restated) and are recorded in
+  `DRAWS` so that the fixture stores them next to the outputs
 
 Nothing in the product imports this file.
 """
@@ -160,6 +164,46 @@ def _decode_png(path, channels=4):
     return T(np.asarray(Image.open(path).convert("RGBA"), dtype=np.uint8))
 
 
+DRAWS = []  # (kind, values) of every random draw the augmentation stand-ins made, in call order
+_RNG = np.random.default_rng(47)
+
+
+def _stateless_random_hue(image, max_delta, seed):
+    from oracle import augment_oracle as ao
+
+    seed = [int(v) for v in np.asarray(T(seed).numpy()).reshape(-1)]
+    delta = np.float32(np.random.default_rng(seed).uniform(-max_delta, max_delta))
+    DRAWS.append(("hue_delta", float(delta)))
+    return T(ao.adjust_hue_f32(T(image).numpy(), delta))
+
+
+class _RandomTranslation:
+    """keras.layers.RandomTranslation(height_factor, width_factor, fill_mode="constant", interpolation="nearest")
+    applied to an unbatched (H,W,C) image (training=True is the default of TF 2.9's layer)."""
+
+    def __init__(self, height_factor, width_factor, fill_mode="reflect", interpolation="bilinear"):
+        assert fill_mode == "constant" and interpolation == "nearest", "only the reference's configuration"
+        as_pair = lambda f: (float(f[0]), float(f[1])) if isinstance(f, (tuple, list)) else (-float(f), float(f))
+        self.height, self.width = as_pair(height_factor), as_pair(width_factor)
+
+    def __call__(self, image):
+        from oracle import augment_oracle as ao
+
+        img = T(image).numpy()
+        h, w = img.shape[:2]
+        dy = np.float32(np.float32(_RNG.uniform(*self.height)) * np.float32(h))
+        dx = np.float32(np.float32(_RNG.uniform(*self.width)) * np.float32(w))
+        DRAWS.append(("translation", (float(dx), float(dy))))
+        return T(ao.translate_nearest(img, dx, dy))
+
+
+def _random_uniform(shape, minval=0, maxval=None, dtype="float32"):
+    if _dt(dtype) in (torch.int32, torch.int64):
+        return T(_RNG.integers(minval, maxval, size=[int(s) for s in shape]).astype(np.int32))
+    hi = 1.0 if maxval is None else maxval
+    return T(np.asarray(_RNG.uniform(minval, hi, size=[int(s) for s in shape]), np.float32))
+
+
 def build():
     """-> a module object to install as sys.modules['tensorflow']."""
     tf = types.ModuleType("tensorflow")
@@ -196,9 +240,10 @@ def build():
     tf.raw_ops = types.SimpleNamespace(UniqueWithCountsV2=lambda x, axis: unique_with_counts_v2(x, axis))
     tf.strings = types.SimpleNamespace(join=lambda parts, sep="": sep.join(str(p) for p in parts))
     tf.io = types.SimpleNamespace(read_file=_read_file)
-    tf.image = types.SimpleNamespace(decode_png=_decode_png)
-    tf.random = types.SimpleNamespace()
-    tf.keras = types.SimpleNamespace(layers=types.SimpleNamespace())
+    tf.image = types.SimpleNamespace(decode_png=_decode_png, stateless_random_hue=_stateless_random_hue)
+    tf.random = types.SimpleNamespace(uniform=_random_uniform)
+    tf.keras = types.SimpleNamespace(layers=types.SimpleNamespace(RandomTranslation=_RandomTranslation))
+    tf.split = lambda x, n, axis=0: [t.as_subclass(RefTensor) for t in torch.chunk(T(x), int(n), dim=int(axis))]
     tf.data = types.SimpleNamespace(AUTOTUNE=-1)
     return tf
 

@@ -109,5 +109,51 @@ def main():
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 
+N_AUGMENT = 16  # sprite pairs pushed through the reference's augment_two
+
+
+def main_augment():
+    """dataset_utils.py:80-102 (`augment_two` = hue rotation of both images + one shared translation) run from the
+    reference's own source on real sprite pairs -> tests/golden/reference_augment.npz, with the random draws the
+    stand-ins made (hue delta, translation in pixels) stored next to the outputs."""
+    from oracle import ref_shim
+
+    ref_shim.install(REFERENCE)
+    cwd = os.getcwd()
+    os.chdir(REFERENCE)
+    try:
+        import dataset_utils as ref_dataset_utils  # noqa: E402
+        from configuration import DATA_FOLDERS
+
+        ref_shim._RNG = np.random.default_rng(47)
+        firsts, seconds, out_first, out_second, deltas, trans = [], [], [], [], [], []
+        for n in range(N_AUGMENT):
+            imgs = []
+            for side, name in ((2, "front"), (3, "right")):
+                path = os.path.join(DATA_FOLDERS[0], "train", f"{side}-{name}", f"{n}.png")
+                imgs.append(ref_dataset_utils.load_image(path, should_normalize=False))
+            del ref_shim.DRAWS[:]
+            a, b = ref_dataset_utils.augment_two(imgs[0], imgs[1])
+            draws = dict((k, v) for k, v in ref_shim.DRAWS)  # both hue calls share the seed, hence the delta
+            assert [k for k, _ in ref_shim.DRAWS] == ["hue_delta", "hue_delta", "translation"]
+            assert ref_shim.DRAWS[0][1] == ref_shim.DRAWS[1][1]
+            firsts.append(imgs[0].numpy()); seconds.append(imgs[1].numpy())
+            out_first.append(a.numpy()); out_second.append(b.numpy())
+            deltas.append(draws["hue_delta"]); trans.append(draws["translation"])
+        out = {"first": np.stack(firsts).astype(np.float32), "second": np.stack(seconds).astype(np.float32),
+               "out_first": np.stack(out_first).astype(np.float32), "out_second": np.stack(out_second).astype(np.float32),
+               "hue_delta": np.asarray(deltas, np.float32), "translation": np.asarray(trans, np.float32)}
+        out["normalized_first"] = np.stack([np.asarray(t.numpy()) for t in
+                                            (ref_dataset_utils.normalize_two(ref_shim.T(a), ref_shim.T(b))[0]
+                                             for a, b in zip(out["out_first"][:4], out["out_second"][:4]))])
+    finally:
+        os.chdir(cwd)
+    path = os.path.join(OUT, "reference_augment.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "augment":
+        sys.exit(main_augment())
     sys.exit(main())

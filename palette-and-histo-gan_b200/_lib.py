@@ -56,6 +56,7 @@ PROTOTYPES = {
     "ph_rgba_to_indexed": (_int, [_p, _i64, _i64, _p, _i64, _int, _p, _p, _int, _p]),
     "ph_one_hot": (_int, [_p, _i64, _int, _p, _p]),
     "ph_u8_to_float_image": (_int, [_p, _i64, _int, _int, _p, _p]),
+    "ph_augment_pair": (_int, [_p, _p, _i64, _int, _int, _p, _p, _p, _int, _p, _p, _p]),
     "ph_indexed_to_rgba": (_int, [_p, _i64, _i64, _p, _i64, _int, _int, _p, _p]),
     "ph_argmax_indexed": (_int, [_p, _i64, _i64, _int, _p, _i64, _int, _p, _p, _p]),
     "ph_load_indexed_images": (_int, [_p, _p, _i64, _i64, _int, _p, _p, _p, _p, _p]),

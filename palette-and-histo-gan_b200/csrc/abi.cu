@@ -252,6 +252,22 @@ int ph_u8_to_float_image(const uint8_t* image_u8, int64_t npixels, int blacken, 
   return launch_u8_to_float_image(image_u8, npixels, blacken, normalize, image, static_cast<cudaStream_t>(stream));
 }
 
+int ph_augment_pair(const float* first, const float* second, int64_t batch, int height, int width,
+                    const float* hue_delta, const float* translation, const uint8_t* apply, int normalize,
+                    float* out_first, float* out_second, void* stream) {
+  PH_CHECK_ARG(first && out_first, "NULL pointer argument");
+  PH_CHECK_ARG((second == nullptr) == (out_second == nullptr), "second and out_second go together");
+  PH_CHECK_ARG(batch >= 0 && height > 0 && width > 0, "bad shape");
+  PH_CHECK_ARG((int64_t)height * width < (1ll << 31), "image too large");
+  PH_CHECK_ARG(out_first != first && out_second != first && (second == nullptr || (out_first != second && out_second != second)),
+               "augmentation cannot run in place (the translation gathers)");
+  PH_CHECK_ARG(((reinterpret_cast<uintptr_t>(first) | reinterpret_cast<uintptr_t>(second) |
+                 reinterpret_cast<uintptr_t>(out_first) | reinterpret_cast<uintptr_t>(out_second)) & 15) == 0,
+               "RGBA float32 images must be 16-byte aligned");
+  return launch_augment_pair(first, second, batch, height, width, hue_delta, translation, apply, normalize, out_first,
+                             out_second, static_cast<cudaStream_t>(stream));
+}
+
 int ph_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, void* stream) {
   PH_CHECK_ARG(indexed && one_hot && n >= 0 && depth > 0, "bad argument");
   PH_CHECK_ARG((reinterpret_cast<uintptr_t>(one_hot) & 15) == 0, "one_hot must be 16-byte aligned");

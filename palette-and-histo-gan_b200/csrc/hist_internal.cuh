@@ -59,6 +59,9 @@ int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, co
 int launch_u8_to_float_image(const uint8_t* src, int64_t npixels, int blacken, int normalize, float* dst,
                              cudaStream_t st);
 int launch_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, cudaStream_t st);
+int launch_augment_pair(const float* first, const float* second, int64_t batch, int height, int width,
+                        const float* hue_delta, const float* translation, const uint8_t* apply, int normalize,
+                        float* out_first, float* out_second, cudaStream_t st);
 int launch_argmax_indexed(const float* probs, int64_t batch, int64_t npix, int depth, const int32_t* palette,
                           int64_t palette_batch, int palette_rows, int32_t* indexed, int32_t* rgba, cudaStream_t st);
 int launch_indexed_to_rgba(const int32_t* indexed, int64_t batch, int64_t npix, const int32_t* palette,

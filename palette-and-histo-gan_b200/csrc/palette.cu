@@ -472,6 +472,119 @@ int launch_u8_to_float_image(const uint8_t* src, int64_t npixels, int blacken, i
 }
 
 // =============================================================================================
+// Augmentation of an image pair (dataset_utils.py:80-102 `augment_two`): hue rotation of both
+// images by the same delta (tf.image.adjust_hue's (h, v_min, v_max) algorithm, float32 without fused multiply-add
+// so that it matches an op-for-op evaluation bit for bit) and one shared nearest-neighbour translation with
+// constant fill 0 (keras RandomTranslation -> ImageProjectiveTransformV3), optionally followed by `normalize`
+// (:39-48).  One thread per output pixel and image: gather 16 B, write 16 B.  Translation moves pixels, hue maps
+// each pixel on its own, so hue(translate(x)) == translate(hue(x)) with the fill applied last.
+// =============================================================================================
+__device__ __forceinline__ void adjust_hue_pixel(float& r, float& g, float& b, float shift6) {
+  float vmax, vmid, vmin;
+  int cat;
+  // rgb_to_hv_range: the comparison tree decides ties
+  if (r < g) {
+    if (b < r) { vmax = g; vmid = r; vmin = b; cat = 1; }
+    else if (b > g) { vmax = b; vmid = g; vmin = r; cat = 3; }
+    else { vmax = g; vmid = b; vmin = r; cat = 2; }
+  } else {
+    if (b < g) { vmax = r; vmid = g; vmin = b; cat = 0; }
+    else if (b > r) { vmax = b; vmid = r; vmin = g; cat = 4; }
+    else { vmax = r; vmid = b; vmin = g; cat = 5; }
+  }
+  const float span = __fsub_rn(vmax, vmin);
+  float h = 0.f;
+  if (vmax != vmin) {
+    const float ratio = __fdiv_rn(__fsub_rn(vmid, vmin), span);
+    h = __fadd_rn((float)cat, (cat & 1) ? __fsub_rn(1.0f, ratio) : ratio);
+  }
+  h = __fadd_rn(h, shift6);
+  for (int k = 0; k < 4 && h < 0.f; ++k) h = __fadd_rn(h, 6.0f);   // |delta| <= 1 is enforced by the caller
+  for (int k = 0; k < 4 && h >= 6.f; ++k) h = __fsub_rn(h, 6.0f);
+  int c2 = (int)h;
+  float ratio2 = __fsub_rn(h, (float)c2);
+  if (c2 & 1) ratio2 = __fsub_rn(1.0f, ratio2);
+  const float mid = __fadd_rn(vmin, __fmul_rn(ratio2, span));
+  switch (c2) {
+    case 0: r = vmax; g = mid; b = vmin; break;
+    case 1: r = mid; g = vmax; b = vmin; break;
+    case 2: r = vmin; g = vmax; b = mid; break;
+    case 3: r = vmin; g = mid; b = vmax; break;
+    case 4: r = mid; g = vmin; b = vmax; break;
+    default: r = vmax; g = vmin; b = mid; break;
+  }
+}
+
+constexpr int AUG_PX_PER_THREAD = 4;
+
+// grid.x = image (first images, then second images), grid.y = chunk of 1024 pixels; 32-bit index arithmetic, four
+// independent 16-byte gathers in flight per thread
+__global__ void __launch_bounds__(256) augment_pair_kernel(const float4* __restrict__ first,
+                                                           const float4* __restrict__ second, int batch,
+                                                           int height, int width,
+                                                           const float* __restrict__ hue_delta,
+                                                           const float* __restrict__ translation,
+                                                           const uint8_t* __restrict__ apply, int normalize,
+                                                           float4* __restrict__ out_first,
+                                                           float4* __restrict__ out_second) {
+  const int npix = height * width;
+  const int which = (int)blockIdx.x >= batch;
+  const int b = (int)blockIdx.x - which * batch;
+  const float4* src = (which ? second : first) + (int64_t)b * npix;
+  float4* dst = (which ? out_second : out_first) + (int64_t)b * npix;
+  const bool on = apply == nullptr || apply[b] != 0;
+  const bool move = on && translation != nullptr, rotate = on && hue_delta != nullptr;
+  const float ndx = move ? -__ldg(translation + 2 * b) : 0.f, ndy = move ? -__ldg(translation + 2 * b + 1) : 0.f;
+  const float shift6 = rotate ? __fmul_rn(__ldg(hue_delta + b), 6.0f) : 0.f;
+  const int px0 = blockIdx.y * (256 * AUG_PX_PER_THREAD) + threadIdx.x;
+  float4 q[AUG_PX_PER_THREAD];
+  bool inside[AUG_PX_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < AUG_PX_PER_THREAD; ++k) {
+    const int px = px0 + k * 256;
+    const int y = px / width, x = px - y * width;
+    int s = px;
+    inside[k] = px < npix;
+    if (move) {
+      // input = 1*x + 0*y + (-dx), rounded half away from zero (std::round); outside -> fill value 0
+      const float fx = roundf(__fadd_rn((float)x, ndx)), fy = roundf(__fadd_rn((float)y, ndy));
+      inside[k] = inside[k] && fx >= 0.f && fx < (float)width && fy >= 0.f && fy < (float)height;
+      s = inside[k] ? (int)fy * width + (int)fx : 0;
+    }
+    q[k] = inside[k] ? __ldg(src + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < AUG_PX_PER_THREAD; ++k) {
+    const int px = px0 + k * 256;
+    if (px >= npix) continue;
+    if (rotate && inside[k]) adjust_hue_pixel(q[k].x, q[k].y, q[k].z, shift6);
+    if (normalize) {
+      q[k].x = __fsub_rn(__fdiv_rn(q[k].x, 127.5f), 1.0f);
+      q[k].y = __fsub_rn(__fdiv_rn(q[k].y, 127.5f), 1.0f);
+      q[k].z = __fsub_rn(__fdiv_rn(q[k].z, 127.5f), 1.0f);
+      q[k].w = __fsub_rn(__fdiv_rn(q[k].w, 127.5f), 1.0f);
+    }
+    __stcs(dst + px, q[k]);
+  }
+}
+
+int launch_augment_pair(const float* first, const float* second, int64_t batch, int height, int width,
+                        const float* hue_delta, const float* translation, const uint8_t* apply, int normalize,
+                        float* out_first, float* out_second, cudaStream_t st) {
+  const int64_t images = batch * (second ? 2 : 1);
+  PH_CHECK_ARG(images < (1ll << 31), "batch too large");
+  if (images == 0) return PH_OK;
+  const int64_t chunks = ceil_div((int64_t)height * width, 256 * AUG_PX_PER_THREAD);
+  PH_CHECK_ARG(chunks <= 65535, "image too large");
+  augment_pair_kernel<<<dim3((unsigned)images, (unsigned)chunks), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(first), reinterpret_cast<const float4*>(second), (int)batch, height, width,
+      hue_delta, translation, apply, normalize, reinterpret_cast<float4*>(out_first),
+      reinterpret_cast<float4*>(out_second));
+  PH_LAUNCH_OK("augment_pair_kernel");
+  return PH_OK;
+}
+
+// =============================================================================================
 // launchers
 // =============================================================================================
 int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows,

@@ -40,7 +40,7 @@ def test_header_declares_expected_surface():
     text = open(HEADER).read()
     for ref in ("histogram.py:36-81", "histogram.py:5-32", "histogram.py:84-89", "io_utils.py:25-65",
                 "io_utils.py:78-93", "io_utils.py:96-103", "pix2pix_model.py:300-301",
-                "dataset_utils.py:138-151"):
+                "dataset_utils.py:138-151", "dataset_utils.py:80-102"):
         assert ref in text, ref
 
 

@@ -278,3 +278,80 @@ def test_reference_run_fixture_is_reproducible(tmp_path, monkeypatch, reference_
     assert set(fresh) == set(reference_run)
     for k in fresh:
         assert np.array_equal(fresh[k], reference_run[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------
+# Augmentation (dataset_utils.py:80-120)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def reference_augment():
+    return dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_augment.npz")))
+
+
+def test_augment_oracle_equals_reference_source(reference_augment):
+    """The reference's own `augment_two` (run over the shim, whose image ops are the restated TF algorithms) and a
+    direct call of the oracle agree bit for bit: pins the glue (hue on channels 0..2 only, alpha carried, one
+    translation shared by the channel-concatenated pair)."""
+    from oracle import augment_oracle as ao
+
+    R = reference_augment
+    for n in range(R["first"].shape[0]):
+        a, b = ao.augment_two(R["first"][n], R["second"][n], R["hue_delta"][n], *R["translation"][n])
+        assert np.array_equal(a, R["out_first"][n]) and np.array_equal(b, R["out_second"][n])
+    assert np.array_equal(ao.normalize(R["out_first"][:4]), R["normalized_first"])
+    assert np.all(np.abs(R["hue_delta"]) <= 0.5)
+    assert np.all(np.abs(R["translation"][:, 0]) <= 8.0) and np.all(R["translation"][:, 1] >= -9.6 - 1e-5)
+    assert np.all(R["translation"][:, 1] <= 4.8 + 1e-5)
+
+
+def test_adjust_hue_against_hsv_arithmetic():
+    """Independent check of the restated `tf.image.adjust_hue`: the textbook RGB -> HSV -> shift h -> RGB route
+    (python's colorsys, float64) gives the same colours to float32 round-off; grey stays grey; a full turn and a
+    zero shift are the identity (up to round-off), +delta then -delta returns."""
+    import colorsys
+    from oracle import augment_oracle as ao
+
+    rng = np.random.default_rng(5)
+    x = rng.integers(0, 256, (400, 3)).astype(np.float32)
+    x[:20, 1] = x[:20, 0]
+    x[20:40, 2] = x[20:40, 1]
+    x[40:60] = x[40:60, :1]
+    for d in (-0.5, -0.31, 0.0, 0.125, 0.49):
+        y = ao.adjust_hue_f32(x, d)
+        ref = np.array([colorsys.hsv_to_rgb((colorsys.rgb_to_hsv(*(p / 255.0))[0] + d) % 1.0,
+                                            *colorsys.rgb_to_hsv(*(p / 255.0))[1:]) for p in x]) * 255.0
+        assert np.abs(y - ref).max() < 5e-4, d
+        assert np.array_equal(y[40:60], x[40:60])              # grey pixels: v_max == v_min
+        assert np.allclose(np.sort(y, -1)[:, [0, 2]], np.sort(x, -1)[:, [0, 2]])  # min and max are kept
+    assert np.abs(ao.adjust_hue_f32(x, 0.0) - x).max() < 2e-4
+    assert np.abs(ao.adjust_hue_f32(x, 1.0) - x).max() < 2e-4
+    assert np.abs(ao.adjust_hue_f32(ao.adjust_hue_f32(x, 0.2), -0.2) - x).max() < 5e-4
+
+
+def test_translate_nearest_semantics():
+    """ImageProjectiveTransformV3 (NEAREST, CONSTANT 0) with a pure translation: integer shifts move the image,
+    x.5 offsets round half away from zero, everything that leaves the frame is zero."""
+    from oracle import augment_oracle as ao
+
+    img = np.arange(1, 6 * 5 * 2 + 1, dtype=np.float32).reshape(6, 5, 2)
+    out = ao.translate_nearest(img, 2.0, -1.0)        # right by 2, up by 1
+    assert np.array_equal(out[:5, 2:], img[1:, :3]) and not out[:, :2].any() and not out[5].any()
+    assert np.array_equal(ao.translate_nearest(img, 0.0, 0.0), img)
+    # out[x] = in[round(x - 0.5)]: round(-0.5) = -1 (outside), round(0.5) = 1, round(1.5) = 2 ...
+    half = ao.translate_nearest(img, 0.5, 0.0)
+    assert not half[:, 0].any() and np.array_equal(half[:, 1:4], img[:, 1:4]) and np.array_equal(half[:, 4], img[:, 4])
+    assert not ao.translate_nearest(img, 50.0, 0.0).any()
+    a, b = ao.augment_translation((img[..., :1], img[..., 1:]), 1.0, 1.0)
+    assert np.array_equal(a[1:, 1:, 0], img[:-1, :-1, 0]) and np.array_equal(b[1:, 1:, 0], img[:-1, :-1, 1])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/datasets"), reason="build container only: needs the reference")
+def test_reference_augment_fixture_is_reproducible(tmp_path, monkeypatch, reference_augment):
+    from oracle import run_reference
+
+    monkeypatch.setattr(run_reference, "OUT", str(tmp_path))
+    run_reference.main_augment()
+    fresh = dict(np.load(tmp_path / "reference_augment.npz"))
+    assert set(fresh) == set(reference_augment)
+    for k in fresh:
+        assert np.array_equal(fresh[k], reference_augment[k]), k
