@@ -40,6 +40,11 @@ size_t tc_bwd_workspace_bytes(int64_t batch, int bins);  // hist_tc_bwd.cu: G^ o
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                     int bins, int method, float sigma_sqr, float eps, float* hist, float* denom,
                     void* workspace, bool dedup, const float* hist_true, double* ssum, cudaStream_t st);
+// hist_tc_fwd256.cu: dedicated 256-bin forward (whole 256 x 256 histogram of a channel in one CTA's tensor memory)
+size_t tc_fwd256_workspace_bytes(int64_t batch, int64_t npix);
+int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int method,
+                      float sigma_sqr, float eps, const float4* ulist, const int* nunique, int dedup_max,
+                      float iy_scale, float* hist, float* denom, void* workspace, cudaStream_t st);
 int launch_hellinger_ssum_accumulate(const float* ht, const float* hp, int64_t n, double* ssum, cudaStream_t st);
 int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                      int bins, int method, float sigma_sqr, float eps, const float* hist_pred,

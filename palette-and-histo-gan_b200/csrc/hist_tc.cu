@@ -29,12 +29,16 @@
 #include "common.cuh"
 #include "hist_internal.cuh"
 #include "tc_ptx.cuh"
+#include "hist_tc_gen.cuh"
 
 namespace ph {
 
 using namespace tc;
 
 namespace fwdtc {
+
+using tcgen::named_bar_sync;
+using tcgen::weight2;
 
 constexpr int BINS = 64;
 constexpr int KB = 32;         // pixels per pipeline stage
@@ -57,7 +61,6 @@ constexpr int D_COLS = 128;                // per channel: [B_hi columns | B_lo 
 constexpr int T_KB_BYTES = 16 * 128;       // 2048: one core-matrix column (8 pixels) for all 128 rows
 constexpr int TILE_BYTES = 4 * T_KB_BYTES; // 8192
 constexpr int STAGE_BYTES = 6 * TILE_BYTES;  // A and B tiles of the three channels: [c][A, B]
-constexpr float W_SCALE = 16384.0f;        // RBF weights are generated as 2^14 K, K in (0, 1] (IQ: K / w, see Params)
 static_assert(3 * D_COLS <= TMEM_COLS, "TMEM budget");
 static_assert(KB == 32, "stage = 32 pixels (shifts below)");
 
@@ -112,10 +115,6 @@ struct Params {
   float inv_scale;   // 1 / (weight scale^2 * iy_scale): raw sums -> true scale
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 // Pixel range of a work item.  A de-duplicated image is a list of (colour, multiplicity) entries: the
 // histogram is linear in the pixels, so identical pixels are contracted once with weight count*Iy.
 struct ItemRange {  // 32-bit pixel range: keeps the role loops in the uniform datapath
@@ -143,23 +142,6 @@ __device__ __forceinline__ ItemRange item_range(const Params& p, int64_t w) {
   r.px0 = (uint32_t)split * (uint32_t)p.px_per_split;
   r.px1 = min(r.px0 + (uint32_t)p.px_per_split, (uint32_t)p.npix);
   return r;
-}
-
-// two scaled bin weights at once (two pixels, one bin): d = x + (-c)
-template <int METHOD>
-__device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 wa2, f32x2 wb2) {
-  const f32x2 d = add2(x, negc);
-  if (METHOD == PH_METHOD_INVERSE_QUADRATIC) {
-    const f32x2 e = fma2(d, d, wb2);
-    // one MUFU.RCP for the two weights (1/e0 = e1 / (e0 e1), 1/e1 = e0 / (e0 e1)): with one reciprocal per weight
-    // the forward is bound by the MUFU pipe (16/clk/SM: 768 cycles per 32-pixel stage), measured 5 % slower
-    const float e0 = lo_of(e), e1 = hi_of(e);
-    const float r = fast_rcp(e0 * e1);
-    return pack2(r * e1, r * e0);
-  } else {
-    const f32x2 e = fma2(mul2(d, d), wa2, wb2);
-    return pack2(fast_ex2(lo_of(e)), fast_ex2(hi_of(e)));
-  }
 }
 
 template <int METHOD, bool FUSE_SSUM>
@@ -605,6 +587,10 @@ size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins) {
   size_t fwd = tail_bytes(tc_fwd_plan(batch, npix, false), batch);
   if (tc_fwd_plan(batch, npix, true).n_whole == batch) fwd += dedup_bytes(batch);
   if (nb > 1) fwd += align_up((size_t)batch * nb * nb * 3 * 64 * 64 * sizeof(float), 256);
+  if (bins == 256) {  // dedicated 256-bin kernel (hist_tc_fwd256.cu): [unique-colour lists][per-item partial sums]
+    const size_t f256 = dedup_bytes(batch) + tc_fwd256_workspace_bytes(batch, npix);
+    if (f256 > fwd) fwd = f256;
+  }
   const size_t bwd = tc_bwd_workspace_bytes(batch, bins);
   return align_up(fwd > bwd ? fwd : bwd, 256) + 256;
 }
@@ -637,6 +623,34 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   using namespace fwdtc;
   PH_CHECK_ARG(bins >= BINS && bins % BINS == 0, "tensor-core forward needs a multiple of 64 bins");
   const int nb = bins / BINS;
+  static const bool fwd256_off = getenv("PH_FWD256") && atoi(getenv("PH_FWD256")) == 0;  // tuning knob: block path
+  if (bins == 256 && !fwd256_off) {
+    // the whole 256 x 256 histogram per CTA (tensor-pipe bound) instead of 16 blocks of 64 x 64
+    char* ws = static_cast<char*>(workspace);
+    const float4* ulist = nullptr;
+    const int* nunique = nullptr;
+    float iy_scale = 1.0f;
+    size_t off = 0;
+    if (dedup) {
+      int e = 0;
+      while (((int64_t)1 << e) < npix) ++e;
+      iy_scale = ldexpf(1.0f, -e);
+      float4* ul = reinterpret_cast<float4*>(ws);
+      int* nu = reinterpret_cast<int*>(ws + align_up((size_t)batch * DEDUP_MAX * sizeof(float4), 256));
+      if (batch > 0) {
+        hist_dedup_kernel<<<(unsigned)batch, 256, 0, st>>>(image, npix, channels, ul, nu);
+        PH_LAUNCH_OK("hist_dedup_kernel");
+      }
+      ulist = ul;
+      nunique = nu;
+      off = dedup_bytes(batch);
+    }
+    const int rc = tc_fwd256_forward(image, batch, npix, channels, dom, method, sigma_sqr, eps, ulist, nunique,
+                                     DEDUP_MAX, iy_scale, hist, denom, ws + off, st);
+    if (rc != PH_OK) return rc;
+    if (ssum != nullptr) return launch_hellinger_ssum_accumulate(hist_true, hist, batch * (int64_t)bins * bins * 3, ssum, st);
+    return PH_OK;
+  }
   Params p{};
   p.image = image;
   p.hist = hist;
@@ -649,21 +663,11 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.px_per_split = ceil_div(ceil_div(npix, p.splits), KB) * KB;
   p.items = p.n_whole + (batch - p.n_whole) * p.splits;
   p.eps = eps;
-  double weight_scale;  // the generated weights are weight_scale * K
-  if (method == PH_METHOD_INVERSE_QUADRATIC) {
-    // s = the power of two nearest to 2^-6.75 / sigma: w = s^2 sigma^2 in [2^-14, 2^-13], weights K / w <= 2^14
-    const int k = (int)lrint(-6.75 - 0.5 * log2((double)sigma_sqr));
-    const double sc = ldexp(1.0, k), w = sc * sc * (double)sigma_sqr;
-    p.coord_scale = (float)sc;
-    p.wa = 0.f;
-    p.wb = (float)w;
-    weight_scale = 1.0 / (double)p.wb;
-  } else {
-    p.coord_scale = 1.0f;
-    p.wa = (float)(-1.4426950408889634 / (double)sigma_sqr);
-    p.wb = 14.0f;
-    weight_scale = (double)W_SCALE;
-  }
+  const tcgen::WeightScales wsc = tcgen::weight_scales(method, sigma_sqr);
+  p.coord_scale = wsc.coord_scale;
+  p.wa = wsc.wa;
+  p.wb = wsc.wb;
+  const double weight_scale = wsc.weight_scale;  // the generated weights are weight_scale * K
   p.iy_scale = 1.0f;
   char* ws = static_cast<char*>(workspace);
   size_t off = 0;

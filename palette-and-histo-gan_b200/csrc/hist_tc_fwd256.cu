@@ -1,0 +1,421 @@
+// RGB-uv histogram forward with 256 bins (cfgE: 256 x 256 images, SURVEY.md §8 "scale sweep"), tensor-core
+// engine: the regime where the Ku^T.Kv contraction (histogram.py:29-30) is bound by the tensor pipe instead of
+// by the generation of the operands.
+//
+// The 64-bin kernel of hist_tc.cu covers 256 bins as 16 blocks of 64 x 64, regenerating the 64 + 64 weights of
+// every pixel for every block (4-fold redundant generation).  Here one CTA contracts the whole 256 x 256
+// histogram of ONE channel at a time: the accumulator is 256 rows (u-bins) x 256 columns (v-bins) of fp32 =
+// two M=128 halves x 256 TMEM columns = all 512 columns of the SM's tensor memory, and every generated weight
+// is used against 256 others (512 algorithmic FLOP per weight instead of 128).
+//
+//   per 16-pixel stage and channel:  A_hi, A_lo (256 u-bins x 16 pixels, Iy-weighted), B_hi, B_lo (256 v-bins x 16)
+//   as fp16 K-major no-swizzle tiles in shared memory (32 KB per stage, 4 stages); the MMA warp issues, per half
+//   h of the u-bins, D[h] += A_hi[h].B_hi + A_hi[h].B_lo + A_lo[h].B_hi  (tcgen05.mma kind::f16, SS, M128 N256 K16:
+//   6 instructions x 128 cycles per stage = the tensor pipe's full rate; the fp16 hi+lo split with three
+//   products carries ~22 significant bits, hist_tc.cu / DESIGN.md §5).
+//
+//   warps 0-7 generate the A side, 8-15 the B side (thread = one bin, 16 pixels per stage), warp 16 issues the
+//   MMAs, warps 17-19 are the pixel pass (128-bit loads, log-chroma u/v of the current channel and Iy into a
+//   shared-memory ring).  The three channels of an item run one after the other (the pixel pass re-reads the
+//   16 B pixel per channel: 3 MB per 256 x 256 image against 77 GFLOP).
+//
+//   Accuracy: as in the 64-bin kernel the accumulation chains are cut every 1024 pixels; the 16 producer warps
+//   then drain the 64 K accumulators (tcgen05.ld) into the item's fp32 partial sums in global memory, laid out
+//   [channel][v-bin][u-bin] so that a warp's 32 TMEM lanes (consecutive u-bins) make one 128-byte access: plain
+//   stores for the first chain, fire-and-forget reductions (RED.ADD.F32) afterwards — every address is owned by
+//   one thread of one CTA, so the sums are deterministic.  `hist256_finalize_kernel` adds the slices of an image
+//   in order, computes the normaliser D (histogram.py:77-79) and writes H / D channel-last (B,256,256,3).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "hist_internal.cuh"
+#include "hist_tc_gen.cuh"
+#include "tc_ptx.cuh"
+
+namespace ph {
+
+using namespace tc;
+
+namespace fwd256 {
+
+using tcgen::weight2;
+
+constexpr int BINS = 256;
+constexpr int KB = 16;         // pixels per stage = one K step of the instruction
+constexpr int SLOT_PX = 32;    // pixels per pixel-ring slot = two stages (lane = pixel in the pixel pass)
+constexpr int NS = 4;          // operand stages
+constexpr int CHAIN_KB = 64;   // stages per TMEM accumulation chain (1024 pixels)
+constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 3;
+constexpr int PROD_WARPS = A_WARPS + B_WARPS;
+constexpr int MMA_WARP = PROD_WARPS;            // 16
+constexpr int PX_WARP0 = MMA_WARP + 1;          // 17
+constexpr int PR = 4;                           // pixel ring slots
+constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 640
+constexpr int TMEM_COLS = 512;
+// one operand part (hi or lo) of one side for one stage: 256 rows x 16 pixels of fp16, K-major, no swizzle:
+//   [kcol = pixel / 8 (2)][row / 8 (32)][row % 8][pixel % 8]     core matrix = 8 rows x 8 halfs = 128 B
+constexpr int KCOL_BYTES = 32 * 128;          // 4096: LBO, the two core-matrix columns along K
+constexpr int TILE_BYTES = 2 * KCOL_BYTES;    // 8192
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // A_hi | A_lo | B_hi | B_lo
+constexpr int HIST_ELEMS = 3 * BINS * BINS;   // per item: [c][j][i]
+
+struct PxSlot {
+  float u[SLOT_PX], v[SLOT_PX], iy[SLOT_PX];
+};
+
+struct Smem {
+  alignas(128) unsigned char ab[NS][STAGE_BYTES];  // 128 KB
+  PxSlot px[PR];
+  float dom[BINS];
+  alignas(8) uint64_t px_full[PR], px_empty[PR], ab_full[NS], ab_empty[NS], d_full, d_empty;
+  uint32_t tmem_base;
+};
+
+struct Params {
+  const float* image;
+  const float* dom;      // 256 bin centres (both sides)
+  float* partial;        // (items, 3, 256, 256) raw scaled sums, [c][j][i]
+  const float4* ulist;   // optional (B, dedup_max): unique colours (r,g,b,count) of each image, or NULL
+  const int* nunique;    // optional (B): number of unique colours, < 0 = image not de-duplicated
+  int dedup_max;
+  int64_t npix;
+  int channels;
+  int splits;            // pixel slices per image (1 when de-duplicated)
+  int64_t px_per_split;  // multiple of SLOT_PX
+  int64_t items;         // B * splits
+  float eps;
+  float wa, wb, coord_scale, iy_scale;  // as in hist_tc.cu
+};
+
+struct ItemRange {
+  int64_t b;
+  uint32_t px0, px1;
+  bool dedup;
+};
+__device__ __forceinline__ ItemRange item_range(const Params& p, int64_t w) {
+  ItemRange r;
+  r.b = w / p.splits;
+  const uint32_t split = (uint32_t)(w - r.b * p.splits);
+  r.px0 = split * (uint32_t)p.px_per_split;
+  r.px1 = min(r.px0 + (uint32_t)p.px_per_split, (uint32_t)p.npix);
+  r.dedup = false;
+  if (p.nunique != nullptr) {
+    const int nu = __shfl_sync(0xffffffffu, __ldg(p.nunique + r.b), 0);
+    if (nu >= 0) { r.px0 = 0; r.px1 = (uint32_t)nu; r.dedup = true; }
+  }
+  return r;
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 1); mbar_init(&S.px_empty[i], PROD_WARPS); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&S.ab_full[i], PROD_WARPS); mbar_init(&S.ab_empty[i], 1); }
+    mbar_init(&S.d_full, 1);
+    mbar_init(&S.d_empty, PROD_WARPS);
+    fence_mbar_init();
+  }
+  if (tid < BINS) S.dom[tid] = p.dom[tid] * p.coord_scale;
+  if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  const int64_t first = blockIdx.x, step = gridDim.x;
+
+  if (warp >= PX_WARP0) {
+    // ===================== pixel pass: one 32-pixel slot of the current channel per round =====================
+    const int me = warp - PX_WARP0;
+    uint32_t sit = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      for (int c = 0; c < 3; ++c) {
+        for (uint32_t base = ir.px0; base < ir.px1; base += SLOT_PX, ++sit) {
+          if ((int)(sit % PXW) != me) continue;
+          const int slot = sit % PR;
+          const uint32_t px = base + lane;
+          float r = 0.f, g = 0.f, bl = 0.f, mult = 1.f;
+          const bool valid = px < ir.px1;
+          if (valid && ir.dedup) {
+            const float4 q = __ldg(p.ulist + ir.b * p.dedup_max + px);
+            r = q.x; g = q.y; bl = q.z; mult = q.w;
+          } else if (valid) {
+            const float* src = p.image + (ir.b * p.npix + px) * p.channels;
+            if (p.channels == 4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+              r = q.x; g = q.y; bl = q.z;
+            } else {
+              r = __ldg(src); g = __ldg(src + 1); bl = __ldg(src + 2);
+            }
+          }
+          // histogram.py:58-66, :13-17, :72-74 — the same expressions as the 64-bin kernel
+          const float x0 = fmaf(r, 0.5f, 0.5f), x1 = fmaf(g, 0.5f, 0.5f), x2 = fmaf(bl, 0.5f, 0.5f);
+          const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
+          const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
+          float u, v;
+          if (c == 0) { u = logf(e0 / e1) * p.coord_scale; v = logf(e0 / e2) * p.coord_scale; }
+          else if (c == 1) { u = -(logf(e0 / e1) * p.coord_scale); v = logf(e1 / e2) * p.coord_scale; }
+          else { u = -(logf(e0 / e2) * p.coord_scale); v = -(logf(e1 / e2) * p.coord_scale); }
+          mbar_wait_relaxed(&S.px_empty[slot], ((sit / PR) & 1) ^ 1, 400);
+          PxSlot& o = S.px[slot];
+          o.u[lane] = u;
+          o.v[lane] = v;
+          o.iy[lane] = valid ? iy * mult * p.iy_scale : 0.f;  // masked pixels contribute nothing (A operand = 0)
+          mbar_arrive_warp(&S.px_full[slot]);
+        }
+      }
+    }
+  } else if (warp < PROD_WARPS) {
+    // ===================== operand producers (A: warps 0-7, B: warps 8-15) + chain drain =====================
+    const int side = warp >> 3;  // warp-uniform
+    const int bin = tid & 255;
+    const float c_bin = S.dom[bin];
+    const f32x2 negc = pack2(-c_bin, -c_bin);
+    const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
+    const uint32_t row_off = (uint32_t)(side * 2 * TILE_BYTES + (bin >> 3) * 128 + (bin & 7) * 16);
+    // drain role: TMEM sub-partition quad = warp % 4 (lanes 32 quad ..), column group cg = warp / 4: u-bin half
+    // h = cg / 2 (accumulator D[h] = columns 256 h ..), v-bins j in [128 (cg % 2), +128)
+    const int quad = warp & 3, cg = warp >> 2;
+    const int i_row = (cg >> 1) * 128 + quad * 32 + lane;
+    const int j0 = (cg & 1) * 128;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    uint32_t it = 0, chain = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const uint32_t nkb = 2 * ((ir.px1 - ir.px0 + SLOT_PX - 1) / SLOT_PX);  // even: a slot is two stages
+      float* item_out = p.partial + w * (int64_t)HIST_ELEMS;
+      for (int c = 0; c < 3; ++c) {
+        for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t sit = it >> 1;
+          const int slot = sit % PR, stage = it % NS, half = it & 1;
+          mbar_wait(&S.px_full[slot], (sit / PR) & 1);
+          const PxSlot& in = S.px[slot];
+          const float* src = (side == 0 ? in.u : in.v) + half * KB;
+          ulonglong2 xx[4], iw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xx[q] = *reinterpret_cast<const ulonglong2*>(src + 4 * q);
+          if (side == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) iw[q] = *reinterpret_cast<const ulonglong2*>(&in.iy[half * KB + 4 * q]);
+          }
+          if (half == 1) mbar_arrive_warp(&S.px_empty[slot]);
+          uint4 hi[2], lo[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            f32x2 w0 = weight2<METHOD>(xx[2 * q].x, negc, wa2, wb2);
+            f32x2 w1 = weight2<METHOD>(xx[2 * q].y, negc, wa2, wb2);
+            f32x2 w2 = weight2<METHOD>(xx[2 * q + 1].x, negc, wa2, wb2);
+            f32x2 w3 = weight2<METHOD>(xx[2 * q + 1].y, negc, wa2, wb2);
+            if (side == 0) {
+              w0 = mul2(w0, iw[2 * q].x); w1 = mul2(w1, iw[2 * q].y);
+              w2 = mul2(w2, iw[2 * q + 1].x); w3 = mul2(w3, iw[2 * q + 1].y);
+            }
+            split_f16x2(w0, mone2, hi[q].x, lo[q].x);
+            split_f16x2(w1, mone2, hi[q].y, lo[q].y);
+            split_f16x2(w2, mone2, hi[q].z, lo[q].z);
+            split_f16x2(w3, mone2, hi[q].w, lo[q].w);
+          }
+          mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this stage are done
+          unsigned char* tile = &S.ab[stage][row_off];
+          *reinterpret_cast<uint4*>(tile) = hi[0];
+          *reinterpret_cast<uint4*>(tile + KCOL_BYTES) = hi[1];
+          *reinterpret_cast<uint4*>(tile + TILE_BYTES) = lo[0];
+          *reinterpret_cast<uint4*>(tile + TILE_BYTES + KCOL_BYTES) = lo[1];
+          fence_proxy_async_smem();
+          mbar_arrive_warp(&S.ab_full[stage]);
+
+          const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
+          if (!chain_end) continue;
+          // ---- chain drain: D (TMEM) -> the item's fp32 partial sums [c][j][i] in global memory ----
+          mbar_wait(&S.d_full, chain & 1);
+          ++chain;
+          tc_fence_after_sync();
+          const bool first_chain = kb < CHAIN_KB;
+          float* dst = item_out + (int64_t)c * (BINS * BINS) + (int64_t)j0 * BINS + i_row;
+#pragma unroll 1
+          for (int blk = 0; blk < 4; ++blk) {
+            uint32_t vals[32];
+            tmem_ld32(tmem + lane_addr + cg * 128 + blk * 32, vals);
+            tmem_ld_wait();
+            if (blk == 3) {
+              tc_fence_before_sync();
+              mbar_arrive_warp(&S.d_empty);  // everything of this chain is in registers: the next chain may start
+            }
+            float* d = dst + (int64_t)(blk * 32) * BINS;
+            if (first_chain) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) d[k * BINS] = __uint_as_float(vals[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) atomicAdd(d + k * BINS, __uint_as_float(vals[k]));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issue: the whole warp runs the (uniform) loop, one elected lane issues ====
+    constexpr uint32_t IDESC = idesc_f16(128, 256);
+    const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(&S.ab[0][0]), KCOL_BYTES, 128);
+    const uint32_t dlo0 = (uint32_t)desc0, dhi = (uint32_t)(desc0 >> 32);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t stage = 0, phase = 0, chain_par = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const uint32_t nkb = 2 * ((ir.px1 - ir.px0 + SLOT_PX - 1) / SLOT_PX);
+      for (int c = 0; c < 3; ++c) {
+        for (uint32_t kb0 = 0; kb0 < nkb; kb0 += CHAIN_KB) {
+          const uint32_t n_this = min((uint32_t)CHAIN_KB, nkb - kb0);
+          for (uint32_t k = 0; k < n_this; ++k) {
+            mbar_wait(&S.ab_full[stage], phase);
+            tc_fence_after_sync();
+            const uint32_t dstage = dlo0 + stage * (STAGE_BYTES >> 4);
+            const uint32_t b_hi = dstage + ((2 * TILE_BYTES) >> 4), b_lo = dstage + ((3 * TILE_BYTES) >> 4);
+            const uint32_t acc0 = (k == 0) ? 0u : 1u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              // rows 128 h .. of the A tiles: 16 row groups x 128 B further
+              const uint32_t a_hi = dstage + ((h * 16 * 128) >> 4), a_lo = a_hi + (TILE_BYTES >> 4);
+              if (elect_one_sync()) {
+                mma_f16_ss2(tm + h * 256, a_hi, b_hi, dhi, IDESC, acc0);
+                mma_f16_ss2(tm + h * 256, a_hi, b_lo, dhi, IDESC, 1u);
+                mma_f16_ss2(tm + h * 256, a_lo, b_hi, dhi, IDESC, 1u);
+              }
+            }
+            if (elect_one_sync()) mma_commit(&S.ab_empty[stage]);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+          if (elect_one_sync()) mma_commit(&S.d_full);
+          mbar_wait(&S.d_empty, chain_par);
+          tc_fence_after_sync();
+          chain_par ^= 1;
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// out[b, i, j, c] = (sum over the slices of partial[b][s][c][j][i]) / D_b,  D_b = sum of all of it
+// (histogram.py:75-79).  One CTA per image: pass 1 adds the slices in order into slice 0 and reduces D, pass 2
+// transposes 32 x 32 (i, j) tiles through shared memory so that both sides are coalesced.
+__global__ void __launch_bounds__(256) hist256_finalize_kernel(float* __restrict__ partial, int splits,
+                                                               float inv_scale, float* __restrict__ hist,
+                                                               float* __restrict__ denom) {
+  constexpr int CH_STRIDE = 32 * 33 + 11;  // channel planes land on different banks
+  __shared__ double scratch[32];
+  __shared__ float tile[3 * CH_STRIDE];
+  const int64_t b = blockIdx.x;
+  float* mine = partial + b * splits * (int64_t)HIST_ELEMS;
+  double acc = 0.0;
+  for (int e = threadIdx.x * 4; e < HIST_ELEMS; e += 256 * 4) {
+    float4 v = *reinterpret_cast<const float4*>(mine + e);
+    for (int s = 1; s < splits; ++s) {
+      const float4 q = *reinterpret_cast<const float4*>(mine + (int64_t)s * HIST_ELEMS + e);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (splits > 1) *reinterpret_cast<float4*>(mine + e) = v;
+    acc += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+  }
+  const float d = (float)block_sum(acc, scratch);
+  if (threadIdx.x == 0) denom[b] = d * inv_scale;
+  const float inv_d = 1.0f / d;
+  __syncthreads();  // pass 1's writes to slice 0 are visible to the whole block
+  float* out = hist + b * (int64_t)HIST_ELEMS;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int t = 0; t < (BINS / 32) * (BINS / 32); ++t) {
+    const int i0 = (t / (BINS / 32)) * 32, j0 = (t % (BINS / 32)) * 32;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int jj = ty; jj < 32; jj += 8)
+        tile[c * CH_STRIDE + jj * 33 + tx] = mine[c * (BINS * BINS) + (j0 + jj) * BINS + i0 + tx];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 96; idx += 256) {
+      const int ii = idx / 96, r = idx - ii * 96, jj = r / 3, c = r - jj * 3;
+      out[(int64_t)(i0 + ii) * (BINS * 3) + j0 * 3 + r] = tile[c * CH_STRIDE + jj * 33 + ii] * inv_d;
+    }
+    __syncthreads();
+  }
+}
+
+struct Plan { int splits; int64_t px_per_split; };
+
+// Pixel slices per image: whole images while they fill the SMs (>= 95 % of the last wave), else the smallest
+// number of slices (<= 16, each a multiple of the 1024-pixel chain) that does.
+static Plan plan(int64_t batch, int64_t npix, bool dedup) {
+  Plan pl{1, ceil_div(npix, SLOT_PX) * SLOT_PX};
+  if (dedup || batch == 0) return pl;
+  const int64_t sms = cached_sm_count();
+  const int64_t chain_px = (int64_t)CHAIN_KB * KB;
+  const int64_t max_s = npix / chain_px < 1 ? 1 : (npix / chain_px > 16 ? 16 : npix / chain_px);
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= max_s; ++s) {
+    const int64_t items = batch * s;
+    const double eff = (double)items / (double)(ceil_div(items, sms) * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    if (eff >= 0.95) break;
+  }
+  int64_t pps = ceil_div(ceil_div(npix, best), chain_px) * chain_px;
+  pl.splits = (int)ceil_div(npix, pps);  // every slice is non-empty
+  pl.px_per_split = pps;
+  return pl;
+}
+
+}  // namespace fwd256
+
+size_t tc_fwd256_workspace_bytes(int64_t batch, int64_t npix) {
+  // the dense plan needs the most partial buffers (de-duplicated images are one item each)
+  const fwd256::Plan pl = fwd256::plan(batch, npix, false);
+  return align_up((size_t)batch * pl.splits * fwd256::HIST_ELEMS * sizeof(float), 256);
+}
+
+int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int method,
+                      float sigma_sqr, float eps, const float4* ulist, const int* nunique, int dedup_max,
+                      float iy_scale, float* hist, float* denom, void* workspace, cudaStream_t st) {
+  using namespace fwd256;
+  PH_CHECK_ARG(npix < (1ll << 31), "too many pixels per image");
+  if (batch == 0) return PH_OK;
+  const Plan pl = plan(batch, npix, ulist != nullptr);
+  Params p{};
+  p.image = image;
+  p.dom = dom;
+  p.partial = static_cast<float*>(workspace);
+  p.ulist = ulist;
+  p.nunique = nunique;
+  p.dedup_max = dedup_max;
+  p.npix = npix;
+  p.channels = channels;
+  p.splits = pl.splits;
+  p.px_per_split = pl.px_per_split;
+  p.items = batch * pl.splits;
+  p.eps = eps;
+  const tcgen::WeightScales wsc = tcgen::weight_scales(method, sigma_sqr);
+  p.wa = wsc.wa;
+  p.wb = wsc.wb;
+  p.coord_scale = wsc.coord_scale;
+  p.iy_scale = iy_scale;
+  const float inv_scale = (float)(1.0 / (wsc.weight_scale * wsc.weight_scale * (double)iy_scale));
+  void (*kern)(Params) = method == PH_METHOD_INVERSE_QUADRATIC ? hist_fwd256_tc_kernel<PH_METHOD_INVERSE_QUADRATIC>
+                                                               : hist_fwd256_tc_kernel<PH_METHOD_RBF>;
+  const size_t smem = sizeof(Smem);
+  PH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = cached_sm_count();
+  if (grid > p.items) grid = (int)p.items;
+  kern<<<grid, THREADS, smem, st>>>(p);
+  PH_LAUNCH_OK("hist_fwd256_tc_kernel");
+  hist256_finalize_kernel<<<(unsigned)batch, 256, 0, st>>>(p.partial, pl.splits, inv_scale, hist, denom);
+  PH_LAUNCH_OK("hist256_finalize_kernel");
+  return PH_OK;
+}
+
+}  // namespace ph
