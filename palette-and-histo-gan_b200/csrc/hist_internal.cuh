@@ -45,6 +45,12 @@ size_t tc_fwd256_workspace_bytes(int64_t batch, int64_t npix);
 int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int method,
                       float sigma_sqr, float eps, const float4* ulist, const int* nunique, int dedup_max,
                       float iy_scale, float* hist, float* denom, void* workspace, cudaStream_t st);
+// hist_tc_bwd256.cu: dedicated 256-bin backward (128-pixel tile x whole 256 x 256 G^ of a channel per round)
+size_t tc_bwd256_workspace_bytes(int64_t batch);
+int tc_bwd256_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int method,
+                       float sigma_sqr, float eps, const float* hist_pred, const float* denom, const float* grad_hist,
+                       const float* hist_true, const double* ssum, int64_t global_batch, const float* loss_scale,
+                       float* grad_image, void* workspace, cudaStream_t st);
 int launch_hellinger_ssum_accumulate(const float* ht, const float* hp, int64_t n, double* ssum, cudaStream_t st);
 int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                      int bins, int method, float sigma_sqr, float eps, const float* hist_pred,

@@ -14,12 +14,12 @@
 //   6 instructions x 128 cycles per stage = the tensor pipe's full rate; the fp16 hi+lo split with three
 //   products carries ~22 significant bits, hist_tc.cu / DESIGN.md §5).
 //
-//   warps 0-7 generate the A side, 8-15 the B side (thread = one bin, 16 pixels per stage), warp 16 issues the
-//   MMAs, warps 17-19 are the pixel pass (128-bit loads, log-chroma u/v of the current channel and Iy into a
-//   shared-memory ring).  The three channels of an item run one after the other (the pixel pass re-reads the
+//   warps 0-7 generate the A side, 8-15 the B side (thread = two bins x 8 pixels per stage), warp 16 issues the
+//   MMAs, warps 17-23 are the pixel pass (128-bit loads, float64 log-chroma u/v of the current channel as hi + lo
+//   pairs and Iy into a shared-memory ring; seven warps because the float64 logs are a long dependent chain).  The three channels of an item run one after the other (the pixel pass re-reads the
 //   16 B pixel per channel: 3 MB per 256 x 256 image against 77 GFLOP).
 //
-//   Accuracy: as in the 64-bin kernel the accumulation chains are cut every 1024 pixels; the 16 producer warps
+//   Accuracy: as in the 64-bin kernel the accumulation chains are cut, here every 512 pixels; the 16 producer warps
 //   then drain the 64 K accumulators (tcgen05.ld) into the item's fp32 partial sums in global memory, laid out
 //   [channel][v-bin][u-bin] so that a warp's 32 TMEM lanes (consecutive u-bins) make one 128-byte access: plain
 //   stores for the first chain, fire-and-forget reductions (RED.ADD.F32) afterwards — every address is owned by
@@ -44,13 +44,13 @@ constexpr int BINS = 256;
 constexpr int KB = 16;         // pixels per stage = one K step of the instruction
 constexpr int SLOT_PX = 32;    // pixels per pixel-ring slot = two stages (lane = pixel in the pixel pass)
 constexpr int NS = 4;          // operand stages
-constexpr int CHAIN_KB = 64;   // stages per TMEM accumulation chain (1024 pixels)
-constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 3;
+constexpr int CHAIN_KB = 32;   // stages per TMEM accumulation chain (512 pixels = 96 accumulating MMAs per half)
+constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 7;  // 24 warps = 6 per scheduler at <= 80 registers
 constexpr int PROD_WARPS = A_WARPS + B_WARPS;
 constexpr int MMA_WARP = PROD_WARPS;            // 16
 constexpr int PX_WARP0 = MMA_WARP + 1;          // 17
-constexpr int PR = 4;                           // pixel ring slots
-constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 640
+constexpr int PR = 8;                           // pixel ring slots
+constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 768
 constexpr int TMEM_COLS = 512;
 // one operand part (hi or lo) of one side for one stage: 256 rows x 16 pixels of fp16, K-major, no swizzle:
 //   [kcol = pixel / 8 (2)][row / 8 (32)][row % 8][pixel % 8]     core matrix = 8 rows x 8 halfs = 128 B
@@ -60,7 +60,7 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // A_hi | A_lo | B_hi | B_lo
 constexpr int HIST_ELEMS = 3 * BINS * BINS;   // per item: [c][j][i]
 
 struct PxSlot {
-  float u[SLOT_PX], v[SLOT_PX], iy[SLOT_PX];
+  float u[SLOT_PX], v[SLOT_PX], ul[SLOT_PX], vl[SLOT_PX], iy[SLOT_PX];  // coordinates as hi + lo pairs
 };
 
 struct Smem {
@@ -153,18 +153,20 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
               r = __ldg(src); g = __ldg(src + 1); bl = __ldg(src + 2);
             }
           }
-          // histogram.py:58-66, :13-17, :72-74 — the same expressions as the 64-bin kernel
-          const float x0 = fmaf(r, 0.5f, 0.5f), x1 = fmaf(g, 0.5f, 0.5f), x2 = fmaf(bl, 0.5f, 0.5f);
-          const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
-          const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
-          float u, v;
-          if (c == 0) { u = logf(e0 / e1) * p.coord_scale; v = logf(e0 / e2) * p.coord_scale; }
-          else if (c == 1) { u = -(logf(e0 / e1) * p.coord_scale); v = logf(e1 / e2) * p.coord_scale; }
-          else { u = -(logf(e0 / e2) * p.coord_scale); v = -(logf(e1 / e2) * p.coord_scale); }
+          // histogram.py:58-66, :13-17, :72-74.  The log-chroma differences are taken in float64 and carried as
+          // float hi + lo pairs into every (u - c), as the backward kernels do (common.cuh): this kernel is bound by
+          // the tensor pipe, the pixel pass has the time, and the histogram lands 10x closer to the float64 oracle
+          // than with float32 logs (which also tightens the Hellinger derivative sqrt(Ht / Hp) of the backward)
+          const PixelTerms pt = pixel_terms(r, g, bl, p.eps);
+          float u, ul, v, vl;
+          channel_uv(pt, c, u, ul, v, vl);
+          const float iy = pt.iy, cs = p.coord_scale;  // power of two: exact for both parts
           mbar_wait_relaxed(&S.px_empty[slot], ((sit / PR) & 1) ^ 1, 400);
           PxSlot& o = S.px[slot];
-          o.u[lane] = u;
-          o.v[lane] = v;
+          o.u[lane] = u * cs;
+          o.v[lane] = v * cs;
+          o.ul[lane] = ul * cs;
+          o.vl[lane] = vl * cs;
           o.iy[lane] = valid ? iy * mult * p.iy_scale : 0.f;  // masked pixels contribute nothing (A operand = 0)
           mbar_arrive_warp(&S.px_full[slot]);
         }
@@ -172,12 +174,17 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
     }
   } else if (warp < PROD_WARPS) {
     // ===================== operand producers (A: warps 0-7, B: warps 8-15) + chain drain =====================
-    const int side = warp >> 3;  // warp-uniform
-    const int bin = tid & 255;
-    const float c_bin = S.dom[bin];
-    const f32x2 negc = pack2(-c_bin, -c_bin);
+    // thread = (side, 8-pixel core-matrix column kc of the stage, bins b and b + 128): the 8 coordinates it loads
+    // serve two bins (half the shared-memory loads of a one-bin-by-16-pixels mapping — this kernel runs close to the
+    // shared-memory bandwidth: the MMAs alone read 96 B per clock), rows b of a warp stay contiguous
+    const int side = warp >> 3;        // warp-uniform
+    const int kc = (warp >> 2) & 1;    // warp-uniform
+    const int bin0 = tid & 127;
+    const float c_b0 = S.dom[bin0], c_b1 = S.dom[bin0 + 128];
+    const f32x2 negc[2] = {pack2(-c_b0, -c_b0), pack2(-c_b1, -c_b1)};
     const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
-    const uint32_t row_off = (uint32_t)(side * 2 * TILE_BYTES + (bin >> 3) * 128 + (bin & 7) * 16);
+    // row of bin0 (bin0 + 128: 16 row groups = 2048 B further)
+    const uint32_t row_off = (uint32_t)(side * 2 * TILE_BYTES + kc * KCOL_BYTES + (bin0 >> 3) * 128 + (bin0 & 7) * 16);
     // drain role: TMEM sub-partition quad = warp % 4 (lanes 32 quad ..), column group cg = warp / 4: u-bin half
     // h = cg / 2 (accumulator D[h] = columns 256 h ..), v-bins j in [128 (cg % 2), +128)
     const int quad = warp & 3, cg = warp >> 2;
@@ -195,26 +202,29 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
           const int slot = sit % PR, stage = it % NS, half = it & 1;
           mbar_wait(&S.px_full[slot], (sit / PR) & 1);
           const PxSlot& in = S.px[slot];
-          const float* src = (side == 0 ? in.u : in.v) + half * KB;
-          ulonglong2 xx[4], iw[4];
+          const int px0 = half * KB + kc * 8;
+          const float* src = (side == 0 ? in.u : in.v) + px0;
+          const float* srl = (side == 0 ? in.ul : in.vl) + px0;
+          ulonglong2 xx[2], xl[2], iw[2];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xx[q] = *reinterpret_cast<const ulonglong2*>(src + 4 * q);
+          for (int q = 0; q < 2; ++q) {
+            xx[q] = *reinterpret_cast<const ulonglong2*>(src + 4 * q);
+            xl[q] = *reinterpret_cast<const ulonglong2*>(srl + 4 * q);
+          }
           if (side == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) iw[q] = *reinterpret_cast<const ulonglong2*>(&in.iy[half * KB + 4 * q]);
+            for (int q = 0; q < 2; ++q) iw[q] = *reinterpret_cast<const ulonglong2*>(&in.iy[px0 + 4 * q]);
           }
           if (half == 1) mbar_arrive_warp(&S.px_empty[slot]);
           uint4 hi[2], lo[2];
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            f32x2 w0 = weight2<METHOD>(xx[2 * q].x, negc, wa2, wb2);
-            f32x2 w1 = weight2<METHOD>(xx[2 * q].y, negc, wa2, wb2);
-            f32x2 w2 = weight2<METHOD>(xx[2 * q + 1].x, negc, wa2, wb2);
-            f32x2 w3 = weight2<METHOD>(xx[2 * q + 1].y, negc, wa2, wb2);
-            if (side == 0) {
-              w0 = mul2(w0, iw[2 * q].x); w1 = mul2(w1, iw[2 * q].y);
-              w2 = mul2(w2, iw[2 * q + 1].x); w3 = mul2(w3, iw[2 * q + 1].y);
-            }
+          for (int q = 0; q < 2; ++q) {  // the two bins
+            // d = (x_hi - c) + x_lo: the first sum is exact near the bin centre, where the weight is steep
+            f32x2 w0 = weight2<METHOD>(add2(xx[0].x, negc[q]), xl[0].x, wa2, wb2);
+            f32x2 w1 = weight2<METHOD>(add2(xx[0].y, negc[q]), xl[0].y, wa2, wb2);
+            f32x2 w2 = weight2<METHOD>(add2(xx[1].x, negc[q]), xl[1].x, wa2, wb2);
+            f32x2 w3 = weight2<METHOD>(add2(xx[1].y, negc[q]), xl[1].y, wa2, wb2);
+            if (side == 0) { w0 = mul2(w0, iw[0].x); w1 = mul2(w1, iw[0].y); w2 = mul2(w2, iw[1].x); w3 = mul2(w3, iw[1].y); }
             split_f16x2(w0, mone2, hi[q].x, lo[q].x);
             split_f16x2(w1, mone2, hi[q].y, lo[q].y);
             split_f16x2(w2, mone2, hi[q].z, lo[q].z);
@@ -223,9 +233,9 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
           mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this stage are done
           unsigned char* tile = &S.ab[stage][row_off];
           *reinterpret_cast<uint4*>(tile) = hi[0];
-          *reinterpret_cast<uint4*>(tile + KCOL_BYTES) = hi[1];
+          *reinterpret_cast<uint4*>(tile + 16 * 128) = hi[1];
           *reinterpret_cast<uint4*>(tile + TILE_BYTES) = lo[0];
-          *reinterpret_cast<uint4*>(tile + TILE_BYTES + KCOL_BYTES) = lo[1];
+          *reinterpret_cast<uint4*>(tile + TILE_BYTES + 16 * 128) = lo[1];
           fence_proxy_async_smem();
           mbar_arrive_warp(&S.ab_full[stage]);
 

@@ -31,6 +31,62 @@ __device__ __forceinline__ f32x2 weight2(f32x2 x, f32x2 negc, f32x2 wa2, f32x2 w
   }
 }
 
+// ---- backward: weight and derivative of two bins at once -----------------------------------------------
+// two bins at once (packed fp32x2): d = (x_hi - c) + x_lo
+template <int METHOD>
+__device__ __forceinline__ void weight_pair2(f32x2 x_hi, f32x2 x_lo, f32x2 c, f32x2 wa2, f32x2 wb2, f32x2 wc2, f32x2 mone2,
+                                             f32x2& k, f32x2& dk) {
+  const f32x2 d = add2(fma2(c, mone2, x_hi), x_lo);
+  if (METHOD == PH_METHOD_INVERSE_QUADRATIC) {
+    const f32x2 e = fma2(d, d, wb2);
+    // one MUFU.RCP per weight: here the issue slots are scarcer than the MUFU pipe (the shared-reciprocal form
+    // of the forward kernel, 1 MUFU + 3 FMUL per pair, measured 6 % slower)
+    k = pack2(fast_rcp(lo_of(e)), fast_rcp(hi_of(e)));
+    dk = mul2(mul2(d, k), k);
+  } else {
+    const f32x2 e = fma2(mul2(d, d), wa2, wb2);
+    k = pack2(fast_ex2(lo_of(e)), fast_ex2(hi_of(e)));
+    dk = mul2(mul2(d, wc2), k);
+  }
+}
+
+// Scales of the backward operands (Params of hist_tc_bwd.cu): k_s = S_k k, dk_s = S_dk dk' with dk' the derivative
+// without the common factor -2 / sigma^2; powers of two that keep the largest weight below fp16's 65504:
+//   IQ:  k <= 1, |dk'| = |d| k^2 <= 0.325 sigma;   RBF: k <= 1, |dk'| = |d| k <= 0.43 sigma
+struct BwdScales {
+  float wa, wb, wc, coord_scale, inv_sk2, inv_sk_sdk;
+};
+static inline BwdScales bwd_scales(int method, float sigma_sqr) {
+  BwdScales r;
+  const double sigma = sqrt((double)sigma_sqr), inv_s2 = 1.0 / (double)sigma_sqr;
+  double s_k, s_dk;
+  if (method == PH_METHOD_INVERSE_QUADRATIC) {
+    // s = the power of two nearest to 2^-5.25 / sigma: w = s^2 sigma^2 in [2^-11, 2^-10];  k_s = k / w <= 2^11,
+    // dk_s = s d k^2 / w^2 <= 0.325 w^-1.5 <= 30 100
+    const int kexp = (int)lrint(-5.25 - 0.5 * log2((double)sigma_sqr));
+    const double sc = ldexp(1.0, kexp);
+    r.coord_scale = (float)sc;
+    r.wa = 0.f;
+    r.wb = (float)(sc * sc * (double)sigma_sqr);
+    r.wc = 1.0f;
+    const double w = (double)r.wb;
+    s_k = 1.0 / w;
+    s_dk = sc / (w * w);
+  } else {
+    int e = (int)floor(log2(60000.0 / (0.43 * sigma)));
+    e = e > 60 ? 60 : (e < -60 ? -60 : e);
+    r.coord_scale = 1.0f;
+    s_k = 16384.0;
+    s_dk = ldexp(1.0, e);
+    r.wa = (float)(-inv_s2 * 1.4426950408889634);
+    r.wb = 14.0f;
+    r.wc = (float)(s_dk / s_k);
+  }
+  r.inv_sk2 = (float)(1.0 / (s_k * s_k));
+  r.inv_sk_sdk = (float)(-2.0 * inv_s2 / (s_k * s_dk));
+  return r;
+}
+
 // Scales of the generated operands (see Params of the kernels): the inverse-quadratic weight is produced as
 // K / w = 1 / (d d + w) with coordinates pre-multiplied by the power of two s, w = s^2 sigma^2 in [2^-14, 2^-13];
 // the RBF weight as 2^14 K = 2^(wa d d + 14).
