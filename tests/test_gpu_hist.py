@@ -393,8 +393,9 @@ def test_against_the_reference_source_run(H, cuda, reference_run, hist_golden, i
 
 @pytest.mark.parametrize("shape,bins", [((2, 16, 16, 4), 128), ((2, 24, 24, 3), 256), ((150, 16, 16, 4), 128)])
 def test_block_decomposed_tensor_core_path(H, cuda, shape, bins):
-    """bins = 128 / 256 (cfgE) on the tcgen05 engine: the histogram is assembled from 64 x 64 blocks (one
-    contraction launch per block, common normaliser) and the gradient is summed over the blocks of G^."""
+    """bins = 128 on the tcgen05 engine: the histogram is assembled from 64 x 64 blocks (one contraction launch per
+    block, common normaliser) and the gradient is summed over the blocks of G^; bins = 256 takes the dedicated
+    256-bin kernels (more cases below)."""
     rng = np.random.default_rng(41)
     real = np.tanh(rng.standard_normal(shape)).astype(np.float32)
     fake = np.tanh(rng.standard_normal(shape)).astype(np.float32)
@@ -418,3 +419,67 @@ def test_block_decomposed_tensor_core_path(H, cuda, shape, bins):
         assert ho.rel_l2(f.grad.cpu().numpy()[sub], f2.grad.cpu().numpy()[sub]) < GRAD_TOL
         assert ho.rel_l2(f.grad.cpu().numpy(), f2.grad.cpu().numpy()) < GRAD_TOL
     assert np.abs(f.grad.cpu().numpy()[..., 3:]).max() == 0.0 if shape[-1] == 4 else True
+
+
+def test_dedicated_256_bin_kernels_against_oracle(H, cuda):
+    """bins = 256 (cfgE) runs on dedicated tcgen05 kernels (hist_tc_fwd256.cu / hist_tc_bwd256.cu: the whole
+    256 x 256 histogram, resp. G^, of a channel per CTA).  Float64 oracle on small images: both methods, 3- and
+    4-channel pixels, pixel counts that are not multiples of the 16-pixel stage / the 128-pixel tile."""
+    rng = np.random.default_rng(256)
+    for shape, method, sigma in [((2, 24, 24, 4), "inverse-quadratic", 0.02), ((2, 20, 13, 3), "inverse-quadratic", 0.02),
+                                 ((1, 40, 40, 4), "inverse-quadratic", 0.05), ((2, 16, 16, 4), "RBF", 0.6)]:
+        real = np.tanh(rng.standard_normal(shape)).astype(np.float32)
+        fake = np.tanh(rng.standard_normal(shape)).astype(np.float32)
+        ref = ho.hist_loss_and_grad_f64(real, fake, size=256, method=method, sigma=sigma)
+        f = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+        loss = H.histogram_loss(torch.from_numpy(real).to(cuda), f, size=256, method=method, sigma=sigma, impl="tc")
+        loss.backward()
+        hist = H.calculate_rgbuv_histogram(torch.from_numpy(fake).to(cuda), size=256, method=method, sigma=sigma,
+                                           impl="tc").cpu().numpy()
+        assert hist.shape == (shape[0], 256, 256, 3)
+        assert ho.rel_l2(hist, ref["hist_fake"]) < HIST_TOL and ho.rel_max(hist, ref["hist_fake"]) < HIST_TOL, (shape, method)
+        assert abs(float(loss.detach()) - ref["loss"]) / ref["loss"] < LOSS_TOL
+        assert ho.rel_l2(f.grad.cpu().numpy(), ref["grad"]) < GRAD_TOL, (shape, method)
+        if shape[-1] == 4:
+            assert np.abs(f.grad.cpu().numpy()[..., 3]).max() == 0.0
+
+
+def test_dedicated_256_bin_kernels_batches_slices_and_sprites(H, cuda):
+    """The work-item plans of the 256-bin kernels against the CUDA-core engine: more images than SMs (whole images
+    per CTA, several tile ranges per image in the backward), a handful of large images (pixel slices in the forward,
+    partial sums added by the finalise kernel), palette sprites as the real side (de-duplicated forward), and an
+    upstream gradient on the histogram itself."""
+    g = torch.Generator(cuda).manual_seed(5)
+    rng = np.random.default_rng(6)
+    for shape in [(150, 16, 16, 4), (5, 96, 96, 4)]:
+        real = torch.tanh(torch.randn(shape, device=cuda, generator=g))
+        fake = torch.tanh(torch.randn(shape, device=cuda, generator=g))
+        out = {}
+        for impl in ("simt", "tc"):
+            f = fake.clone().requires_grad_(True)
+            loss = H.histogram_loss(real, f, size=256, impl=impl)
+            loss.backward()
+            out[impl] = (float(loss.detach()), f.grad.cpu().numpy(),
+                         H.calculate_rgbuv_histogram(fake, size=256, impl=impl).cpu().numpy())
+        assert abs(out["tc"][0] - out["simt"][0]) / out["simt"][0] < LOSS_TOL
+        assert ho.rel_l2(out["tc"][1], out["simt"][1]) < GRAD_TOL, shape
+        assert ho.rel_l2(out["tc"][2], out["simt"][2]) < HIST_TOL, shape
+        assert np.allclose(out["tc"][2].sum(axis=(1, 2, 3)), 1.0, atol=3e-6)
+    spr = torch.from_numpy(sprite_like_batch(rng, 6).astype(np.float32) / np.float32(127.5) - 1).to(cuda)
+    fake = torch.tanh(torch.randn(6, 64, 64, 4, device=cuda, generator=g))
+    res = {}
+    for impl, dedup in (("simt", False), ("tc", True), ("tc", False)):
+        f = fake.clone().requires_grad_(True)
+        loss = H.histogram_loss(spr, f, size=256, impl=impl, dedup_real=dedup)
+        loss.backward()
+        res[(impl, dedup)] = (float(loss.detach()), f.grad.cpu().numpy())
+    for key in (("tc", True), ("tc", False)):
+        assert abs(res[key][0] - res[("simt", False)][0]) / res[("simt", False)][0] < LOSS_TOL
+        assert ho.rel_l2(res[key][1], res[("simt", False)][1]) < GRAD_TOL
+    up = torch.randn(3, 256, 256, 3, device=cuda, generator=g) * 1e-3
+    grads = {}
+    for impl in ("simt", "tc"):
+        x = fake[:3].clone().requires_grad_(True)
+        H.calculate_rgbuv_histogram(x, size=256, impl=impl).backward(up)
+        grads[impl] = x.grad.cpu().numpy()
+    assert ho.rel_l2(grads["tc"], grads["simt"]) < GRAD_TOL
