@@ -20,10 +20,10 @@
 //   16 B pixel per channel: 3 MB per 256 x 256 image against 77 GFLOP).
 //
 //   Accuracy: as in the 64-bin kernel the accumulation chains are cut, here every 512 pixels; the 16 producer warps
-//   then drain the 64 K accumulators (tcgen05.ld) into the item's fp32 partial sums in global memory, laid out
-//   [channel][v-bin][u-bin] so that a warp's 32 TMEM lanes (consecutive u-bins) make one 128-byte access: plain
-//   stores for the first chain, fire-and-forget reductions (RED.ADD.F32) afterwards — every address is owned by
-//   one thread of one CTA, so the sums are deterministic.  `hist256_finalize_kernel` adds the slices of an image
+//   then drain the 64 K accumulators (tcgen05.ld) through a shared-memory staging buffer into the item's fp32
+//   partial sums in global memory ([channel][v-bin][u-bin]): a bulk copy for the first chain, bulk fp32 reductions
+//   (cp.reduce.async.bulk: the additions happen at the L2, asynchronously) afterwards — every address is owned by
+//   one CTA and the operations of successive chains are ordered, so the sums are deterministic.  `hist256_finalize_kernel` adds the slices of an image
 //   in order, computes the normaliser D (histogram.py:77-79) and writes H / D channel-last (B,256,256,3).
 #include <stdlib.h>
 
@@ -38,6 +38,7 @@ using namespace tc;
 
 namespace fwd256 {
 
+using tcgen::named_bar_sync;
 using tcgen::weight2;
 
 constexpr int BINS = 256;
@@ -63,8 +64,13 @@ struct PxSlot {
   float u[SLOT_PX], v[SLOT_PX], ul[SLOT_PX], vl[SLOT_PX], iy[SLOT_PX];  // coordinates as hi + lo pairs
 };
 
+constexpr int DRAIN_COLS = 32;                       // v-bins j per drain chunk: 32 rows of 256 u-bins = 32 KB
+constexpr int DRAIN_CHUNKS = BINS / DRAIN_COLS;      // 8
+constexpr int DRAIN_BYTES = DRAIN_COLS * BINS * 4;
+
 struct Smem {
   alignas(128) unsigned char ab[NS][STAGE_BYTES];  // 128 KB
+  alignas(128) float stage_out[2][DRAIN_COLS * BINS];  // 64 KB: chain drain staging [j][i], double-buffered
   PxSlot px[PR];
   float dom[BINS];
   alignas(8) uint64_t px_full[PR], px_empty[PR], ab_full[NS], ab_empty[NS], d_full, d_empty;
@@ -185,11 +191,11 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
     const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
     // row of bin0 (bin0 + 128: 16 row groups = 2048 B further)
     const uint32_t row_off = (uint32_t)(side * 2 * TILE_BYTES + kc * KCOL_BYTES + (bin0 >> 3) * 128 + (bin0 & 7) * 16);
-    // drain role: TMEM sub-partition quad = warp % 4 (lanes 32 quad ..), column group cg = warp / 4: u-bin half
-    // h = cg / 2 (accumulator D[h] = columns 256 h ..), v-bins j in [128 (cg % 2), +128)
+    // drain role: TMEM sub-partition quad = warp % 4 (lanes 32 quad ..), cg = warp / 4: u-bin half h = cg % 2
+    // (accumulator D[h] = columns 256 h ..), and within every 32-column chunk the columns 16 (cg / 2) .. + 15
     const int quad = warp & 3, cg = warp >> 2;
-    const int i_row = (cg >> 1) * 128 + quad * 32 + lane;
-    const int j0 = (cg & 1) * 128;
+    const int dh = cg & 1, jhalf = cg >> 1;
+    const int i_row = dh * 128 + quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t it = 0, chain = 0;
     for (int64_t w = first; w < p.items; w += step) {
@@ -241,33 +247,45 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
 
           const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
           if (!chain_end) continue;
-          // ---- chain drain: D (TMEM) -> the item's fp32 partial sums [c][j][i] in global memory ----
+          // ---- chain drain: D (TMEM) -> registers -> shared-memory staging [j][i] -> bulk copy (first chain) or
+          //      bulk fp32 reduction (later chains) into the item's partial sums [c][j][i] in global memory.  The TMA
+          //      engine performs the 64 K additions of a chain at the L2 while the SM is back at the MMAs (per-lane
+          //      REDs kept the 16 warps in the memory-pipeline throttle for ~9 us per chain: ncu lg_throttle).
           mbar_wait(&S.d_full, chain & 1);
           ++chain;
           tc_fence_after_sync();
           const bool first_chain = kb < CHAIN_KB;
-          float* dst = item_out + (int64_t)c * (BINS * BINS) + (int64_t)j0 * BINS + i_row;
+          float* dst = item_out + (int64_t)c * (BINS * BINS);
+          // every earlier bulk operation of this CTA has been performed (they were issued a whole chain ago): the
+          // additions to an address happen in chain order, so the sums are deterministic
+          if (tid == 0) bulk_wait_group<0>();
 #pragma unroll 1
-          for (int blk = 0; blk < 4; ++blk) {
-            uint32_t vals[32];
-            tmem_ld32(tmem + lane_addr + cg * 128 + blk * 32, vals);
+          for (int ch = 0; ch < DRAIN_CHUNKS; ++ch) {
+            uint32_t vals[16];
+            tmem_ld16(tmem + lane_addr + dh * 256 + ch * DRAIN_COLS + jhalf * 16, vals);
             tmem_ld_wait();
-            if (blk == 3) {
+            if (ch == DRAIN_CHUNKS - 1) {
               tc_fence_before_sync();
-              mbar_arrive_warp(&S.d_empty);  // everything of this chain is in registers: the next chain may start
+              mbar_arrive_warp(&S.d_empty);  // everything of this chain has left TMEM: the next chain may start
             }
-            float* d = dst + (int64_t)(blk * 32) * BINS;
-            if (first_chain) {
+            named_bar_sync(5, PROD_WARPS * 32);  // staging buffer ch % 2 is free (thread 0 waited for its last reader)
+            float* so = &S.stage_out[ch & 1][(jhalf * 16) * BINS + i_row];
 #pragma unroll
-              for (int k = 0; k < 32; ++k) d[k * BINS] = __uint_as_float(vals[k]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 32; ++k) atomicAdd(d + k * BINS, __uint_as_float(vals[k]));
+            for (int k = 0; k < 16; ++k) so[k * BINS] = __uint_as_float(vals[k]);
+            fence_proxy_async_smem();
+            named_bar_sync(5, PROD_WARPS * 32);  // the chunk is complete in shared memory
+            if (tid == 0) {
+              float* g = dst + (int64_t)ch * (DRAIN_COLS * BINS);
+              if (first_chain) bulk_store_s2g(g, &S.stage_out[ch & 1][0], DRAIN_BYTES);
+              else bulk_reduce_add_f32_s2g(g, &S.stage_out[ch & 1][0], DRAIN_BYTES);
+              bulk_commit_group();
+              bulk_wait_group_read<1>();  // the operation issued one chunk ago has read its buffer = the next one's
             }
           }
         }
       }
     }
+    if (tid == 0) bulk_wait_group<0>();
   } else if (warp == MMA_WARP) {
     // ===================== MMA issue: the whole warp runs the (uniform) loop, one elected lane issues ====
     constexpr uint32_t IDESC = idesc_f16(128, 256);
