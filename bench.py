@@ -377,7 +377,7 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_generator_step:
         generator_step = bench_generator_step(torch, dev, world, rank, distributed, barrier)
 
-    # ---- cfgE scale sweep: 256 x 256 images, 256 bins, global batch 1024 (block-decomposed tensor-core path) ----
+    # ---- cfgE scale sweep: 256 x 256 images, 256 bins, global batch 1024 (dedicated 256-bin tensor-core kernels) ----
     scale_sweep = None
     if not args.no_scale_sweep:
         scale_sweep = bench_scale_sweep(torch, dev, world, rank, distributed, barrier, peaks)
@@ -417,7 +417,8 @@ def run_ours(args, rank, world, local_rank):
 
 def bench_scale_sweep(torch, dev, world, rank, distributed, barrier, peaks):
     """cfgE (BASELINE.json config 5): histogram loss fwd+bwd at 256 x 256 pixels and 256 bins, global batch 1024 sharded
-    over the ranks.  The tensor-core engine assembles the 256 x 256 histogram from sixteen 64 x 64 blocks."""
+    over the ranks, on the dedicated 256-bin kernels (hist_tc_fwd256.cu / hist_tc_bwd256.cu: the tensor-pipe-bound
+    regime; PH_FWD256=0 PH_BWD256=0 select the block-decomposed path)."""
     import torch.distributed as dist
     from palette_and_histo_gan_b200 import histogram as H
 
@@ -453,10 +454,38 @@ def bench_scale_sweep(torch, dev, world, rank, distributed, barrier, peaks):
     if distributed:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     tflops = 24.0 * bins * bins * side * side * gb / (float(ms) * 1e-3) / 1e12
+    # per-phase breakdown of one step on this rank (CUDA events between the phases, as for cfgC)
+    dom = H.histogram_domain(bins, dev)
+    s2, impl_id = H._sigma_sqr(0.02), 0
+    fake_d = fake.detach()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    barrier()
+    ev[0].record()
+    hr, _ = H._forward(real, dom, 0, s2, impl_id | H.DEDUP_FLAG)
+    ev[1].record()
+    hf, df, ssum = H._forward_ssum(fake_d, dom, 0, s2, impl_id, hr)
+    ev[2].record()
+    gbs = H._reduce_over_ranks(ssum, hi - lo, group, gb)
+    H._finish(ssum, gbs)
+    ev[3].record()
+    H._backward(fake_d, dom, 0, s2, impl_id, hf, df, hist_true=hr, ssum=ssum, global_batch=gbs)
+    ev[4].record()
+    barrier()
+    ph = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+    unit = float(bins) * bins * side * side * (hi - lo) / 1e12   # S^2 N B in units of 1e12
+    fwd_tf, bwd_tf = 6.0 * unit / (ph[1] * 1e-3), 12.0 * unit / (ph[3] * 1e-3)
+    peak = peaks["bf16_tflops_sustained"]
     out = {"workload": "cfgE: histogram loss fwd+bwd, 256x256 RGBA, 256 bins, global batch 1024",
            "images_per_s": gb / (float(ms) * 1e-3), "ms_per_step": float(ms), "per_gpu_batch": hi - lo,
            "algorithmic_tflops": tflops, "frac_of_f16_peak": tflops / (peaks["bf16_tflops_sustained"] * world),
-           "loss": float(loss.detach())}
+           "loss": float(loss.detach()),
+           "phase_ms": {"fwd_real(dedup)": ph[0], "fwd_fake+hellinger_sum": ph[1], "allreduce+loss": ph[2], "bwd": ph[3]},
+           "roofline": {"bound": "tensor", "kernel": "hist_bwd256_tc_kernel (+ prologue)", "achieved": bwd_tf, "peak": peak,
+                        "unit": "TFLOP/s", "frac": bwd_tf / peak, "frac_of_emulation_ceiling": 3.0 * bwd_tf / peak,
+                        "forward": {"kernel": "hist_fwd256_tc_kernel (+ finalise, Hellinger sum)", "achieved": fwd_tf,
+                                    "frac": fwd_tf / peak, "frac_of_emulation_ceiling": 3.0 * fwd_tf / peak},
+                        "note": "rank 0's shard; three fp16 products per fp32 product, so the emulation ceiling is peak / 3; "
+                                "ncu (profiles/r1_prof_hist256_raw.csv): tensor pipe active 70 % (backward), 59 % (forward)"}}
     del fake, real
     torch.cuda.empty_cache()
     return out
