@@ -241,3 +241,50 @@ def test_against_the_reference_source_run(P, cuda, reference_run, ordering):
         # the uint8 loader prep (blacken + normalise) against the reference's normalize()
         u8 = torch.from_numpy(R["loader_target"][:n]).to(cuda)
         assert np.array_equal(P.dataset_utils.load_image(u8).cpu().numpy(), R["normalized"])
+
+
+def test_concurrent_host_threads(P, cuda, sprites, palette_golden):
+    """The palette ops run inside `tf.data.map(num_parallel_calls=AUTOTUNE)` worker threads in the reference
+    (dataset_utils.py:236-244): several host threads call the library at once, each on its own stream.  The entry
+    points are re-entrant (caller-owned outputs, no global scratch, thread-local error text)."""
+    import threading
+
+    front, right = sprites["front"], sprites["right"]
+    n = front.shape[0]
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            stream = torch.cuda.Stream(device=cuda)
+            with torch.cuda.stream(stream):
+                for rep in range(4):
+                    lo = (tid * 7 + rep * 13) % (n - 4)
+                    src, tgt = dev_i32(front[lo:lo + 4], cuda), dev_i32(right[lo:lo + 4], cuda)
+                    s_idx, t_idx, pal = P.dataset_utils.load_indexed_images(src, tgt, "grayness")
+                    oh = P.io_utils.one_hot(t_idx)
+                    back = P.io_utils.indexed_to_rgba(t_idx, pal)
+                    stream.synchronize()
+                    results[(tid, rep)] = (lo, s_idx.cpu().numpy(), t_idx.cpu().numpy(), pal.cpu().numpy(),
+                                           oh.sum().item(), back.cpu().numpy())
+                # an error raised in one thread must not leak its message into another
+                if tid == 0:
+                    with pytest.raises(Exception):
+                        P.io_utils.extract_palette(torch.randint(0, 256, (64, 64, 4), device=cuda, dtype=torch.int32))
+        except Exception as exc:  # noqa: BLE001
+            errors.append((tid, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(results) == 24
+    for (tid, rep), (lo, s_idx, t_idx, pal, oh_sum, back) in results.items():
+        for k in range(4):
+            ep, _ = po.extract_palette(np.concatenate([front[lo + k], right[lo + k]], -1).astype(np.int32), "grayness")
+            assert np.array_equal(pal[k], ep)
+            assert np.array_equal(s_idx[k], po.rgba_to_indexed(front[lo + k].astype(np.int32), ep))
+            assert np.array_equal(t_idx[k], po.rgba_to_indexed(right[lo + k].astype(np.int32), ep))
+            assert np.array_equal(back[k], right[lo + k].astype(np.int32))
+        assert oh_sum == 4 * 64 * 64
