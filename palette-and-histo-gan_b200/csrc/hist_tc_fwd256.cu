@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
             }
           }
           // histogram.py:58-66, :13-17, :72-74.  The log-chroma differences are taken in float64 and carried as
-          // float hi + lo pairs into every (u - c), as the backward kernels do (common.cuh): this kernel is bound by
-          // the tensor pipe, the pixel pass has the time, and the histogram lands 10x closer to the float64 oracle
-          // than with float32 logs (which also tightens the Hellinger derivative sqrt(Ht / Hp) of the backward)
+          // float hi + lo pairs into every (u - c), as the backward kernels do (common.cuh): seven pixel warps have
+          // the time for it, one more packed add per weight pair in the producers, and the 256-bin gradients land
+          // 2e-6 closer to the float64 oracle (the forward's histogram error feeds sqrt(Ht / Hp) of the backward)
           const PixelTerms pt = pixel_terms(r, g, bl, p.eps);
           float u, ul, v, vl;
           channel_uv(pt, c, u, ul, v, vl);
@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
           if (!chain_end) continue;
           // ---- chain drain: D (TMEM) -> registers -> shared-memory staging [j][i] -> bulk copy (first chain) or
           //      bulk fp32 reduction (later chains) into the item's partial sums [c][j][i] in global memory.  The TMA
-          //      engine performs the 64 K additions of a chain at the L2 while the SM is back at the MMAs (per-lane
-          //      REDs kept the 16 warps in the memory-pipeline throttle for ~9 us per chain: ncu lg_throttle).
+          //      engine performs the 64 K additions of a chain at the L2 while the SM is back at the MMAs (with per-lane
+          //      REDs the 16 warps sat in the memory-pipeline throttle: ncu lg_throttle 1.1 per issue, now 0).
           mbar_wait(&S.d_full, chain & 1);
           ++chain;
           tc_fence_after_sync();
