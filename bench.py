@@ -605,12 +605,24 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
     # e2e through the host API (pinned int32 images in; indices, palettes and one-hot out)
     src_h, tgt_h = torch.from_numpy(src_np).pin_memory(), torch.from_numpy(tgt_np).pin_memory()
     ctx = hostapi.HostContext(dev.index)
-    hostapi.load_indexed_images(src_h, tgt_h, "grayness", ctx=ctx)
+    # caller-owned, page-locked result buffers (as a loader that recycles its batches would hold them)
+    outs = (torch.empty((PALETTE_BATCH, HW, HW, 1), dtype=torch.int32).pin_memory(),
+            torch.empty((PALETTE_BATCH, HW, HW, 1), dtype=torch.int32).pin_memory(),
+            torch.empty((PALETTE_BATCH, 256, 4), dtype=torch.int32).pin_memory())
+    hostapi.load_indexed_images(src_h, tgt_h, "grayness", out=outs, ctx=ctx)
     t0 = time.perf_counter()
     reps = 5
     for _ in range(reps):
-        hostapi.load_indexed_images(src_h, tgt_h, "grayness", ctx=ctx)
+        hostapi.load_indexed_images(src_h, tgt_h, "grayness", out=outs, ctx=ctx)
     e2e_s = (time.perf_counter() - t0) / reps
+    # the same call with the images as the decoded PNG's uint8 (a quarter of the upload)
+    src_h8 = torch.from_numpy(src_np.astype(np.uint8)).pin_memory()
+    tgt_h8 = torch.from_numpy(tgt_np.astype(np.uint8)).pin_memory()
+    hostapi.load_indexed_images(src_h8, tgt_h8, "grayness", out=outs, ctx=ctx)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        hostapi.load_indexed_images(src_h8, tgt_h8, "grayness", out=outs, ctx=ctx)
+    e2e_u8_s = (time.perf_counter() - t0) / reps
     ctx.close()
     return {
         "metric": "palette-index Gpix/s", "unit": "Gpix/s",
@@ -634,7 +646,9 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
                                        "note": "36 B/px, one fused launch of 256 CTAs (one per pair) over ~2 Mpix: latency bound"}},
         "e2e": {"value": npx / e2e_s / 1e9, "unit": "Gpix/s", "h2d_bytes_per_step": int(2 * src_np.nbytes),
                 "d2h_bytes_per_step": int(npx * 4 + PALETTE_BATCH * (256 * 16 + 4)),
-                "api": "hostapi.load_indexed_images -> ph_host_load_indexed_images (no one-hot download)"},
+                "api": "hostapi.load_indexed_images(out=pinned buffers) -> ph_host_load_indexed_images (no one-hot download)",
+                "uint8_input": {"value": npx / e2e_u8_s / 1e9, "h2d_bytes_per_step": int(2 * src_np.size),
+                                "api": "ph_host_load_indexed_images_u8: decoded PNG bytes in, widened on the device"}},
         "l2": "256 MiB flush write between timed iterations",
     }
 

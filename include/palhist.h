@@ -244,6 +244,13 @@ PH_API int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_h
                                 int32_t* target_indexed_host, int32_t* palette_host,
                                 int32_t* ncolors_host, float* target_one_hot_host);
 
+/* Same with the images as the decoded PNG's uint8 RGBA (dataset_utils.py:66-70 `decode_png` before the casts of
+ * :72 and :140-141): a quarter of the upload; widened to int32 on the device, outputs identical. */
+PH_API int ph_host_load_indexed_images_u8(ph_host_ctx* ctx, const uint8_t* source_host, const uint8_t* target_host,
+                                   int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
+                                   int32_t* target_indexed_host, int32_t* palette_host,
+                                   int32_t* ncolors_host, float* target_one_hot_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,7 @@ int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, co
                            cudaStream_t st);
 int launch_u8_to_float_image(const uint8_t* src, int64_t npixels, int blacken, int normalize, float* dst,
                              cudaStream_t st);
+int launch_u8_to_i32_image(const uint8_t* src, int64_t npixels, int32_t* dst, cudaStream_t st);
 int launch_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, cudaStream_t st);
 int launch_augment_pair(const float* first, const float* second, int64_t batch, int height, int width,
                         const float* hue_delta, const float* translation, const uint8_t* apply, int normalize,

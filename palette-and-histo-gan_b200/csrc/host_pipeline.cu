@@ -350,10 +350,14 @@ int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const float* fak
   return ph_host_hist_finish(ctx, ssum, batch, loss_host, grad_fake_host, nullptr);
 }
 
-int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,
-                                int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
-                                int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
-                                float* target_one_hot_host) {
+}  // extern "C"
+
+// source / target as int32 (elem_bytes 4) or as the decoded PNG's uint8 (elem_bytes 1: a quarter of the upload,
+// widened to int32 on the device)
+static int host_load_indexed(ph_host_ctx* ctx, const void* source_host, const void* target_host, int elem_bytes,
+                             int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
+                             int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
+                             float* target_one_hot_host) {
   PH_CHECK_ARG(ctx && source_host && target_host && source_indexed_host && target_indexed_host && palette_host &&
                    ncolors_host,
                "NULL pointer argument");
@@ -365,6 +369,8 @@ int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, co
     Carver cv(pass == 0 ? nullptr : ctx->arena);
     int32_t* d_src = cv.take<int32_t>(img);
     int32_t* d_tgt = cv.take<int32_t>(img);
+    uint8_t* d_src8 = elem_bytes == 1 ? cv.take<uint8_t>(img) : nullptr;
+    uint8_t* d_tgt8 = elem_bytes == 1 ? cv.take<uint8_t>(img) : nullptr;
     int32_t* d_sidx = cv.take<int32_t>((size_t)batch * npix);
     int32_t* d_tidx = cv.take<int32_t>((size_t)batch * npix);
     int32_t* d_pal = cv.take<int32_t>((size_t)batch * depth * 4);
@@ -376,9 +382,18 @@ int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, co
       continue;
     }
     cudaStream_t st = ctx->s_compute;
-    PH_CUDA_OK(cudaMemcpyAsync(d_src, source_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    PH_CUDA_OK(cudaMemcpyAsync(d_tgt, target_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    int rc = ph_load_indexed_images(d_src, d_tgt, batch, npix, ordering, d_sidx, d_tidx, d_pal, d_nc, st);
+    int rc;
+    if (elem_bytes == 1) {
+      PH_CUDA_OK(cudaMemcpyAsync(d_src8, source_host, img, cudaMemcpyHostToDevice, st));
+      PH_CUDA_OK(cudaMemcpyAsync(d_tgt8, target_host, img, cudaMemcpyHostToDevice, st));
+      rc = launch_u8_to_i32_image(d_src8, (int64_t)batch * npix, d_src, st);
+      if (rc == PH_OK) rc = launch_u8_to_i32_image(d_tgt8, (int64_t)batch * npix, d_tgt, st);
+      if (rc != PH_OK) return rc;
+    } else {
+      PH_CUDA_OK(cudaMemcpyAsync(d_src, source_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      PH_CUDA_OK(cudaMemcpyAsync(d_tgt, target_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    rc = ph_load_indexed_images(d_src, d_tgt, batch, npix, ordering, d_sidx, d_tidx, d_pal, d_nc, st);
     if (rc != PH_OK) return rc;
     if (d_oh) {
       rc = ph_one_hot(d_tidx, batch * npix, depth, d_oh, st);
@@ -393,6 +408,24 @@ int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, co
     PH_CUDA_OK(cudaStreamSynchronize(st));
   }
   return PH_OK;
+}
+
+extern "C" {
+
+int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,
+                                int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
+                                int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
+                                float* target_one_hot_host) {
+  return host_load_indexed(ctx, source_host, target_host, 4, batch, npix, ordering, source_indexed_host,
+                           target_indexed_host, palette_host, ncolors_host, target_one_hot_host);
+}
+
+int ph_host_load_indexed_images_u8(ph_host_ctx* ctx, const uint8_t* source_host, const uint8_t* target_host,
+                                   int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
+                                   int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
+                                   float* target_one_hot_host) {
+  return host_load_indexed(ctx, source_host, target_host, 1, batch, npix, ordering, source_indexed_host,
+                           target_indexed_host, palette_host, ncolors_host, target_one_hot_host);
 }
 
 }  // extern "C"

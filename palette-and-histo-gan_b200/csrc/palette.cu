@@ -459,6 +459,28 @@ __global__ void __launch_bounds__(256) u8_to_float_image_kernel(const uchar4* __
   }
 }
 
+// decoded PNG pixels (uint8 RGBA) -> the int32 pixels the palette kernels read (`tf.cast(image, "int32")`,
+// dataset_utils.py:140-141): lets a host caller upload 4 B per pixel instead of 16
+__global__ void __launch_bounds__(256) u8_to_i32_image_kernel(const uchar4* __restrict__ src, int64_t npixels,
+                                                              int4* __restrict__ dst) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npixels; i += stride) {
+    const uchar4 q = __ldg(src + i);
+    dst[i] = make_int4(q.x, q.y, q.z, q.w);
+  }
+}
+
+int launch_u8_to_i32_image(const uint8_t* src, int64_t npixels, int32_t* dst, cudaStream_t st) {
+  if (npixels == 0) return PH_OK;
+  int64_t grid = ceil_div(npixels, 256 * 4);
+  const int64_t cap = (int64_t)cached_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  u8_to_i32_image_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const uchar4*>(src), npixels,
+                                                         reinterpret_cast<int4*>(dst));
+  PH_LAUNCH_OK("u8_to_i32_image_kernel");
+  return PH_OK;
+}
+
 int launch_u8_to_float_image(const uint8_t* src, int64_t npixels, int blacken, int normalize, float* dst,
                              cudaStream_t st) {
   if (npixels == 0) return PH_OK;

@@ -128,26 +128,41 @@ def histogram_loss_finish(ssum_global: float, global_batch: int, out_grad=None, 
 
 
 def load_indexed_images(source_image, target_image, palette_ordering="grayness", *, with_one_hot=False,
-                        ctx=None, device=0):
-    """dataset_utils.py:138-151 for host images (B,H,W,4) int32 (values 0..255).
-    Returns (source_indexed, target_indexed, palette[, target_one_hot]) as numpy arrays."""
+                        out=None, ctx=None, device=0):
+    """dataset_utils.py:138-151 for host images (B,H,W,4), int32 (values 0..255) or uint8 (the decoded PNG as it
+    is: a quarter of the upload, widened on the device).  Returns (source_indexed, target_indexed, palette
+    [, target_one_hot]) as numpy arrays.  `out=(source_indexed, target_indexed, palette)`: caller-owned int32 result
+    buffers of shapes (B,H,W,1), (B,H,W,1), (B,256,4) — numpy arrays or pinned CPU torch tensors (page-locked
+    results download at PCIe speed; fresh pageable arrays take a staged copy)."""
     from .io_utils import PaletteOverflowError, _ordering_id
     from .configuration import MAX_PALETTE_SIZE
 
     if palette_ordering == "shuffled":
         raise ValueError("'shuffled' is nondeterministic; use the tensor API (dataset_utils.load_indexed_images)")
-    src = _np(source_image, np.int32, "source_image")
-    tgt = _np(target_image, np.int32, "target_image")
+    def _is_u8(x):
+        return str(getattr(x, "dtype", "")).endswith("uint8")  # numpy or (pinned) CPU torch tensor
+
+    as_u8 = _is_u8(source_image) and _is_u8(target_image)
+    dt = np.uint8 if as_u8 else np.int32
+    src = _np(source_image, dt, "source_image")
+    tgt = _np(target_image, dt, "target_image")
     if src.shape != tgt.shape or src.ndim != 4 or src.shape[-1] != 4:
         raise ValueError("source_image and target_image must both be (B,H,W,4)")
     b, h, w, _ = src.shape
-    s_idx = np.empty((b, h, w, 1), np.int32)
-    t_idx = np.empty((b, h, w, 1), np.int32)
-    pal = np.empty((b, MAX_PALETTE_SIZE, 4), np.int32)
+    if out is not None:
+        s_idx, t_idx, pal = (_np(o, np.int32, "out") for o in out)
+        if s_idx.shape != (b, h, w, 1) or t_idx.shape != (b, h, w, 1) or pal.shape != (b, MAX_PALETTE_SIZE, 4):
+            raise ValueError("out buffers must have shapes (B,H,W,1), (B,H,W,1), (B,256,4)")
+        if not (s_idx.flags.writeable and t_idx.flags.writeable and pal.flags.writeable):
+            raise ValueError("out buffers must be writeable")
+    else:
+        s_idx = np.empty((b, h, w, 1), np.int32)
+        t_idx = np.empty((b, h, w, 1), np.int32)
+        pal = np.empty((b, MAX_PALETTE_SIZE, 4), np.int32)
     nc = np.empty((b,), np.int32)
     oh = np.empty((b, h, w, MAX_PALETTE_SIZE), np.float32) if with_one_hot else None
     ctx = ctx or default_context(device)
-    _lib.call("ph_host_load_indexed_images", ctx._h, src.ctypes.data, tgt.ctypes.data, b, h * w,
+    _lib.call("ph_host_load_indexed_images_u8" if as_u8 else "ph_host_load_indexed_images", ctx._h, src.ctypes.data, tgt.ctypes.data, b, h * w,
               _ordering_id(palette_ordering), s_idx.ctypes.data, t_idx.ctypes.data, pal.ctypes.data,
               nc.ctypes.data, oh.ctypes.data if oh is not None else None)
     if (nc == _lib.PALETTE_BAD_VALUE).any():

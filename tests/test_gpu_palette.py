@@ -169,6 +169,23 @@ def test_host_api_matches_device_api(P, cuda, sprites):
         es, et, ep = po.load_indexed_images(s[i], t[i], "grayness")
         assert np.array_equal(hs[i], es) and np.array_equal(ht[i], et) and np.array_equal(hp[i], ep)
         assert np.array_equal(oh[i], po.one_hot(et))
+    # the decoded PNG as it is (uint8): a quarter of the upload, identical outputs; numpy or pinned torch tensors
+    s8, t8 = sprites["front"][:8].astype(np.uint8), sprites["right"][:8].astype(np.uint8)
+    us, ut, up = P.hostapi.load_indexed_images(s8, t8, "grayness")
+    assert np.array_equal(us, hs) and np.array_equal(ut, ht) and np.array_equal(up, hp)
+    us, ut, up = P.hostapi.load_indexed_images(torch.from_numpy(s8).pin_memory(), torch.from_numpy(t8).pin_memory(), "top2bottom")
+    es, et, ep = po.load_indexed_images(s[3], t[3], "top2bottom")
+    assert np.array_equal(us[3], es) and np.array_equal(ut[3], et) and np.array_equal(up[3], ep)
+    with pytest.raises(TypeError):
+        P.hostapi.load_indexed_images(s8, t, "grayness")
+    # caller-owned (pinned) result buffers
+    outs = (torch.empty((8, 64, 64, 1), dtype=torch.int32).pin_memory(), torch.empty((8, 64, 64, 1), dtype=torch.int32).pin_memory(),
+            torch.empty((8, 256, 4), dtype=torch.int32).pin_memory())
+    rs, rt, rp = P.hostapi.load_indexed_images(s8, t8, "grayness", out=outs)
+    assert np.array_equal(outs[0].numpy(), hs) and np.array_equal(outs[1].numpy(), ht) and np.array_equal(outs[2].numpy(), hp)
+    assert np.shares_memory(rs, outs[0].numpy())
+    with pytest.raises(ValueError):
+        P.hostapi.load_indexed_images(s8, t8, "grayness", out=(outs[0], outs[1], torch.empty((8, 255, 4), dtype=torch.int32)))
 
 
 def test_fused_loader_filler_colour_and_batching(P, cuda):
