@@ -8,13 +8,13 @@
 // two M=128 halves x 256 TMEM columns = all 512 columns of the SM's tensor memory, and every generated weight
 // is used against 256 others (512 algorithmic FLOP per weight instead of 128).
 //
-//   per 16-pixel stage and channel:  A_hi, A_lo (256 u-bins x 16 pixels, Iy-weighted), B_hi, B_lo (256 v-bins x 16)
-//   as fp16 K-major no-swizzle tiles in shared memory (32 KB per stage, 4 stages); the MMA warp issues, per half
-//   h of the u-bins, D[h] += A_hi[h].B_hi + A_hi[h].B_lo + A_lo[h].B_hi  (tcgen05.mma kind::f16, SS, M128 N256 K16:
-//   6 instructions x 128 cycles per stage = the tensor pipe's full rate; the fp16 hi+lo split with three
+//   per 32-pixel stage and channel:  A_hi, A_lo (256 u-bins x 32 pixels, Iy-weighted), B_hi, B_lo (256 v-bins x 32)
+//   as fp16 K-major no-swizzle tiles in shared memory (64 KB per stage, 2 stages); the MMA warp issues, per K step
+//   of 16 pixels and half h of the u-bins, D[h] += A_hi[h].B_hi + A_hi[h].B_lo + A_lo[h].B_hi  (tcgen05.mma
+//   kind::f16, SS, M128 N256 K16: 12 instructions x 128 cycles per stage = the tensor pipe's full rate; the fp16 hi+lo split with three
 //   products carries ~22 significant bits, hist_tc.cu / DESIGN.md §5).
 //
-//   warps 0-7 generate the A side, 8-15 the B side (thread = two bins x 8 pixels per stage), warp 16 issues the
+//   warps 0-7 generate the A side, 8-15 the B side (thread = four bins x 8 pixels per stage), warp 16 issues the
 //   MMAs, warps 17-23 are the pixel pass (128-bit loads, float64 log-chroma u/v of the current channel as hi + lo
 //   pairs and Iy into a shared-memory ring; seven warps because the float64 logs are a long dependent chain).  The three channels of an item run one after the other (the pixel pass re-reads the
 //   16 B pixel per channel: 3 MB per 256 x 256 image against 77 GFLOP).
@@ -42,10 +42,12 @@ using tcgen::named_bar_sync;
 using tcgen::weight2;
 
 constexpr int BINS = 256;
-constexpr int KB = 16;         // pixels per stage = one K step of the instruction
-constexpr int SLOT_PX = 32;    // pixels per pixel-ring slot = two stages (lane = pixel in the pixel pass)
-constexpr int NS = 4;          // operand stages
-constexpr int CHAIN_KB = 32;   // stages per TMEM accumulation chain (512 pixels = 96 accumulating MMAs per half)
+constexpr int KB = 32;         // pixels per stage = two K steps of the instruction (= one pixel-ring slot): the
+                               // per-stage overhead of a producer warp (barrier waits / arrivals, proxy fence, address
+                               // arithmetic, ~110 of its instructions) is paid once per 32 weights of a thread
+constexpr int SLOT_PX = KB;
+constexpr int NS = 2;          // operand stages (64 KB each)
+constexpr int CHAIN_KB = 16;   // stages per TMEM accumulation chain (512 pixels = 96 accumulating MMAs per half)
 constexpr int A_WARPS = 8, B_WARPS = 8, PXW = 7;  // 24 warps = 6 per scheduler at <= 80 registers
 constexpr int PROD_WARPS = A_WARPS + B_WARPS;
 constexpr int MMA_WARP = PROD_WARPS;            // 16
@@ -53,11 +55,11 @@ constexpr int PX_WARP0 = MMA_WARP + 1;          // 17
 constexpr int PR = 8;                           // pixel ring slots
 constexpr int THREADS = (PX_WARP0 + PXW) * 32;  // 768
 constexpr int TMEM_COLS = 512;
-// one operand part (hi or lo) of one side for one stage: 256 rows x 16 pixels of fp16, K-major, no swizzle:
-//   [kcol = pixel / 8 (2)][row / 8 (32)][row % 8][pixel % 8]     core matrix = 8 rows x 8 halfs = 128 B
-constexpr int KCOL_BYTES = 32 * 128;          // 4096: LBO, the two core-matrix columns along K
-constexpr int TILE_BYTES = 2 * KCOL_BYTES;    // 8192
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // A_hi | A_lo | B_hi | B_lo
+// one operand part (hi or lo) of one side for one stage: 256 rows x 32 pixels of fp16, K-major, no swizzle:
+//   [kcol = pixel / 8 (4)][row / 8 (32)][row % 8][pixel % 8]     core matrix = 8 rows x 8 halfs = 128 B
+constexpr int KCOL_BYTES = 32 * 128;          // 4096: LBO, the distance of the two core-matrix columns of a K step
+constexpr int TILE_BYTES = 4 * KCOL_BYTES;    // 16384
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // A_hi | A_lo | B_hi | B_lo = 65536
 constexpr int HIST_ELEMS = 3 * BINS * BINS;   // per item: [c][j][i]
 
 struct PxSlot {
@@ -180,16 +182,18 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
     }
   } else if (warp < PROD_WARPS) {
     // ===================== operand producers (A: warps 0-7, B: warps 8-15) + chain drain =====================
-    // thread = (side, 8-pixel core-matrix column kc of the stage, bins b and b + 128): the 8 coordinates it loads
-    // serve two bins (half the shared-memory loads of a one-bin-by-16-pixels mapping — this kernel runs close to the
-    // shared-memory bandwidth: the MMAs alone read 96 B per clock), rows b of a warp stay contiguous
+    // thread = (side, 8-pixel core-matrix column kc of the stage, bins b, b + 64, b + 128, b + 192): the 8 coordinates
+    // it loads serve four bins — ncu shows this kernel at 94 % of the shared-memory bandwidth (the MMAs alone read 96 B
+    // per clock), so every broadcast load that is not issued counts; rows b of a warp stay contiguous (conflict-free
+    // 16-byte stores)
     const int side = warp >> 3;        // warp-uniform
-    const int kc = (warp >> 2) & 1;    // warp-uniform
-    const int bin0 = tid & 127;
-    const float c_b0 = S.dom[bin0], c_b1 = S.dom[bin0 + 128];
-    const f32x2 negc[2] = {pack2(-c_b0, -c_b0), pack2(-c_b1, -c_b1)};
+    const int kc = (warp >> 1) & 3;    // warp-uniform: pixels [8 kc, 8 kc + 8) of the stage
+    const int bin0 = tid & 63;
+    f32x2 negc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float cb = S.dom[bin0 + 64 * q]; negc[q] = pack2(-cb, -cb); }
     const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
-    // row of bin0 (bin0 + 128: 16 row groups = 2048 B further)
+    // row of bin0 in core-matrix column kc (bin0 + 64 q: 8 q row groups = 1024 q bytes further)
     const uint32_t row_off = (uint32_t)(side * 2 * TILE_BYTES + kc * KCOL_BYTES + (bin0 >> 3) * 128 + (bin0 & 7) * 16);
     // drain role: TMEM sub-partition quad = warp % 4 (lanes 32 quad ..), cg = warp / 4: u-bin half h = cg % 2
     // (accumulator D[h] = columns 256 h ..), and within every 32-column chunk the columns 16 (cg / 2) .. + 15
@@ -200,17 +204,15 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
     uint32_t it = 0, chain = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const ItemRange ir = item_range(p, w);
-      const uint32_t nkb = 2 * ((ir.px1 - ir.px0 + SLOT_PX - 1) / SLOT_PX);  // even: a slot is two stages
+      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) / KB;
       float* item_out = p.partial + w * (int64_t)HIST_ELEMS;
       for (int c = 0; c < 3; ++c) {
         for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t sit = it >> 1;
-          const int slot = sit % PR, stage = it % NS, half = it & 1;
-          mbar_wait(&S.px_full[slot], (sit / PR) & 1);
+          const int slot = it % PR, stage = it % NS;
+          mbar_wait(&S.px_full[slot], (it / PR) & 1);
           const PxSlot& in = S.px[slot];
-          const int px0 = half * KB + kc * 8;
-          const float* src = (side == 0 ? in.u : in.v) + px0;
-          const float* srl = (side == 0 ? in.ul : in.vl) + px0;
+          const float* src = (side == 0 ? in.u : in.v) + 8 * kc;
+          const float* srl = (side == 0 ? in.ul : in.vl) + 8 * kc;
           ulonglong2 xx[2], xl[2], iw[2];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
@@ -219,29 +221,27 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
           }
           if (side == 0) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) iw[q] = *reinterpret_cast<const ulonglong2*>(&in.iy[px0 + 4 * q]);
+            for (int q = 0; q < 2; ++q) iw[q] = *reinterpret_cast<const ulonglong2*>(&in.iy[8 * kc + 4 * q]);
           }
-          if (half == 1) mbar_arrive_warp(&S.px_empty[slot]);
-          uint4 hi[2], lo[2];
+          mbar_arrive_warp(&S.px_empty[slot]);
+          mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this stage are done
+          unsigned char* tile = &S.ab[stage][row_off];
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {  // the two bins
+          for (int q = 0; q < 4; ++q) {    // the four bins
             // d = (x_hi - c) + x_lo: the first sum is exact near the bin centre, where the weight is steep
             f32x2 w0 = weight2<METHOD>(add2(xx[0].x, negc[q]), xl[0].x, wa2, wb2);
             f32x2 w1 = weight2<METHOD>(add2(xx[0].y, negc[q]), xl[0].y, wa2, wb2);
             f32x2 w2 = weight2<METHOD>(add2(xx[1].x, negc[q]), xl[1].x, wa2, wb2);
             f32x2 w3 = weight2<METHOD>(add2(xx[1].y, negc[q]), xl[1].y, wa2, wb2);
             if (side == 0) { w0 = mul2(w0, iw[0].x); w1 = mul2(w1, iw[0].y); w2 = mul2(w2, iw[1].x); w3 = mul2(w3, iw[1].y); }
-            split_f16x2(w0, mone2, hi[q].x, lo[q].x);
-            split_f16x2(w1, mone2, hi[q].y, lo[q].y);
-            split_f16x2(w2, mone2, hi[q].z, lo[q].z);
-            split_f16x2(w3, mone2, hi[q].w, lo[q].w);
+            uint4 hi, lo;
+            split_f16x2(w0, mone2, hi.x, lo.x);
+            split_f16x2(w1, mone2, hi.y, lo.y);
+            split_f16x2(w2, mone2, hi.z, lo.z);
+            split_f16x2(w3, mone2, hi.w, lo.w);
+            *reinterpret_cast<uint4*>(tile + q * (8 * 128)) = hi;
+            *reinterpret_cast<uint4*>(tile + TILE_BYTES + q * (8 * 128)) = lo;
           }
-          mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this stage are done
-          unsigned char* tile = &S.ab[stage][row_off];
-          *reinterpret_cast<uint4*>(tile) = hi[0];
-          *reinterpret_cast<uint4*>(tile + 16 * 128) = hi[1];
-          *reinterpret_cast<uint4*>(tile + TILE_BYTES) = lo[0];
-          *reinterpret_cast<uint4*>(tile + TILE_BYTES + 16 * 128) = lo[1];
           fence_proxy_async_smem();
           mbar_arrive_warp(&S.ab_full[stage]);
 
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
     uint32_t stage = 0, phase = 0, chain_par = 0;
     for (int64_t w = first; w < p.items; w += step) {
       const ItemRange ir = item_range(p, w);
-      const uint32_t nkb = 2 * ((ir.px1 - ir.px0 + SLOT_PX - 1) / SLOT_PX);
+      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) / KB;
       for (int c = 0; c < 3; ++c) {
         for (uint32_t kb0 = 0; kb0 < nkb; kb0 += CHAIN_KB) {
           const uint32_t n_this = min((uint32_t)CHAIN_KB, nkb - kb0);
@@ -303,16 +303,19 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
             mbar_wait(&S.ab_full[stage], phase);
             tc_fence_after_sync();
             const uint32_t dstage = dlo0 + stage * (STAGE_BYTES >> 4);
-            const uint32_t b_hi = dstage + ((2 * TILE_BYTES) >> 4), b_lo = dstage + ((3 * TILE_BYTES) >> 4);
-            const uint32_t acc0 = (k == 0) ? 0u : 1u;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              // rows 128 h .. of the A tiles: 16 row groups x 128 B further
-              const uint32_t a_hi = dstage + ((h * 16 * 128) >> 4), a_lo = a_hi + (TILE_BYTES >> 4);
-              if (elect_one_sync()) {
-                mma_f16_ss2(tm + h * 256, a_hi, b_hi, dhi, IDESC, acc0);
-                mma_f16_ss2(tm + h * 256, a_hi, b_lo, dhi, IDESC, 1u);
-                mma_f16_ss2(tm + h * 256, a_lo, b_hi, dhi, IDESC, 1u);
+            for (int ks = 0; ks < KB / 16; ++ks) {
+              const uint32_t b_hi = dstage + ((2 * TILE_BYTES + ks * 2 * KCOL_BYTES) >> 4), b_lo = b_hi + (TILE_BYTES >> 4);
+              const uint32_t acc0 = (k == 0 && ks == 0) ? 0u : 1u;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                // rows 128 h .. of the A tiles: 16 row groups x 128 B further
+                const uint32_t a_hi = dstage + ((ks * 2 * KCOL_BYTES + h * 16 * 128) >> 4), a_lo = a_hi + (TILE_BYTES >> 4);
+                if (elect_one_sync()) {
+                  mma_f16_ss2(tm + h * 256, a_hi, b_hi, dhi, IDESC, acc0);
+                  mma_f16_ss2(tm + h * 256, a_hi, b_lo, dhi, IDESC, 1u);
+                  mma_f16_ss2(tm + h * 256, a_lo, b_hi, dhi, IDESC, 1u);
+                }
               }
             }
             if (elect_one_sync()) mma_commit(&S.ab_empty[stage]);
