@@ -96,6 +96,22 @@ def test_host_argument_validation(pkg):
         pkg._tensor.from_any([1, 2, 3])
     with pytest.raises(ValueError):
         pkg.io_utils.extract_palette(torch.zeros((4, 4, 3), dtype=torch.int32), "grayness", channels=3)
+    # host API: dtype / shape errors are raised before any device call
+    img8 = np.zeros((2, 8, 8, 4), np.uint8)
+    with pytest.raises(TypeError):
+        pkg.hostapi.load_indexed_images(img8, img8.astype(np.int32))
+    with pytest.raises(ValueError):
+        pkg.hostapi.load_indexed_images(img8, img8, out=(np.zeros((2, 8, 8, 1), np.int32), np.zeros((2, 8, 8, 1), np.int32),
+                                                         np.zeros((2, 255, 4), np.int32)))
+    with pytest.raises(ValueError):
+        pkg.hostapi.load_indexed_images(img8, img8, "shuffled")
+    # augmentation: CPU tensors and out-of-range hue shifts are refused
+    d = pkg.dataset_utils
+    with pytest.raises(ValueError):
+        d.augment_two(torch.zeros(8, 8, 4), torch.zeros(8, 8, 4))
+    assert d.HEIGHT_FACTOR == (-0.15, 0.075) and d.WIDTH_FACTOR == (-0.125, 0.125) and d.MAX_HUE_DELTA == 0.5
+    t = d._draw_translations(64, 64, 64, torch.Generator().manual_seed(0))
+    assert t.shape == (64, 2) and float(t[:, 0].abs().max()) <= 8.0 and float(t[:, 1].min()) >= -9.6001
 
 
 def test_linspace_matches_oracle(pkg):
