@@ -485,7 +485,7 @@ def bench_scale_sweep(torch, dev, world, rank, distributed, barrier, peaks):
                         "forward": {"kernel": "hist_fwd256_tc_kernel (+ finalise, Hellinger sum)", "achieved": fwd_tf,
                                     "frac": fwd_tf / peak, "frac_of_emulation_ceiling": 3.0 * fwd_tf / peak},
                         "note": "rank 0's shard; three fp16 products per fp32 product, so the emulation ceiling is peak / 3; "
-                                "ncu (profiles/r1_prof_hist256_raw.csv): tensor pipe active 70 % (backward), 59 % (forward)"}}
+                                "ncu (profiles/r1_prof_hist256_raw.csv): tensor pipe active 70 % (backward), 62 % (forward)"}}
     del fake, real
     torch.cuda.empty_cache()
     return out
