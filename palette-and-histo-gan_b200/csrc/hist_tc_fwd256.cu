@@ -202,6 +202,43 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
     const int i_row = dh * 128 + quad * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t it = 0, chain = 0;
+    // ---- chain drain: D (TMEM) -> registers -> shared-memory staging [j][i] -> bulk copy (first chain) or bulk fp32
+    //      reduction (later chains) into the item's partial sums [c][j][i] in global memory.  The TMA engine performs
+    //      the 64 K additions of a chain at the L2 while the SM is back at the MMAs (with per-lane REDs the 16 warps
+    //      sat in the memory-pipeline throttle: ncu lg_throttle 1.1 per issue, now 0).
+    auto drain = [&](float* dst, bool first_chain) {
+      mbar_wait(&S.d_full, chain & 1);
+      ++chain;
+      tc_fence_after_sync();
+      // every earlier bulk operation of this CTA has been performed (they were issued a whole chain ago): the
+      // additions to an address happen in chain order, so the sums are deterministic
+      if (tid == 0) bulk_wait_group<0>();
+#pragma unroll 1
+      for (int ch = 0; ch < DRAIN_CHUNKS; ++ch) {
+        uint32_t vals[16];
+        tmem_ld16(tmem + lane_addr + dh * 256 + ch * DRAIN_COLS + jhalf * 16, vals);
+        tmem_ld_wait();
+        if (ch == DRAIN_CHUNKS - 1) {
+          tc_fence_before_sync();
+          mbar_arrive_warp(&S.d_empty);  // everything of this chain has left TMEM: the next chain may start
+        }
+        named_bar_sync(5, PROD_WARPS * 32);  // staging buffer ch % 2 is free (thread 0 waited for its last reader)
+        float* so = &S.stage_out[ch & 1][(jhalf * 16) * BINS + i_row];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) so[k * BINS] = __uint_as_float(vals[k]);
+        fence_proxy_async_smem();
+        named_bar_sync(5, PROD_WARPS * 32);  // the chunk is complete in shared memory
+        if (tid == 0) {
+          float* g = dst + (int64_t)ch * (DRAIN_COLS * BINS);
+          if (first_chain) bulk_store_s2g(g, &S.stage_out[ch & 1][0], DRAIN_BYTES);
+          else bulk_reduce_add_f32_s2g(g, &S.stage_out[ch & 1][0], DRAIN_BYTES);
+          bulk_commit_group();
+          bulk_wait_group_read<1>();  // the operation issued one chunk ago has read its buffer = the next one's
+        }
+      }
+    };
+    float* pend_dst = nullptr;  // accumulators of a finished chain still to be drained
+    bool pend_first = false;
     for (int64_t w = first; w < p.items; w += step) {
       const ItemRange ir = item_range(p, w);
       const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) / KB;
@@ -245,46 +282,18 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
           fence_proxy_async_smem();
           mbar_arrive_warp(&S.ab_full[stage]);
 
-          const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
-          if (!chain_end) continue;
-          // ---- chain drain: D (TMEM) -> registers -> shared-memory staging [j][i] -> bulk copy (first chain) or
-          //      bulk fp32 reduction (later chains) into the item's partial sums [c][j][i] in global memory.  The TMA
-          //      engine performs the 64 K additions of a chain at the L2 while the SM is back at the MMAs (with per-lane
-          //      REDs the 16 warps sat in the memory-pipeline throttle: ncu lg_throttle 1.1 per issue, now 0).
-          mbar_wait(&S.d_full, chain & 1);
-          ++chain;
-          tc_fence_after_sync();
-          const bool first_chain = kb < CHAIN_KB;
-          float* dst = item_out + (int64_t)c * (BINS * BINS);
-          // every earlier bulk operation of this CTA has been performed (they were issued a whole chain ago): the
-          // additions to an address happen in chain order, so the sums are deterministic
-          if (tid == 0) bulk_wait_group<0>();
-#pragma unroll 1
-          for (int ch = 0; ch < DRAIN_CHUNKS; ++ch) {
-            uint32_t vals[16];
-            tmem_ld16(tmem + lane_addr + dh * 256 + ch * DRAIN_COLS + jhalf * 16, vals);
-            tmem_ld_wait();
-            if (ch == DRAIN_CHUNKS - 1) {
-              tc_fence_before_sync();
-              mbar_arrive_warp(&S.d_empty);  // everything of this chain has left TMEM: the next chain may start
-            }
-            named_bar_sync(5, PROD_WARPS * 32);  // staging buffer ch % 2 is free (thread 0 waited for its last reader)
-            float* so = &S.stage_out[ch & 1][(jhalf * 16) * BINS + i_row];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) so[k * BINS] = __uint_as_float(vals[k]);
-            fence_proxy_async_smem();
-            named_bar_sync(5, PROD_WARPS * 32);  // the chunk is complete in shared memory
-            if (tid == 0) {
-              float* g = dst + (int64_t)ch * (DRAIN_COLS * BINS);
-              if (first_chain) bulk_store_s2g(g, &S.stage_out[ch & 1][0], DRAIN_BYTES);
-              else bulk_reduce_add_f32_s2g(g, &S.stage_out[ch & 1][0], DRAIN_BYTES);
-              bulk_commit_group();
-              bulk_wait_group_read<1>();  // the operation issued one chunk ago has read its buffer = the next one's
-            }
+          // A chain that ended with the PREVIOUS stage is drained now, after this stage has been generated: when the
+          // MMA warp gets the accumulators back it finds the first stage of the next chain ready instead of waiting
+          // for the producers to refill the pipeline.
+          if (pend_dst != nullptr) { drain(pend_dst, pend_first); pend_dst = nullptr; }
+          if (((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb)) {
+            pend_dst = item_out + (int64_t)c * (BINS * BINS);
+            pend_first = kb < CHAIN_KB;
           }
         }
       }
     }
+    if (pend_dst != nullptr) drain(pend_dst, pend_first);
     if (tid == 0) bulk_wait_group<0>();
   } else if (warp == MMA_WARP) {
     // ===================== MMA issue: the whole warp runs the (uniform) loop, one elected lane issues ====
