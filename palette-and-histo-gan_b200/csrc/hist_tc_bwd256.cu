@@ -186,6 +186,35 @@ __global__ void __launch_bounds__(THREADS, 1) hist_bwd256_tc_kernel(Params p) {
     const uint32_t a_row = (uint32_t)(kcol * A_KCOL_BYTES + pl * 16);  // [pixel / 8][pixel % 8] rows are 16 B apart
     const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), wc2 = pack2(p.wc, p.wc), mone2 = pack2(-1.0f, -1.0f);
     uint32_t nround = 0, tt = 0;  // (tile, channel) rounds = d_full phases; tiles = pixel-ring phases
+    // A rows [Kv_hi | Kv_lo | dKv_hi | dKv_lo] of this thread's pixel for K-step k (bins j = 16 k + 8 kcol .. + 7) of
+    // round `round`, from the pixel's v coordinate (hi + lo)
+    auto gen_kstep = [&](int k, uint32_t round, f32x2 vh2, f32x2 vl2) {
+      const uint32_t ks = round * KSTEPS + k;  // global K-step: stage ks % NSA, phase ks / NSA
+      const uint32_t sa = ks % NSA;
+      uint4 kh, kl, dh4, dl4;
+      {
+        const float* cj = &S.dom[k * 16 + kcol * 8];
+        const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(cj);
+        const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(cj + 4);
+        f32x2 kk, dk;
+        weight_pair2<METHOD>(vh2, vl2, c0.x, wa2, wb2, wc2, mone2, kk, dk);
+        split_f16x2(kk, mone2, kh.x, kl.x); split_f16x2(dk, mone2, dh4.x, dl4.x);
+        weight_pair2<METHOD>(vh2, vl2, c0.y, wa2, wb2, wc2, mone2, kk, dk);
+        split_f16x2(kk, mone2, kh.y, kl.y); split_f16x2(dk, mone2, dh4.y, dl4.y);
+        weight_pair2<METHOD>(vh2, vl2, c1.x, wa2, wb2, wc2, mone2, kk, dk);
+        split_f16x2(kk, mone2, kh.z, kl.z); split_f16x2(dk, mone2, dh4.z, dl4.z);
+        weight_pair2<METHOD>(vh2, vl2, c1.y, wa2, wb2, wc2, mone2, kk, dk);
+        split_f16x2(kk, mone2, kh.w, kl.w); split_f16x2(dk, mone2, dh4.w, dl4.w);
+      }
+      mbar_wait(&S.a_empty[sa], ((ks / NSA) & 1) ^ 1);  // the MMAs that read this stage are done
+      unsigned char* row = &S.a[sa][a_row];
+      *reinterpret_cast<uint4*>(row) = kh;
+      *reinterpret_cast<uint4*>(row + A_PART_BYTES) = kl;
+      *reinterpret_cast<uint4*>(row + 2 * A_PART_BYTES) = dh4;
+      *reinterpret_cast<uint4*>(row + 3 * A_PART_BYTES) = dl4;
+      fence_proxy_async_smem();
+      mbar_arrive_warp(&S.a_full[sa]);
+    };
     for (int64_t w = first; w < items; w += step) {
       const int64_t b = w / p.bsplit;
       const int64_t t_begin = (w % p.bsplit) * p.tiles_per_item;
@@ -211,33 +240,14 @@ __global__ void __launch_bounds__(THREADS, 1) hist_bwd256_tc_kernel(Params p) {
           const float v_lo = c == 0 ? dl[1] : (c == 1 ? dl[2] : -dl[2]);
           const f32x2 uh2 = pack2(u_hi, u_hi), ul2 = pack2(u_lo, u_lo), vh2 = pack2(v_hi, v_hi), vl2 = pack2(v_lo, v_lo);
           // ---- A rows of this pixel for the K-steps of this thread's parity ----
+          // (the first one was generated before the previous round's epilogue when that round was of the same tile)
 #pragma unroll 1
-          for (int k = gpar; k < KSTEPS; k += 2) {
-            const uint32_t ks = nround * KSTEPS + k;  // global K-step: stage ks % NSA, phase ks / NSA
-            const uint32_t sa = ks % NSA;
-            uint4 kh, kl, dh4, dl4;
-            {
-              const float* cj = &S.dom[k * 16 + kcol * 8];
-              const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(cj);
-              const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(cj + 4);
-              f32x2 kk, dk;
-              weight_pair2<METHOD>(vh2, vl2, c0.x, wa2, wb2, wc2, mone2, kk, dk);
-              split_f16x2(kk, mone2, kh.x, kl.x); split_f16x2(dk, mone2, dh4.x, dl4.x);
-              weight_pair2<METHOD>(vh2, vl2, c0.y, wa2, wb2, wc2, mone2, kk, dk);
-              split_f16x2(kk, mone2, kh.y, kl.y); split_f16x2(dk, mone2, dh4.y, dl4.y);
-              weight_pair2<METHOD>(vh2, vl2, c1.x, wa2, wb2, wc2, mone2, kk, dk);
-              split_f16x2(kk, mone2, kh.z, kl.z); split_f16x2(dk, mone2, dh4.z, dl4.z);
-              weight_pair2<METHOD>(vh2, vl2, c1.y, wa2, wb2, wc2, mone2, kk, dk);
-              split_f16x2(kk, mone2, kh.w, kl.w); split_f16x2(dk, mone2, dh4.w, dl4.w);
-            }
-            mbar_wait(&S.a_empty[sa], ((ks / NSA) & 1) ^ 1);  // the MMAs that read this stage are done
-            unsigned char* row = &S.a[sa][a_row];
-            *reinterpret_cast<uint4*>(row) = kh;
-            *reinterpret_cast<uint4*>(row + A_PART_BYTES) = kl;
-            *reinterpret_cast<uint4*>(row + 2 * A_PART_BYTES) = dh4;
-            *reinterpret_cast<uint4*>(row + 3 * A_PART_BYTES) = dl4;
-            fence_proxy_async_smem();
-            mbar_arrive_warp(&S.a_full[sa]);
+          for (int k = gpar + (c > 0 ? 2 : 0); k < KSTEPS; k += 2) gen_kstep(k, nround, vh2, vl2);
+          if (c < 2) {
+            // first K-step of the NEXT channel's round, before this round's epilogue: when the MMA warp gets the
+            // accumulators back it finds K-steps 0 and 1 ready instead of waiting for the producers to restart
+            const float nv_hi = c == 0 ? dh[2] : -dh[2], nv_lo = c == 0 ? dl[2] : -dl[2];
+            gen_kstep(gpar, nround + 1, pack2(nv_hi, nv_hi), pack2(nv_lo, nv_lo));
           }
           // ---- epilogue of the round: dot products of P, P' (own lane) with the u-side weights of 64 bins ----
           // the weights of the first 16 bins are evaluated before waiting for the accumulators
