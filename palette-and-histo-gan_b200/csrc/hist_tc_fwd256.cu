@@ -88,7 +88,7 @@ struct Params {
   int dedup_max;
   int64_t npix;
   int channels;
-  int splits;            // pixel slices per image (1 when de-duplicated)
+  int splits;            // pixel slices per image (a de-duplicated image uses slice 0 only)
   int64_t px_per_split;  // multiple of SLOT_PX
   int64_t items;         // B * splits
   float eps;
@@ -109,7 +109,8 @@ __device__ __forceinline__ ItemRange item_range(const Params& p, int64_t w) {
   r.dedup = false;
   if (p.nunique != nullptr) {
     const int nu = __shfl_sync(0xffffffffu, __ldg(p.nunique + r.b), 0);
-    if (nu >= 0) { r.px0 = 0; r.px1 = (uint32_t)nu; r.dedup = true; }
+    // a de-duplicated image is one short list: slice 0 contracts it, the other slices of the image stay empty
+    if (nu >= 0) { r.px0 = 0; r.px1 = split == 0 ? (uint32_t)nu : 0u; r.dedup = true; }
   }
   return r;
 }
@@ -348,13 +349,14 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
 // (histogram.py:75-79).  One CTA per image: pass 1 adds the slices in order into slice 0 and reduces D, pass 2
 // transposes 32 x 32 (i, j) tiles through shared memory so that both sides are coalesced.
 __global__ void __launch_bounds__(256) hist256_finalize_kernel(float* __restrict__ partial, int splits,
-                                                               float inv_scale, float* __restrict__ hist,
-                                                               float* __restrict__ denom) {
+                                                               const int* __restrict__ nunique, float inv_scale,
+                                                               float* __restrict__ hist, float* __restrict__ denom) {
   constexpr int CH_STRIDE = 32 * 33 + 11;  // channel planes land on different banks
   __shared__ double scratch[32];
   __shared__ float tile[3 * CH_STRIDE];
   const int64_t b = blockIdx.x;
   float* mine = partial + b * splits * (int64_t)HIST_ELEMS;
+  if (nunique != nullptr && nunique[b] >= 0) splits = 1;  // de-duplicated image: only slice 0 was written
   double acc = 0.0;
   for (int e = threadIdx.x * 4; e < HIST_ELEMS; e += 256 * 4) {
     float4 v = *reinterpret_cast<const float4*>(mine + e);
@@ -391,9 +393,9 @@ struct Plan { int splits; int64_t px_per_split; };
 
 // Pixel slices per image: whole images while they fill the SMs (>= 95 % of the last wave), else the smallest
 // number of slices (<= 16, each a multiple of the 1024-pixel chain) that does.
-static Plan plan(int64_t batch, int64_t npix, bool dedup) {
+static Plan plan(int64_t batch, int64_t npix) {
   Plan pl{1, ceil_div(npix, SLOT_PX) * SLOT_PX};
-  if (dedup || batch == 0) return pl;
+  if (batch == 0) return pl;
   const int64_t sms = cached_sm_count();
   const int64_t chain_px = (int64_t)CHAIN_KB * KB;
   const int64_t max_s = npix / chain_px < 1 ? 1 : (npix / chain_px > 16 ? 16 : npix / chain_px);
@@ -414,8 +416,7 @@ static Plan plan(int64_t batch, int64_t npix, bool dedup) {
 }  // namespace fwd256
 
 size_t tc_fwd256_workspace_bytes(int64_t batch, int64_t npix) {
-  // the dense plan needs the most partial buffers (de-duplicated images are one item each)
-  const fwd256::Plan pl = fwd256::plan(batch, npix, false);
+  const fwd256::Plan pl = fwd256::plan(batch, npix);
   return align_up((size_t)batch * pl.splits * fwd256::HIST_ELEMS * sizeof(float), 256);
 }
 
@@ -425,7 +426,9 @@ int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int chann
   using namespace fwd256;
   PH_CHECK_ARG(npix < (1ll << 31), "too many pixels per image");
   if (batch == 0) return PH_OK;
-  const Plan pl = plan(batch, npix, ulist != nullptr);
+  // one plan for dense and de-duplicated batches: whether an image de-duplicates is known on the device only
+  // (more than 512 colours -> dense), so a de-duplicated image simply leaves its slices > 0 empty
+  const Plan pl = plan(batch, npix);
   Params p{};
   p.image = image;
   p.dom = dom;
@@ -453,7 +456,7 @@ int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int chann
   if (grid > p.items) grid = (int)p.items;
   kern<<<grid, THREADS, smem, st>>>(p);
   PH_LAUNCH_OK("hist_fwd256_tc_kernel");
-  hist256_finalize_kernel<<<(unsigned)batch, 256, 0, st>>>(p.partial, pl.splits, inv_scale, hist, denom);
+  hist256_finalize_kernel<<<(unsigned)batch, 256, 0, st>>>(p.partial, pl.splits, nunique, inv_scale, hist, denom);
   PH_LAUNCH_OK("hist256_finalize_kernel");
   return PH_OK;
 }
