@@ -308,7 +308,6 @@ int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_bat
   PH_CUDA_OK(cudaSetDevice(ctx->device));
   ctx->job_valid = false;
   const ph_host_ctx::Job& J = ctx->job;
-  const size_t hist_elems = (size_t)J.bins * J.bins * 3;
   PH_CUDA_OK(cudaMemcpyAsync(J.d_ssum, &ssum_global, sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
   int rc = ph_hellinger_finish(J.d_ssum, global_batch, J.d_loss, ctx->s_compute);
   if (rc != PH_OK) return rc;
