@@ -85,6 +85,12 @@ PH_API void ph_reset_launch_count(void);
 /* sm_count / compute capability of `device`; PH_ERR_CUDA without a usable GPU. */
 PH_API int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
+/* Host-only query (no device needed): how the dedicated 256-bin kernels cut a batch into work
+ * items on this device's SM count.  plan4 = { forward: pixel slices per image, pixels per slice (a multiple of the
+ * 512-pixel accumulation chain); backward: items (tile ranges) per image, 128-pixel tiles per item }.  The slices /
+ * items cover every pixel exactly once and none is empty (tests/test_abi.py). */
+PH_API int ph_hist256_plan(int64_t batch, int64_t npix, int64_t* plan4);
+
 /* ------------------------------------------------------------------------------------------
  * RGB-uv histogram  (histogram.py:36-81 `calculate_rgbuv_histogram`)
  * ------------------------------------------------------------------------------------------

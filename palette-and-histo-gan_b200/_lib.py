@@ -41,6 +41,7 @@ PROTOTYPES = {
     "ph_launch_count": (_i64, []),
     "ph_reset_launch_count": (None, []),
     "ph_device_info": (_int, [_int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
+    "ph_hist256_plan": (_int, [_i64, _i64, C.POINTER(_i64)]),
     "ph_hist_workspace_bytes": (_sz, [_i64, _i64, _int, _int]),
     "ph_hist_forward": (_int, [_p, _i64, _i64, _int, _p, _int, _int, _f, _f, _p, _p, _p, _sz, _int, _p]),
     "ph_hist_forward_ssum": (_int, [_p, _i64, _i64, _int, _p, _int, _int, _f, _f, _p, _p, _p, _p, _int, _p, _sz, _int,

@@ -76,6 +76,16 @@ int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
   return PH_OK;
 }
 
+int ph_hist256_plan(int64_t batch, int64_t npix, int64_t* plan4) {
+  PH_CHECK_ARG(plan4 != nullptr && batch >= 1 && npix >= 1 && npix < (1ll << 31), "bad argument");
+  int slices = 1, items = 1, tpi = 1;
+  int64_t pps = 0;
+  tc_fwd256_plan(batch, npix, &slices, &pps);
+  tc_bwd256_plan(batch, npix, &items, &tpi);
+  plan4[0] = slices; plan4[1] = pps; plan4[2] = items; plan4[3] = tpi;
+  return PH_OK;
+}
+
 size_t ph_hist_workspace_bytes(int64_t batch, int64_t npix, int bins, int impl) {
   if (batch <= 0 || npix <= 0 || bins <= 0) return 256;
   size_t s = simt_workspace_bytes(batch, npix, bins);

@@ -42,11 +42,13 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
                     void* workspace, bool dedup, const float* hist_true, double* ssum, cudaStream_t st);
 // hist_tc_fwd256.cu: dedicated 256-bin forward (whole 256 x 256 histogram of a channel in one CTA's tensor memory)
 size_t tc_fwd256_workspace_bytes(int64_t batch, int64_t npix);
+void tc_fwd256_plan(int64_t batch, int64_t npix, int* slices_per_image, int64_t* px_per_slice);  // host-only work plan
 int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int method,
                       float sigma_sqr, float eps, const float4* ulist, const int* nunique, int dedup_max,
                       float iy_scale, float* hist, float* denom, void* workspace, cudaStream_t st);
 // hist_tc_bwd256.cu: dedicated 256-bin backward (128-pixel tile x whole 256 x 256 G^ of a channel per round)
 size_t tc_bwd256_workspace_bytes(int64_t batch);
+void tc_bwd256_plan(int64_t batch, int64_t npix, int* items_per_image, int* tiles_per_item);  // host-only work plan
 int tc_bwd256_backward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int method,
                        float sigma_sqr, float eps, const float* hist_pred, const float* denom, const float* grad_hist,
                        const float* hist_true, const double* ssum, int64_t global_batch, const float* loss_scale,

@@ -439,6 +439,29 @@ __global__ void __launch_bounds__(256) ghat_absmax256_kernel(const float* __rest
 
 }  // namespace bwd256
 
+// Items per image (tile ranges): the split that minimises (waves of items) x (item size) — with at least sms / 32
+// items per image, so that the CTAs of a wave stream the G^ of at most ~32 images (24 MB) and find it in L2: at one
+// image per CTA the 148 streams (114 MB) evict each other and every K-step comes from HBM (measured 1.6x slower).
+void tc_bwd256_plan(int64_t batch, int64_t npix, int* items_per_image, int* tiles_per_item) {
+  const int64_t sms = cached_sm_count();
+  const int64_t tiles = ceil_div(npix, bwd256::TILE);
+  int64_t smin = ceil_div(sms, 32);
+  if (smin > tiles) smin = tiles;
+  int best = (int)smin;
+  double best_cost = 1e30;
+  for (int64_t sidx = smin; sidx <= 32 && sidx <= tiles; ++sidx) {
+    const int64_t tpi = ceil_div(tiles, sidx);
+    if (sidx > 1 && tpi * (sidx - 1) >= tiles) continue;
+    const double cost = (double)ceil_div(batch * sidx, sms) * ((double)tpi + 0.25);  // + pipeline fill / drain
+    if (cost < best_cost * 0.97) { best_cost = cost; best = (int)sidx; }
+  }
+  int bsplit = best;
+  const int tpi = (int)ceil_div(tiles, best);
+  if ((int64_t)tpi * (bsplit - 1) >= tiles) bsplit = (int)ceil_div(tiles, tpi);  // no empty item
+  *items_per_image = bsplit;
+  *tiles_per_item = tpi;
+}
+
 // workspace: [fp16 operand stream of G^ (B x 768 KB)][gscale (B)][float G^ (B x 768 KB)][gmax (B)]
 size_t tc_bwd256_workspace_bytes(int64_t batch) {
   return align_up((size_t)batch * bwd256::G_IMG_BYTES, 256) + 2 * align_up((size_t)batch * sizeof(float), 256) +
@@ -485,26 +508,7 @@ int tc_bwd256_backward(const float* image, int64_t batch, int64_t npix, int chan
   p.wa = sc.wa; p.wb = sc.wb; p.wc = sc.wc;
   p.inv_sk2 = sc.inv_sk2;
   p.inv_sk_sdk = sc.inv_sk_sdk;
-  {
-    // Items per image: the split that minimises (waves of items) x (item size) — with at least sms / 32 items per
-    // image, so that the CTAs of a wave stream the G^ of at most ~32 images (24 MB) and find it in L2: at one
-    // image per CTA the 148 streams (114 MB) evict each other and every K-step comes from HBM (measured 1.6x slower).
-    const int64_t sms = cached_sm_count();
-    const int64_t tiles = ceil_div(npix, TILE);
-    int64_t smin = ceil_div(sms, 32);
-    if (smin > tiles) smin = tiles;
-    int best = (int)smin;
-    double best_cost = 1e30;
-    for (int64_t sidx = smin; sidx <= 32 && sidx <= tiles; ++sidx) {
-      const int64_t tpi = ceil_div(tiles, sidx);
-      if (sidx > 1 && tpi * (sidx - 1) >= tiles) continue;
-      const double cost = (double)ceil_div(batch * sidx, sms) * ((double)tpi + 0.25);  // + pipeline fill / drain
-      if (cost < best_cost * 0.97) { best_cost = cost; best = (int)sidx; }
-    }
-    p.bsplit = best;
-    p.tiles_per_item = (int)ceil_div(tiles, best);
-    if ((int64_t)p.tiles_per_item * (p.bsplit - 1) >= tiles) p.bsplit = (int)ceil_div(tiles, p.tiles_per_item);  // no empty item
-  }
+  tc_bwd256_plan(batch, npix, &p.bsplit, &p.tiles_per_item);
   const size_t smem = sizeof(Smem);
   int grid = cached_sm_count();
   if (grid > batch * p.bsplit) grid = (int)(batch * p.bsplit);

@@ -415,6 +415,12 @@ static Plan plan(int64_t batch, int64_t npix) {
 
 }  // namespace fwd256
 
+void tc_fwd256_plan(int64_t batch, int64_t npix, int* slices_per_image, int64_t* px_per_slice) {
+  const fwd256::Plan pl = fwd256::plan(batch, npix);
+  *slices_per_image = pl.splits;
+  *px_per_slice = pl.px_per_split;
+}
+
 size_t tc_fwd256_workspace_bytes(int64_t batch, int64_t npix) {
   const fwd256::Plan pl = fwd256::plan(batch, npix);
   return align_up((size_t)batch * pl.splits * fwd256::HIST_ELEMS * sizeof(float), 256);

@@ -146,3 +146,34 @@ def test_compute_entry_point_fails_loudly_without_gpu(pkg):
     rc = pkg._lib.load().ph_device_info(0, ctypes.byref(sm), None, None)
     assert rc == pkg._lib.PH_ERR_CUDA
     assert "failed" in pkg._lib.last_error()
+
+
+def test_256_bin_work_plans_cover_every_pixel_once(pkg):
+    """Host logic of the dedicated 256-bin kernels (no device needed: the SM count falls back to 148): for a sweep of
+    batch sizes and image sizes the forward's pixel slices and the backward's tile ranges cover every pixel exactly
+    once, none is empty, slices are whole accumulation chains, the workspace holds every item's partial sums, and the
+    cfgE shapes of the 1 / 2 / 4 / 8-GPU runs fill at least 95 % of their last wave."""
+    lib = pkg._lib.load()
+    out = (ctypes.c_int64 * 4)()
+    sms = 148
+    for batch in (1, 2, 5, 20, 37, 128, 147, 148, 149, 256, 512, 1024, 4096):
+        for npix in (1, 31, 32, 100, 512, 513, 4096, 9216, 65536, 65537, 1 << 20):
+            assert lib.ph_hist256_plan(batch, npix, out) == 0
+            slices, pps, items, tpi = (int(v) for v in out)
+            assert slices >= 1 and pps % 32 == 0
+            assert slices * pps >= npix and (slices - 1) * pps < npix            # covered, last slice non-empty
+            if slices > 1:
+                assert pps % 512 == 0                                             # whole 512-pixel chains
+            tiles = -(-npix // 128)
+            assert items >= 1 and items * tpi >= tiles and (items - 1) * tpi < tiles
+            assert items <= max(32, 1)
+            need = batch * slices * 3 * 256 * 256 * 4
+            assert lib.ph_hist_workspace_bytes(batch, npix, 256, pkg._lib.IMPLS["tc"]) >= need
+    for per_gpu in (1024, 512, 256, 128):                                         # cfgE on 1, 2, 4, 8 GPUs
+        assert lib.ph_hist256_plan(per_gpu, 65536, out) == 0
+        n_items = per_gpu * int(out[0])
+        assert n_items / (-(-n_items // sms) * sms) >= 0.95
+        n_items = per_gpu * int(out[2])
+        assert n_items / (-(-n_items // sms) * sms) >= 0.93
+        assert int(out[2]) >= 5                                                   # G^ streams of <= ~32 images per wave
+    assert lib.ph_hist256_plan(0, 64, out) != 0 and lib.ph_hist256_plan(4, 0, out) != 0
