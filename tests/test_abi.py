@@ -177,3 +177,16 @@ def test_256_bin_work_plans_cover_every_pixel_once(pkg):
         assert n_items / (-(-n_items // sms) * sms) >= 0.93
         assert int(out[2]) >= 5                                                   # G^ streams of <= ~32 images per wave
     assert lib.ph_hist256_plan(0, 64, out) != 0 and lib.ph_hist256_plan(4, 0, out) != 0
+
+
+def test_tf_adapter_is_import_safe_without_tensorflow(pkg):
+    """INTEGRATION.md §2 as code: importable without TensorFlow, a clear ImportError on first use when it is absent."""
+    import importlib
+
+    mod = importlib.import_module("palette_and_histo_gan_b200.tf_adapter")
+    assert callable(mod.histogram_loss) and callable(mod.calculate_rgbuv_histogram)
+    try:
+        import tensorflow  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="TensorFlow"):
+            mod.histogram_loss(None, None)
