@@ -176,7 +176,10 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
           o.v[lane] = v * cs;
           o.ul[lane] = ul * cs;
           o.vl[lane] = vl * cs;
-          o.iy[lane] = valid ? iy * mult * p.iy_scale : 0.f;  // masked pixels contribute nothing (A operand = 0)
+          // masked pixels contribute nothing (A operand = 0).  The intensity scale that keeps count * Iy * K below
+          // fp16's maximum applies to de-duplicated images only: a dense image of the same batch (more than 512 colours)
+          // would lose its far-bin weights to fp16 subnormals under 2^-16 — any per-image power of two cancels in H / D
+          o.iy[lane] = valid ? iy * mult * (ir.dedup ? p.iy_scale : 1.0f) : 0.f;
           mbar_arrive_warp(&S.px_full[slot]);
         }
       }
@@ -350,13 +353,16 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
 // transposes 32 x 32 (i, j) tiles through shared memory so that both sides are coalesced.
 __global__ void __launch_bounds__(256) hist256_finalize_kernel(float* __restrict__ partial, int splits,
                                                                const int* __restrict__ nunique, float inv_scale,
-                                                               float* __restrict__ hist, float* __restrict__ denom) {
+                                                               float iy_scale, float* __restrict__ hist,
+                                                               float* __restrict__ denom) {
   constexpr int CH_STRIDE = 32 * 33 + 11;  // channel planes land on different banks
   __shared__ double scratch[32];
   __shared__ float tile[3 * CH_STRIDE];
   const int64_t b = blockIdx.x;
   float* mine = partial + b * splits * (int64_t)HIST_ELEMS;
   if (nunique != nullptr && nunique[b] >= 0) splits = 1;  // de-duplicated image: only slice 0 was written
+  // a dense image inside a de-duplicated batch was contracted without the intensity scale (inv_scale contains 1 / iy_scale)
+  if (nunique != nullptr && nunique[b] < 0) inv_scale *= iy_scale;
   double acc = 0.0;
   for (int e = threadIdx.x * 4; e < HIST_ELEMS; e += 256 * 4) {
     float4 v = *reinterpret_cast<const float4*>(mine + e);
@@ -462,7 +468,7 @@ int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int chann
   if (grid > p.items) grid = (int)p.items;
   kern<<<grid, THREADS, smem, st>>>(p);
   PH_LAUNCH_OK("hist_fwd256_tc_kernel");
-  hist256_finalize_kernel<<<(unsigned)batch, 256, 0, st>>>(p.partial, pl.splits, nunique, inv_scale, hist, denom);
+  hist256_finalize_kernel<<<(unsigned)batch, 256, 0, st>>>(p.partial, pl.splits, nunique, inv_scale, iy_scale, hist, denom);
   PH_LAUNCH_OK("hist256_finalize_kernel");
   return PH_OK;
 }

@@ -507,9 +507,10 @@ def test_cfgE_full_image_size(H, cuda):
     assert loss_err < LOSS_TOL and grad_err < GRAD_TOL, (loss_err, grad_err)     # measured 2e-8 / 3.6e-6
     # Two dense images drawn from the SAME distribution are the ill-conditioned case of the Hellinger derivative
     # 1 - sqrt(Ht / Hp): at 65 536 pixels the two histograms agree to a few percent, so G^ is a difference of nearly
-    # equal terms that amplifies every upstream rounding (forward histogram, float32 evaluation of that expression)
-    # (measured 1.0e-5; the CUDA-core engine 4e-6; the product chains themselves contribute 1e-6, tools/emul_trunc_bwd.py;
-    # the reference's own float32 evaluation would be several 1e-5).  Held to a bar that reflects the conditioning.
+    # equal terms that amplifies every upstream rounding (measured 1.0e-5 while the dense real image was contracted
+    # under the de-duplication mode's 2^-16 intensity scale, ~4e-6 since that scale applies to de-duplicated images
+    # only; the CUDA-core engine 4e-6; the product chains contribute 1e-6, tools/emul_trunc_bwd.py; the reference's own
+    # float32 evaluation would be several 1e-5).  Held to a bar that reflects the conditioning.
     loss_err, grad_err = against_oracle(fake[1:2], fake[2:3])
     assert loss_err < LOSS_TOL and grad_err < 3e-5, (loss_err, grad_err)
     h_small = H.calculate_rgbuv_histogram(fake, size=256, impl="tc")
