@@ -4,7 +4,7 @@
  * Drop-in boundary for the per-pixel colour path of fegemo/palette-and-histo-gan.  The reference
  * has no FFI of its own: its boundary is a set of Python callables over TensorFlow ops.  Each entry
  * point below names the reference callable (file:line under /root/reference) whose arithmetic it
- * replaces; the Python host in `palette-and-histo-gan_b200/` keeps those callables' signatures and
+ * replaces; the Python host in `palette_and_histo_gan_b200/` keeps those callables' signatures and
  * forwards to these functions through ctypes (see INTEGRATION.md for the binding).
  *
  * Conventions

@@ -1,7 +1,7 @@
 """CPU oracle for the colour hot path of fegemo/palette-and-histo-gan.
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product package
-(`palette-and-histo-gan_b200/`) may import this.  The only legitimate callers are
+(`palette_and_histo_gan_b200/`) may import this.  The only legitimate callers are
 `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs.
 
 PARITY UNPINNED: the reference (TensorFlow 2.9.1, `requirements.txt:99`) cannot be imported in

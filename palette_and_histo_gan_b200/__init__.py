@@ -1,10 +1,18 @@
-"""Importable alias of the package directory `palette-and-histo-gan_b200/` (a hyphen is not a valid
-Python identifier).  `import palette_and_histo_gan_b200` executes that directory's `__init__.py` with
-this module's `__path__` pointing at it, so submodules resolve there."""
-import os as _os
+"""B200-native colour kernels behind the call signatures of fegemo/palette-and-histo-gan.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "palette-and-histo-gan_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
-del _f
+    from palette_and_histo_gan_b200 import histogram, io_utils, dataset_utils
+
+`histogram`, `io_utils` and `dataset_utils` mirror the reference modules of the same names for the
+per-pixel colour path (RGB-uv histogram + Hellinger loss forward/backward, palette extraction,
+colour indexing, one-hot).  Everything computes in hand-written sm_100a CUDA inside
+`libpalhist.so` (C ABI: include/palhist.h); importing this package without the built library
+raises ImportError — there is no CPU or framework fallback.
+"""
+from . import _lib
+
+_lib.load()  # fail loudly at import time if the CUDA library is missing
+
+from . import configuration, dataset_utils, histogram, hostapi, io_utils  # noqa: E402
+
+__all__ = ["configuration", "dataset_utils", "histogram", "hostapi", "io_utils"]
+__version__ = "0.1.0"

@@ -23,7 +23,7 @@ def declared_symbols():
 def pkg():
     import __graft_entry__ as g
 
-    if not os.path.exists(os.path.join(ROOT, "palette-and-histo-gan_b200", "libpalhist.so")):
+    if not os.path.exists(os.path.join(ROOT, "palette_and_histo_gan_b200", "libpalhist.so")):
         g.build()
     import palette_and_histo_gan_b200 as p
 
@@ -80,7 +80,7 @@ def test_no_cpu_fallback(pkg):
     with pytest.raises(ValueError, match="CUDA"):
         pkg.io_utils.extract_palette(torch.zeros((4, 4, 4), dtype=torch.int32), "grayness")
     out = subprocess.run(["grep", "-rIl", "--include=*.py", "--include=*.cu", "--include=*.cuh", "-E",
-                          r"^\s*(from|import)\s+oracle|oracle/", os.path.join(ROOT, "palette-and-histo-gan_b200")],
+                          r"^\s*(from|import)\s+oracle|oracle/", os.path.join(ROOT, "palette_and_histo_gan_b200")],
                          capture_output=True, text=True)
     assert out.stdout.strip() == "", f"product package references the oracle: {out.stdout}"
 

@@ -4,7 +4,7 @@
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
-#include "../palette-and-histo-gan_b200/csrc/tc_ptx.cuh"
+#include "../palette_and_histo_gan_b200/csrc/tc_ptx.cuh"
 using namespace ph::tc;
 
 __device__ __forceinline__ void mma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
