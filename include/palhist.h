@@ -15,8 +15,9 @@
  *     enqueued on it and the call returns without synchronising unless stated otherwise;
  *   - return value: PH_OK (0) or a negative PH_ERR_* code; `ph_last_error()` returns a
  *     thread-local message for the last failing call on this host thread;
- *   - re-entrant: no global mutable state; scratch memory is passed in by the caller
- *     (`workspace`, size from the matching `*_workspace_bytes`).
+ *   - re-entrant: scratch memory is passed in by the caller (`workspace`, size from the matching
+ *     `*_workspace_bytes`); the only process-wide state is the launch counter and the sticky asynchronous
+ *     status word of ph_async_status();
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     PH_ERR_CUDA.
  */
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 1
+#define PH_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -48,8 +49,11 @@ enum ph_status {
 /* histogram.py:22-27 — the two bin kernels the reference implements. */
 enum ph_method { PH_METHOD_INVERSE_QUADRATIC = 0, PH_METHOD_RBF = 1 };
 
-/* io_utils.py:44-58 — deterministic palette orderings ("shuffled" is a host-side permutation). */
-enum ph_ordering { PH_ORDER_TOP2BOTTOM = 0, PH_ORDER_BOTTOM2TOP = 1, PH_ORDER_GRAYNESS = 2 };
+/* io_utils.py:44-58 — palette orderings.  PH_ORDER_SHUFFLED is the reference's else-branch
+ * (`tf.random.shuffle(colors)`, :56-58): the colours in first-occurrence order are permuted by ranking
+ * caller-provided independent uniform keys (`shuffle_keys`, (batch,256) float32 on the device) — a uniformly
+ * random permutation, reproducible from the caller's seed; TensorFlow's own random stream is not reproduced. */
+enum ph_ordering { PH_ORDER_TOP2BOTTOM = 0, PH_ORDER_BOTTOM2TOP = 1, PH_ORDER_GRAYNESS = 2, PH_ORDER_SHUFFLED = 3 };
 
 /* rgba_to_indexed flavour: the reference's exact-match scatter-add (io_utils.py:84-91) or
  * nearest colour (first arg-min of squared RGBA distance; equal to the former whenever every
@@ -82,6 +86,14 @@ PH_API const char* ph_last_error(void);
  * last reset (bench.py's `gpu_launches`). */
 PH_API int64_t ph_launch_count(void);
 PH_API void ph_reset_launch_count(void);
+/* Sticky asynchronous status of the kernels launched by this process on `device` (-1: the current device): bit 0 =
+ * a histogram forward on the tensor-core engine met a pixel whose intensity-weighted operand does not fit fp16
+ * (an image far outside [-1,1]: the reference, histogram.py:58, accepts any float; results of that launch are
+ * inf / NaN — re-run it with PH_IMPL_SIMT).  The word lives in mapped host memory, so reading it never
+ * synchronises; it is as current as the last completed kernel.  clear != 0 resets it.  Every ph_hist_* call also
+ * checks it on entry and fails with PH_ERR_UNSUPPORTED (clearing it), like CUDA's own asynchronous errors. */
+#define PH_ASYNC_RANGE 1
+PH_API int ph_async_status(int device, int clear);
 /* sm_count / compute capability of `device`; PH_ERR_CUDA without a usable GPU. */
 PH_API int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
@@ -159,9 +171,10 @@ PH_API int ph_mean_abs_or_sq_diff(const float* a, const float* b, int64_t n, int
  * ------------------------------------------------------------------------------------------ */
 /* io_utils.py:25-65 `extract_palette`, batched.  image (batch, rows, 4) int32 with values in
  * [0,255]; rows are the pixels in reshape(-1,4) order.  palette (batch,256,4) int32 padded with
- * INVALID_INDEX_COLOR (configuration.py:32); ncolors (batch) int32, see PH_PALETTE_BAD_VALUE. */
+ * INVALID_INDEX_COLOR (configuration.py:32); ncolors (batch) int32, see PH_PALETTE_BAD_VALUE.
+ * shuffle_keys: (batch,256) float32, required for PH_ORDER_SHUFFLED, ignored (may be NULL) otherwise. */
 PH_API int ph_extract_palette(const int32_t* image, int64_t batch, int64_t rows, int ordering,
-                       int32_t* palette, int32_t* ncolors, void* stream);
+                       const float* shuffle_keys, int32_t* palette, int32_t* ncolors, void* stream);
 
 /* io_utils.py:78-93 `rgba_to_indexed`, batched, optionally fused with the one-hot of
  * pix2pix_model.py:300-301.  image (batch,npix,4) int32; palette (palette_batch,256,4) int32 with
@@ -209,8 +222,46 @@ PH_API int ph_argmax_indexed(const float* probabilities, int64_t batch, int64_t 
  * src px0, tgt px0, src px1, ... as the channel-axis concat + reshape(-1,4) produces), then both
  * index images.  source/target (batch,npix,4) int32. */
 PH_API int ph_load_indexed_images(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
-                           int ordering, int32_t* source_indexed, int32_t* target_indexed,
-                           int32_t* palette, int32_t* ncolors, void* stream);
+                           int ordering, const float* shuffle_keys, int32_t* source_indexed,
+                           int32_t* target_indexed, int32_t* palette, int32_t* ncolors, void* stream);
+/* Same with source/target as the decoded PNG's uint8 RGBA (batch,npix,4) on the device (dataset_utils.py:66-70
+ * before the int32 cast of :140-141): 4 B per pixel read instead of 16, identical outputs. */
+PH_API int ph_load_indexed_images_u8(const uint8_t* source, const uint8_t* target, int64_t batch, int64_t npix,
+                              int ordering, const float* shuffle_keys, int32_t* source_indexed,
+                              int32_t* target_indexed, int32_t* palette, int32_t* ncolors, void* stream);
+
+/* The loader's pixel helpers on device tensors (dataset_utils.py:11-20, :39-60), n elements of float32:
+ *   PH_MAP_BLACKEN      RGBA groups of four: alpha == 0 -> the whole pixel becomes 0 (n a multiple of 4);
+ *   PH_MAP_NORMALIZE    x / 127.5 - 1  (true division and a subtraction, the reference's two roundings);
+ *   PH_MAP_DENORMALIZE  (x + 1) * 127.5.
+ * In place (out == in) is allowed. */
+enum ph_map_op { PH_MAP_BLACKEN = 0, PH_MAP_NORMALIZE = 1, PH_MAP_DENORMALIZE = 2 };
+PH_API int ph_pixel_map(const float* in, int64_t n, int op, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sharded batches on one NVLink / NVSwitch box: the one exchange of the path — the sum over ranks of the Hellinger
+ * sum of squares (histogram.py:88-89 takes one sqrt over the WHOLE batch) — as a single 32-thread kernel over peer
+ * memory instead of a library collective.  Every rank owns a small mailbox in its HBM; the kernel stores this
+ * rank's value into the mailbox of every peer (P2P stores over NVLink, release at system scope), waits until the
+ * values of all ranks for this round have landed in its own mailbox (acquire polls of local memory) and adds them
+ * in rank order, so all ranks obtain the same bits.  ~3 us against ~30 us for an 8-byte NCCL all-reduce, no host
+ * round trip, no SM-residency requirement beyond one warp.
+ *   ph_comm_create   allocates this rank's mailbox on `device`;
+ *   ph_comm_export   its 64-byte CUDA IPC handle (exchange the handles of all ranks by any means, e.g.
+ *                    torch.distributed.all_gather_object);
+ *   ph_comm_connect  maps the peers' mailboxes (handles_host: world x 64 bytes, rank order; own entry ignored);
+ *   ph_comm_allreduce_sum_f64  *value (device double, `count` <= 2 of them) <- sum over ranks, in place, enqueued
+ *                    on `stream`; a collective: every rank must call it the same number of times.
+ * A rank that waits longer than ~10 s for a peer aborts its kernel (trap -> launch error) instead of hanging.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct ph_comm ph_comm;
+#define PH_COMM_HANDLE_BYTES 64
+#define PH_COMM_MAX_WORLD 16
+PH_API int ph_comm_create(int device, int rank, int world, ph_comm** comm);
+PH_API int ph_comm_export(ph_comm* comm, void* handle_host);
+PH_API int ph_comm_connect(ph_comm* comm, const void* handles_host);
+PH_API int ph_comm_allreduce_sum_f64(ph_comm* comm, double* value, int count, void* stream);
+PH_API void ph_comm_destroy(ph_comm* comm);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer convenience (the call a CPU-side caller such as a tf.data worker binds):
@@ -243,18 +294,24 @@ PH_API int ph_host_hist_begin_u8real(ph_host_ctx* ctx, const uint8_t* real_u8_ho
                               float sigma_sqr, float epsilon, int impl, double* ssum_local_host);
 PH_API int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
                         float* grad_fake_host, float* grad_fake_device);
+/* `finish` for ranks connected by a ph_comm: the shard's sum of squares left on the device by `begin` is
+ * summed over the ranks by ph_comm_allreduce_sum_f64 on the context's stream — no host round trip between the
+ * phases (the host value `begin` returned is not needed). */
+PH_API int ph_host_hist_finish_comm(ph_host_ctx* ctx, ph_comm* comm, int64_t global_batch, float* loss_host,
+                             float* grad_fake_host, float* grad_fake_device);
 
 /* dataset_utils.py:138-151 for host images (+ optional one-hot of the target indices). */
 PH_API int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,
-                                int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
-                                int32_t* target_indexed_host, int32_t* palette_host,
+                                int64_t batch, int64_t npix, int ordering, const float* shuffle_keys_host,
+                                int32_t* source_indexed_host, int32_t* target_indexed_host, int32_t* palette_host,
                                 int32_t* ncolors_host, float* target_one_hot_host);
 
 /* Same with the images as the decoded PNG's uint8 RGBA (dataset_utils.py:66-70 `decode_png` before the casts of
- * :72 and :140-141): a quarter of the upload; widened to int32 on the device, outputs identical. */
+ * :72 and :140-141): a quarter of the upload, read as uint8 by the kernel, outputs identical.
+ * shuffle_keys_host: (batch,256) float32 for PH_ORDER_SHUFFLED, else NULL. */
 PH_API int ph_host_load_indexed_images_u8(ph_host_ctx* ctx, const uint8_t* source_host, const uint8_t* target_host,
-                                   int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
-                                   int32_t* target_indexed_host, int32_t* palette_host,
+                                   int64_t batch, int64_t npix, int ordering, const float* shuffle_keys_host,
+                                   int32_t* source_indexed_host, int32_t* target_indexed_host, int32_t* palette_host,
                                    int32_t* ncolors_host, float* target_one_hot_host);
 
 #ifdef __cplusplus

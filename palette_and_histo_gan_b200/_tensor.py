@@ -12,9 +12,16 @@ import torch
 
 
 def from_any(x, *, name="tensor") -> torch.Tensor:
-    """Borrow `x` as a torch tensor without copying."""
+    """Borrow `x` as a torch tensor without copying.  A TensorFlow tensor is produced on TensorFlow's own stream,
+    which DLPack does not carry: its device work is drained first (see tf_adapter.py)."""
     if isinstance(x, torch.Tensor):
         return x
+    if is_tf_tensor(x):
+        import tensorflow as tf  # only reachable when the caller already uses TensorFlow
+
+        from .tf_adapter import _sync_tf
+
+        _sync_tf(tf, x)
     if type(x).__name__ == "PyCapsule":
         return torch.utils.dlpack.from_dlpack(x)
     if hasattr(x, "__dlpack__"):
@@ -50,5 +57,6 @@ def to_caller_framework(out: torch.Tensor, like):
     if is_tf_tensor(like):
         import tensorflow as tf  # only reachable when the caller already uses TensorFlow
 
+        torch.cuda.current_stream(out.device).synchronize()  # TensorFlow reads on its own stream
         return tf.experimental.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(out))
     return out

@@ -36,6 +36,45 @@ int cached_sm_count() {
   return counts[dev];
 }
 
+// sticky asynchronous status: one word of mapped (zero-copy) host memory per device, written by kernels with plain
+// stores and read by the host without any synchronisation
+static int* g_status_host[64];
+static int* g_status_dev[64];
+static std::mutex g_status_mutex;
+int* async_status_word() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_status_mutex);
+  if (g_status_dev[dev] == nullptr) {
+    int* h = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    *h = 0;
+    int* d = nullptr;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), h, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFreeHost(h);
+      return nullptr;
+    }
+    g_status_host[dev] = h;
+    g_status_dev[dev] = d;
+  }
+  return g_status_dev[dev];
+}
+// entry check of the ph_hist_* calls: an earlier launch on this device left the range flag
+static int consume_async_status() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PH_OK;
+  volatile int* h = g_status_host[dev];
+  if (h == nullptr || *h == 0) return PH_OK;
+  *h = 0;
+  set_error("an earlier histogram launch on the tensor-core engine met pixels outside its operand range (image far "
+            "outside [-1, 1]); its results are inf / NaN — re-run that call with the CUDA-core engine (impl = simt)");
+  return PH_ERR_UNSUPPORTED;
+}
+
 static int resolve_impl(int impl, int64_t npix, int bins, int method) {
   impl &= PH_IMPL_ENGINE_MASK;
   if (impl == PH_IMPL_AUTO) return tc_supported(npix, bins, method) ? PH_IMPL_TC : PH_IMPL_SIMT;
@@ -66,6 +105,16 @@ int ph_abi_version(void) { return PH_ABI_VERSION; }
 const char* ph_last_error(void) { return g_error; }
 int64_t ph_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void ph_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+int ph_async_status(int device, int clear) {
+  if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return 0;
+  if (device < 0 || device >= 64) return 0;
+  volatile int* h = g_status_host[device];
+  if (h == nullptr) return 0;
+  const int v = *h;
+  if (clear) *h = 0;
+  return v;
+}
 
 int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
   cudaDeviceProp prop;
@@ -102,6 +151,7 @@ static int hist_forward_impl(const float* image, int64_t batch, int64_t npix, in
                              size_t workspace_bytes, int impl, void* stream) {
   int rc = check_hist_args(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr);
   if (rc != PH_OK) return rc;
+  if ((rc = consume_async_status()) != PH_OK) return rc;
   PH_CHECK_ARG(hist != nullptr && denom != nullptr, "hist / denom must not be NULL");
   PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
                "bad impl %d", impl);
@@ -168,6 +218,7 @@ int ph_hist_backward(const float* image, int64_t batch, int64_t npix, int channe
                      int impl, void* stream) {
   int rc = check_hist_args(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr);
   if (rc != PH_OK) return rc;
+  if ((rc = consume_async_status()) != PH_OK) return rc;
   PH_CHECK_ARG(hist_pred && denom_pred && grad_image, "hist_pred / denom_pred / grad_image must not be NULL");
   PH_CHECK_ARG(grad_hist != nullptr || (hist_true != nullptr && ssum != nullptr && global_batch > 0),
                "either grad_hist or (hist_true, ssum, global_batch>0) must be given");
@@ -219,14 +270,14 @@ int ph_mean_abs_or_sq_diff(const float* a, const float* b, int64_t n, int kind, 
   return launch_diff_reduce(a, b, n, kind, out, static_cast<cudaStream_t>(stream));
 }
 
-int ph_extract_palette(const int32_t* image, int64_t batch, int64_t rows, int ordering,
+int ph_extract_palette(const int32_t* image, int64_t batch, int64_t rows, int ordering, const float* shuffle_keys,
                        int32_t* palette, int32_t* ncolors, void* stream) {
   PH_CHECK_ARG(image && palette && ncolors, "NULL pointer argument");
   PH_CHECK_ARG(batch >= 0 && rows > 0, "bad shape");
-  PH_CHECK_ARG(ordering >= PH_ORDER_TOP2BOTTOM && ordering <= PH_ORDER_GRAYNESS, "bad ordering %d", ordering);
+  PH_CHECK_ARG(ordering >= PH_ORDER_TOP2BOTTOM && ordering <= PH_ORDER_SHUFFLED, "bad ordering %d", ordering);
   PH_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0 && (reinterpret_cast<uintptr_t>(palette) & 15) == 0,
                "image / palette must be 16-byte aligned");
-  return launch_extract_palette(image, nullptr, batch, rows, ordering, palette, ncolors,
+  return launch_extract_palette(image, nullptr, batch, rows, ordering, shuffle_keys, palette, ncolors,
                                 static_cast<cudaStream_t>(stream));
 }
 
@@ -319,18 +370,38 @@ int ph_argmax_indexed(const float* probabilities, int64_t batch, int64_t npix, i
                                static_cast<cudaStream_t>(stream));
 }
 
-int ph_load_indexed_images(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
-                           int ordering, int32_t* source_indexed, int32_t* target_indexed,
+int ph_load_indexed_images(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix, int ordering,
+                           const float* shuffle_keys, int32_t* source_indexed, int32_t* target_indexed,
                            int32_t* palette, int32_t* ncolors, void* stream) {
   PH_CHECK_ARG(source && target && source_indexed && target_indexed && palette && ncolors, "NULL pointer argument");
   PH_CHECK_ARG(batch >= 0 && npix > 0, "bad shape");
-  PH_CHECK_ARG(ordering >= PH_ORDER_TOP2BOTTOM && ordering <= PH_ORDER_GRAYNESS, "bad ordering %d", ordering);
+  PH_CHECK_ARG(ordering >= PH_ORDER_TOP2BOTTOM && ordering <= PH_ORDER_SHUFFLED, "bad ordering %d", ordering);
   PH_CHECK_ARG((reinterpret_cast<uintptr_t>(source) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(palette) & 15) == 0,
                "source / target / palette must be 16-byte aligned");
   // one launch: the palette is extracted and both images are indexed from the same CTA-resident table
-  return launch_load_indexed_fused(source, target, batch, npix, ordering, source_indexed, target_indexed, palette,
-                                   ncolors, static_cast<cudaStream_t>(stream));
+  return launch_load_indexed_fused(source, target, 4, batch, npix, ordering, shuffle_keys, source_indexed, target_indexed,
+                                   palette, ncolors, static_cast<cudaStream_t>(stream));
+}
+
+int ph_load_indexed_images_u8(const uint8_t* source, const uint8_t* target, int64_t batch, int64_t npix, int ordering,
+                              const float* shuffle_keys, int32_t* source_indexed, int32_t* target_indexed,
+                              int32_t* palette, int32_t* ncolors, void* stream) {
+  PH_CHECK_ARG(source && target && source_indexed && target_indexed && palette && ncolors, "NULL pointer argument");
+  PH_CHECK_ARG(batch >= 0 && npix > 0, "bad shape");
+  PH_CHECK_ARG(ordering >= PH_ORDER_TOP2BOTTOM && ordering <= PH_ORDER_SHUFFLED, "bad ordering %d", ordering);
+  PH_CHECK_ARG((reinterpret_cast<uintptr_t>(source) & 3) == 0 && (reinterpret_cast<uintptr_t>(target) & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(palette) & 15) == 0,
+               "uint8 source / target must be 4-byte aligned and the palette 16-byte aligned");
+  return launch_load_indexed_fused(source, target, 1, batch, npix, ordering, shuffle_keys, source_indexed, target_indexed,
+                                   palette, ncolors, static_cast<cudaStream_t>(stream));
+}
+
+int ph_pixel_map(const float* in, int64_t n, int op, float* out, void* stream) {
+  PH_CHECK_ARG(in && out && n >= 0, "bad argument");
+  PH_CHECK_ARG(op >= PH_MAP_BLACKEN && op <= PH_MAP_DENORMALIZE, "bad op %d", op);
+  PH_CHECK_ARG(op != PH_MAP_BLACKEN || n % 4 == 0, "blacken works on RGBA pixels: n must be a multiple of 4");
+  return launch_pixel_map(in, n, op, out, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

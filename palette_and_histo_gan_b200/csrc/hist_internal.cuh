@@ -8,6 +8,9 @@
 namespace ph {
 
 int cached_sm_count();  // SM count of the current device (148 on B200), cached per device
+// Device-usable pointer to the current device's sticky status word in mapped host memory (ph_async_status), created
+// on first use; NULL if the allocation failed.
+int* async_status_word();
 
 // ---- hist_simt.cu ---------------------------------------------------------------------------
 int simt_fwd_splits(int64_t batch, int64_t npix, int bins);
@@ -61,17 +64,17 @@ int tc_hist_backward(const float* image, int64_t batch, int64_t npix, int channe
                      void* workspace, cudaStream_t st);
 
 // ---- palette.cu -------------------------------------------------------------------------------
-int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows,
-                           int ordering, int32_t* palette, int32_t* ncolors, cudaStream_t st);
-int launch_load_indexed_fused(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
-                              int ordering, int32_t* source_indexed, int32_t* target_indexed, int32_t* palette,
-                              int32_t* ncolors, cudaStream_t st);
+int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows, int ordering,
+                           const float* shuffle_keys, int32_t* palette, int32_t* ncolors, cudaStream_t st);
+int launch_load_indexed_fused(const void* source, const void* target, int elem_bytes, int64_t batch, int64_t npix,
+                              int ordering, const float* shuffle_keys, int32_t* source_indexed,
+                              int32_t* target_indexed, int32_t* palette, int32_t* ncolors, cudaStream_t st);
+int launch_pixel_map(const float* in, int64_t n, int op, float* out, cudaStream_t st);
 int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,
                            int64_t palette_batch, int mode, int32_t* indexed, float* one_hot, int depth,
                            cudaStream_t st);
 int launch_u8_to_float_image(const uint8_t* src, int64_t npixels, int blacken, int normalize, float* dst,
                              cudaStream_t st);
-int launch_u8_to_i32_image(const uint8_t* src, int64_t npixels, int32_t* dst, cudaStream_t st);
 int launch_one_hot(const int32_t* indexed, int64_t n, int depth, float* one_hot, cudaStream_t st);
 int launch_augment_pair(const float* first, const float* second, int64_t batch, int height, int width,
                         const float* hue_delta, const float* translation, const uint8_t* apply, int normalize,

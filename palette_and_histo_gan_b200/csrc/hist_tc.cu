@@ -39,6 +39,7 @@ namespace fwdtc {
 
 using tcgen::named_bar_sync;
 using tcgen::weight2;
+using tcgen::weight4;
 
 constexpr int BINS = 64;
 constexpr int KB = 32;         // pixels per pipeline stage
@@ -110,9 +111,13 @@ struct Params {
   // the inverse-quadratic weight needs one FMA and a reciprocal:  IQ: K / w = 1 / (d d + wb),  wb = w = s^2 sigma^2
   // in [2^-14, 2^-13];  RBF: 2^14 K = 2^(wa d d + wb)
   float wa, wb, coord_scale;
-  float iy_scale;    // power of two applied to the intensity (x multiplicity) so that the A operand stays below
-                     // fp16's 65504: 1 for dense images, 2^-ceil(log2 npix) for de-duplicated ones
-  float inv_scale;   // 1 / (weight scale^2 * iy_scale): raw sums -> true scale
+  float iy_scale;    // power of two applied to the intensity x multiplicity of a DE-DUPLICATED image so that the A
+                     // operand stays below fp16's 65504: 2^-ceil(log2 npix).  Dense images (also those a
+                     // de-duplicated batch falls back on) keep scale 1: with the batch-wide scale their far-bin
+                     // weights dropped into fp16 subnormals
+  float inv_scale;        // 1 / (weight scale^2 * iy_scale): raw sums of a de-duplicated image -> true scale
+  float inv_scale_dense;  // 1 / weight scale^2: raw sums of a dense image -> true scale
+  int* status;            // mapped host word (ph_async_status): bit PH_ASYNC_RANGE when an A operand would overflow fp16
 };
 
 // Pixel range of a work item.  A de-duplicated image is a list of (colour, multiplicity) entries: the
@@ -207,7 +212,11 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         o.u[0][lane] = d_rg;  o.v[0][lane] = d_rb;
         o.u[1][lane] = -d_rg; o.v[1][lane] = d_gb;
         o.u[2][lane] = -d_rb; o.v[2][lane] = -d_gb;
-        o.iy[lane] = valid ? iy * mult * p.iy_scale : 0.f;  // masked pixels contribute nothing (A operand = 0)
+        const float a_iy = valid ? iy * mult * (ir.dedup ? p.iy_scale : 1.0f) : 0.f;  // masked pixels contribute nothing (A operand = 0)
+        // the A operand is a_iy x (scaled weight <= 2^14): an image far outside [-1, 1] would overflow fp16 where the
+        // reference computes a finite value (histogram.py:58) — flagged, never silent
+        if (a_iy > tcgen::IY_OPERAND_LIMIT) *reinterpret_cast<volatile int*>(p.status) = PH_ASYNC_RANGE;
+        o.iy[lane] = a_iy;
         mbar_arrive_warp(&S.px_full[slot]);
       }
     }
@@ -251,10 +260,9 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         uint4 hi[3], lo[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          f32x2 w0 = weight2<METHOD>(xx[c][0].x, negc, wa2, wb2);
-          f32x2 w1 = weight2<METHOD>(xx[c][0].y, negc, wa2, wb2);
-          f32x2 w2 = weight2<METHOD>(xx[c][1].x, negc, wa2, wb2);
-          f32x2 w3 = weight2<METHOD>(xx[c][1].y, negc, wa2, wb2);
+          f32x2 w0, w1, w2, w3;
+          weight4<METHOD>(xx[c][0].x, xx[c][0].y, negc, wa2, wb2, w0, w1);
+          weight4<METHOD>(xx[c][1].x, xx[c][1].y, negc, wa2, wb2, w2, w3);
           if (side == 0) { w0 = mul2(w0, iw[0].x); w1 = mul2(w1, iw[0].y); w2 = mul2(w2, iw[1].x); w3 = mul2(w3, iw[1].y); }
           split_f16x2(w0, mone2, hi[c].x, lo[c].x);
           split_f16x2(w1, mone2, hi[c].y, lo[c].y);
@@ -316,12 +324,13 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         named_bar_sync(5, PROD_WARPS * 32);
         const int t = tid;  // 0..511
         bool finish = ir.whole;
-        float dscale = p.inv_scale;  // raw sum -> true scale of the normaliser D
+        const float item_inv_scale = ir.dedup ? p.inv_scale : p.inv_scale_dense;
+        float dscale = item_inv_scale;  // raw sum -> true scale of the normaliser D
         if (!ir.whole) {
           float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
           for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
             const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
-            dst[e] = S.acc[c][j][i] * p.inv_scale;
+            dst[e] = S.acc[c][j][i] * item_inv_scale;
           }
           __threadfence();
           named_bar_sync(5, PROD_WARPS * 32);
@@ -686,6 +695,9 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     off += dedup_bytes(batch);
   }
   p.inv_scale = (float)(1.0 / (weight_scale * weight_scale * (double)p.iy_scale));
+  p.inv_scale_dense = (float)(1.0 / (weight_scale * weight_scale));
+  p.status = async_status_word();
+  PH_CHECK_ARG(p.status != nullptr, "no mapped status word (cudaHostAlloc failed)");
   const int64_t n_tail = batch - p.n_whole;
   if (n_tail > 0) {
     p.partial = reinterpret_cast<float*>(ws + off);

@@ -40,6 +40,7 @@ namespace fwd256 {
 
 using tcgen::named_bar_sync;
 using tcgen::weight2;
+using tcgen::weight4;
 
 constexpr int BINS = 256;
 constexpr int KB = 32;         // pixels per stage = two K steps of the instruction (= one pixel-ring slot): the
@@ -93,6 +94,7 @@ struct Params {
   int64_t items;         // B * splits
   float eps;
   float wa, wb, coord_scale, iy_scale;  // as in hist_tc.cu
+  int* status;                          // as in hist_tc.cu
 };
 
 struct ItemRange {
@@ -179,7 +181,9 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
           // masked pixels contribute nothing (A operand = 0).  The intensity scale that keeps count * Iy * K below
           // fp16's maximum applies to de-duplicated images only: a dense image of the same batch (more than 512 colours)
           // would lose its far-bin weights to fp16 subnormals under 2^-16 — any per-image power of two cancels in H / D
-          o.iy[lane] = valid ? iy * mult * (ir.dedup ? p.iy_scale : 1.0f) : 0.f;
+          const float a_iy = valid ? iy * mult * (ir.dedup ? p.iy_scale : 1.0f) : 0.f;
+          if (a_iy > tcgen::IY_OPERAND_LIMIT) *reinterpret_cast<volatile int*>(p.status) = PH_ASYNC_RANGE;  // see hist_tc.cu
+          o.iy[lane] = a_iy;
           mbar_arrive_warp(&S.px_full[slot]);
         }
       }
@@ -270,10 +274,9 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd256_tc_kernel(Params p) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {    // the four bins
             // d = (x_hi - c) + x_lo: the first sum is exact near the bin centre, where the weight is steep
-            f32x2 w0 = weight2<METHOD>(add2(xx[0].x, negc[q]), xl[0].x, wa2, wb2);
-            f32x2 w1 = weight2<METHOD>(add2(xx[0].y, negc[q]), xl[0].y, wa2, wb2);
-            f32x2 w2 = weight2<METHOD>(add2(xx[1].x, negc[q]), xl[1].x, wa2, wb2);
-            f32x2 w3 = weight2<METHOD>(add2(xx[1].y, negc[q]), xl[1].y, wa2, wb2);
+            f32x2 w0, w1, w2, w3;
+            weight4<METHOD>(add2(xx[0].x, negc[q]), add2(xx[0].y, negc[q]), xl[0].x, xl[0].y, wa2, wb2, w0, w1);
+            weight4<METHOD>(add2(xx[1].x, negc[q]), add2(xx[1].y, negc[q]), xl[1].x, xl[1].y, wa2, wb2, w2, w3);
             if (side == 0) { w0 = mul2(w0, iw[0].x); w1 = mul2(w1, iw[0].y); w2 = mul2(w2, iw[1].x); w3 = mul2(w3, iw[1].y); }
             uint4 hi, lo;
             split_f16x2(w0, mone2, hi.x, lo.x);
@@ -459,6 +462,8 @@ int tc_fwd256_forward(const float* image, int64_t batch, int64_t npix, int chann
   p.wb = wsc.wb;
   p.coord_scale = wsc.coord_scale;
   p.iy_scale = iy_scale;
+  p.status = async_status_word();
+  PH_CHECK_ARG(p.status != nullptr, "no mapped status word (cudaHostAlloc failed)");
   const float inv_scale = (float)(1.0 / (wsc.weight_scale * wsc.weight_scale * (double)iy_scale));
   void (*kern)(Params) = method == PH_METHOD_INVERSE_QUADRATIC ? hist_fwd256_tc_kernel<PH_METHOD_INVERSE_QUADRATIC>
                                                                : hist_fwd256_tc_kernel<PH_METHOD_RBF>;

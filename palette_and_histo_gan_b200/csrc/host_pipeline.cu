@@ -81,6 +81,13 @@ static int launch_grad_rescale(const float* in, float* out, int64_t n, const dou
   return PH_OK;
 }
 
+// *out = parts[0] (+ parts[1]): the two compute streams' shares of the shard's sum of squares
+__global__ void sum_parts_kernel(const double* __restrict__ parts, int n, double* __restrict__ out) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += parts[i];
+  *out = s;
+}
+
 static int ensure_arena(ph_host_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->arena_bytes) return PH_OK;
   if (ctx->arena) {
@@ -277,11 +284,11 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   // ---- the one coupling scalar ----
   PH_CUDA_OK(cudaEventRecord(ctx->ev_join, ctx->s_compute2));
   PH_CUDA_OK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_join, 0));
-  double parts[2] = {0.0, 0.0};
-  PH_CUDA_OK(cudaMemcpyAsync(parts, J.d_ssum2, sizeof(double) * (nchunks > 1 ? 2 : 1), cudaMemcpyDeviceToHost,
-                             ctx->s_compute));
+  // the shard's sum stays on the device (ph_host_hist_finish_comm all-reduces it there) and is also returned
+  sum_parts_kernel<<<1, 1, 0, ctx->s_compute>>>(J.d_ssum2, nchunks > 1 ? 2 : 1, J.d_ssum);
+  PH_LAUNCH_OK("sum_parts_kernel");
+  PH_CUDA_OK(cudaMemcpyAsync(ssum_local_host, J.d_ssum, sizeof(double), cudaMemcpyDeviceToHost, ctx->s_compute));
   PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
-  *ssum_local_host = parts[0] + parts[1];
   ctx->job_valid = true;
   return PH_OK;
 }
@@ -300,16 +307,22 @@ int ph_host_hist_begin_u8real(ph_host_ctx* ctx, const uint8_t* real_u8_host, con
                               sigma_sqr, epsilon, impl, true, ssum_local_host);
 }
 
-int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
-                        float* grad_fake_host, float* grad_fake_device) {
+static int host_hist_finish_impl(ph_host_ctx* ctx, ph_comm* comm, double ssum_global, int64_t global_batch,
+                                 float* loss_host, float* grad_fake_host, float* grad_fake_device) {
   PH_CHECK_ARG(ctx && loss_host, "NULL pointer argument");
   PH_CHECK_ARG(ctx->job_valid, "ph_host_hist_finish without a preceding successful ph_host_hist_begin");
   PH_CHECK_ARG(global_batch > 0, "global_batch must be positive");
   PH_CUDA_OK(cudaSetDevice(ctx->device));
   ctx->job_valid = false;
   const ph_host_ctx::Job& J = ctx->job;
-  PH_CUDA_OK(cudaMemcpyAsync(J.d_ssum, &ssum_global, sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
-  int rc = ph_hellinger_finish(J.d_ssum, global_batch, J.d_loss, ctx->s_compute);
+  int rc;
+  if (comm != nullptr) {  // sum over the ranks on the device, over peer memory: no host round trip
+    rc = ph_comm_allreduce_sum_f64(comm, J.d_ssum, 1, ctx->s_compute);
+    if (rc != PH_OK) return rc;
+  } else {
+    PH_CUDA_OK(cudaMemcpyAsync(J.d_ssum, &ssum_global, sizeof(double), cudaMemcpyHostToDevice, ctx->s_compute));
+  }
+  rc = ph_hellinger_finish(J.d_ssum, global_batch, J.d_loss, ctx->s_compute);
   if (rc != PH_OK) return rc;
   PH_CUDA_OK(cudaMemcpyAsync(loss_host, J.d_loss, sizeof(float), cudaMemcpyDeviceToHost, ctx->s_compute));
   // ---- phase 2: scale the stored unit gradient by 1 / (B sqrt(S)); it either stays on the device (the consumer
@@ -339,6 +352,17 @@ int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_bat
   return PH_OK;
 }
 
+int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_batch, float* loss_host,
+                        float* grad_fake_host, float* grad_fake_device) {
+  return host_hist_finish_impl(ctx, nullptr, ssum_global, global_batch, loss_host, grad_fake_host, grad_fake_device);
+}
+
+int ph_host_hist_finish_comm(ph_host_ctx* ctx, ph_comm* comm, int64_t global_batch, float* loss_host,
+                             float* grad_fake_host, float* grad_fake_device) {
+  PH_CHECK_ARG(comm != nullptr, "comm must not be NULL");
+  return host_hist_finish_impl(ctx, comm, 0.0, global_batch, loss_host, grad_fake_host, grad_fake_device);
+}
+
 int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
                       int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
                       float sigma_sqr, float epsilon, int impl, float* loss_host, float* grad_fake_host) {
@@ -354,26 +378,28 @@ int ph_host_hist_loss(ph_host_ctx* ctx, const float* real_host, const float* fak
 // source / target as int32 (elem_bytes 4) or as the decoded PNG's uint8 (elem_bytes 1: a quarter of the upload,
 // widened to int32 on the device)
 static int host_load_indexed(ph_host_ctx* ctx, const void* source_host, const void* target_host, int elem_bytes,
-                             int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
+                             int64_t batch, int64_t npix, int ordering, const float* shuffle_keys_host,
+                             int32_t* source_indexed_host,
                              int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
                              float* target_one_hot_host) {
   PH_CHECK_ARG(ctx && source_host && target_host && source_indexed_host && target_indexed_host && palette_host &&
                    ncolors_host,
                "NULL pointer argument");
   PH_CHECK_ARG(batch > 0 && npix > 0, "bad shape");
+  PH_CHECK_ARG(ordering != PH_ORDER_SHUFFLED || shuffle_keys_host != nullptr, "'shuffled' ordering needs shuffle keys");
   PH_CUDA_OK(cudaSetDevice(ctx->device));
   const size_t img = (size_t)batch * npix * 4;
   const int depth = PH_MAX_PALETTE_SIZE;
   for (int pass = 0; pass < 2; ++pass) {
     Carver cv(pass == 0 ? nullptr : ctx->arena);
-    int32_t* d_src = cv.take<int32_t>(img);
-    int32_t* d_tgt = cv.take<int32_t>(img);
-    uint8_t* d_src8 = elem_bytes == 1 ? cv.take<uint8_t>(img) : nullptr;
-    uint8_t* d_tgt8 = elem_bytes == 1 ? cv.take<uint8_t>(img) : nullptr;
+    // pixels in the element type the caller has them in: the kernel reads uint8 RGBA as it is (4 B per pixel)
+    void* d_src = cv.take<char>(img * elem_bytes);
+    void* d_tgt = cv.take<char>(img * elem_bytes);
     int32_t* d_sidx = cv.take<int32_t>((size_t)batch * npix);
     int32_t* d_tidx = cv.take<int32_t>((size_t)batch * npix);
     int32_t* d_pal = cv.take<int32_t>((size_t)batch * depth * 4);
     int32_t* d_nc = cv.take<int32_t>((size_t)batch);
+    float* d_keys = ordering == PH_ORDER_SHUFFLED ? cv.take<float>((size_t)batch * depth) : nullptr;
     float* d_oh = target_one_hot_host ? cv.take<float>((size_t)batch * npix * depth) : nullptr;
     if (pass == 0) {
       int rc = ensure_arena(ctx, align_up(cv.off, 256) + 256);
@@ -382,17 +408,16 @@ static int host_load_indexed(ph_host_ctx* ctx, const void* source_host, const vo
     }
     cudaStream_t st = ctx->s_compute;
     int rc;
-    if (elem_bytes == 1) {
-      PH_CUDA_OK(cudaMemcpyAsync(d_src8, source_host, img, cudaMemcpyHostToDevice, st));
-      PH_CUDA_OK(cudaMemcpyAsync(d_tgt8, target_host, img, cudaMemcpyHostToDevice, st));
-      rc = launch_u8_to_i32_image(d_src8, (int64_t)batch * npix, d_src, st);
-      if (rc == PH_OK) rc = launch_u8_to_i32_image(d_tgt8, (int64_t)batch * npix, d_tgt, st);
-      if (rc != PH_OK) return rc;
-    } else {
-      PH_CUDA_OK(cudaMemcpyAsync(d_src, source_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      PH_CUDA_OK(cudaMemcpyAsync(d_tgt, target_host, img * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    }
-    rc = ph_load_indexed_images(d_src, d_tgt, batch, npix, ordering, d_sidx, d_tidx, d_pal, d_nc, st);
+    PH_CUDA_OK(cudaMemcpyAsync(d_src, source_host, img * elem_bytes, cudaMemcpyHostToDevice, st));
+    PH_CUDA_OK(cudaMemcpyAsync(d_tgt, target_host, img * elem_bytes, cudaMemcpyHostToDevice, st));
+    if (d_keys)
+      PH_CUDA_OK(cudaMemcpyAsync(d_keys, shuffle_keys_host, (size_t)batch * depth * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (elem_bytes == 1)
+      rc = ph_load_indexed_images_u8(static_cast<const uint8_t*>(d_src), static_cast<const uint8_t*>(d_tgt), batch, npix,
+                                     ordering, d_keys, d_sidx, d_tidx, d_pal, d_nc, st);
+    else
+      rc = ph_load_indexed_images(static_cast<const int32_t*>(d_src), static_cast<const int32_t*>(d_tgt), batch, npix,
+                                  ordering, d_keys, d_sidx, d_tidx, d_pal, d_nc, st);
     if (rc != PH_OK) return rc;
     if (d_oh) {
       rc = ph_one_hot(d_tidx, batch * npix, depth, d_oh, st);
@@ -412,18 +437,18 @@ static int host_load_indexed(ph_host_ctx* ctx, const void* source_host, const vo
 extern "C" {
 
 int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,
-                                int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
-                                int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
-                                float* target_one_hot_host) {
-  return host_load_indexed(ctx, source_host, target_host, 4, batch, npix, ordering, source_indexed_host,
+                                int64_t batch, int64_t npix, int ordering, const float* shuffle_keys_host,
+                                int32_t* source_indexed_host, int32_t* target_indexed_host, int32_t* palette_host,
+                                int32_t* ncolors_host, float* target_one_hot_host) {
+  return host_load_indexed(ctx, source_host, target_host, 4, batch, npix, ordering, shuffle_keys_host, source_indexed_host,
                            target_indexed_host, palette_host, ncolors_host, target_one_hot_host);
 }
 
 int ph_host_load_indexed_images_u8(ph_host_ctx* ctx, const uint8_t* source_host, const uint8_t* target_host,
-                                   int64_t batch, int64_t npix, int ordering, int32_t* source_indexed_host,
-                                   int32_t* target_indexed_host, int32_t* palette_host, int32_t* ncolors_host,
-                                   float* target_one_hot_host) {
-  return host_load_indexed(ctx, source_host, target_host, 1, batch, npix, ordering, source_indexed_host,
+                                   int64_t batch, int64_t npix, int ordering, const float* shuffle_keys_host,
+                                   int32_t* source_indexed_host, int32_t* target_indexed_host, int32_t* palette_host,
+                                   int32_t* ncolors_host, float* target_one_hot_host) {
+  return host_load_indexed(ctx, source_host, target_host, 1, batch, npix, ordering, shuffle_keys_host, source_indexed_host,
                            target_indexed_host, palette_host, ncolors_host, target_one_hot_host);
 }
 

@@ -26,32 +26,54 @@ __device__ __forceinline__ unsigned hash_slot(unsigned key) {
 }
 
 // =============================================================================================
-// extract_palette: one CTA per image.
+// extract_palette: one CTA (512 threads) per image.
 //   1. every row (pixel) is packed to a 32-bit key; lanes holding the same key elect the lane with
 //      the earliest row (warp match) and only that lane touches the hash table;
 //   2. the table keeps (key, earliest row) per colour  -> first-occurrence order of
 //      UniqueWithCountsV2 (io_utils.py:46-57);
 //   3. entries are ranked by earliest row, and for "grayness" re-ranked by the float32 key
 //      ((r*0.2989+g*0.5870)+b*0.1140)+a*0 with ties broken by first occurrence = stable argsort
-//      (io_utils.py:51-55);
+//      (io_utils.py:51-55); "shuffled" (io_utils.py:56-58) re-ranks by caller-provided random keys the same way;
 //   4. rows n..255 are INVALID_INDEX_COLOR (io_utils.py:61-63, configuration.py:32).
+// The pass is a chain load -> match -> hash per row, so what bounds it is how many loads are in flight: every thread
+// issues FOUR independent loads before it touches the table (a batch of 2048 rows per CTA), and when the image fits
+// (rows <= 512 x 16 = 8192: a 64 x 64 source||target pair exactly) the packed keys stay in registers, so the index
+// pass of the fused variant reads no pixel a second time.
 // =============================================================================================
-constexpr int PAL_THREADS = 256;
+constexpr int PAL_THREADS = 512;
 constexpr int PAL_HASH_BITS = 11;
 constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;
 constexpr int PAL_MAX = PH_MAX_PALETTE_SIZE;
+constexpr int PAL_INFLIGHT = 4;                           // loads in flight per thread
+constexpr int PAL_BATCH = PAL_THREADS * PAL_INFLIGHT;     // rows per batch
+constexpr int PAL_KEEP = 16;                              // keys a thread keeps in registers (cached variant)
+
+// U8: pixels are the decoded PNG's uint8 RGBA (4 B, already the packed key); otherwise int32 RGBA (16 B).
+template <bool U8>
+__device__ __forceinline__ unsigned load_pixel_key(const void* src0, const void* src1, int64_t r, bool& bad) {
+  // src1 != nullptr: rows interleave source/target pixels (dataset_utils.py:142-145)
+  const void* base = (src1 != nullptr && (r & 1)) ? src1 : src0;
+  const int64_t i = src1 != nullptr ? (r >> 1) : r;
+  if (U8) return __ldg(static_cast<const unsigned*>(base) + i);
+  const int4 c = __ldg(static_cast<const int4*>(base) + i);
+  if (!in_byte_range(c)) bad = true;
+  return pack_rgba(c);
+}
 
 // FUSED_INDEX: also index both images of the pair from the same CTA-resident table
 // (dataset_utils.py:148-149 in the same launch): after the colours are ranked, each table slot is
 // rewritten to (key, final palette index) and every pixel is looked up with one probe.
-template <bool FUSED_INDEX>
+// CACHED: rows <= PAL_THREADS * PAL_KEEP, the keys of the thread's rows stay in registers.
+template <bool FUSED_INDEX, bool U8, bool CACHED>
 __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
-    const int4* __restrict__ image, const int4* __restrict__ image2, int64_t rows, int ordering,
-    int4* __restrict__ palette, int* __restrict__ ncolors, int* __restrict__ indexed, int* __restrict__ indexed2) {
+    const void* __restrict__ image, const void* __restrict__ image2, int64_t rows, int ordering,
+    const float* __restrict__ shuffle_keys, int4* __restrict__ palette, int* __restrict__ ncolors,
+    int* __restrict__ indexed, int* __restrict__ indexed2) {
   __shared__ unsigned long long table[PAL_HASH_SIZE];
   __shared__ unsigned long long entries[PAL_MAX];
   __shared__ unsigned first_order[PAL_MAX];  // keys in first-occurrence order
-  __shared__ float gray[PAL_MAX];
+  __shared__ float gray[PAL_MAX];            // secondary sort key in first-occurrence order
+  __shared__ int final_rank[PAL_MAX];        // palette row of the colour with first-occurrence rank i
   __shared__ int s_count, s_bad, s_n;
 
   const int64_t b = blockIdx.x;
@@ -60,48 +82,60 @@ __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
   if (tid == 0) { s_count = 0; s_bad = 0; s_n = 0; }
   __syncthreads();
 
-  // image2 != nullptr: rows interleave source/target pixels (dataset_utils.py:142-145)
   const int64_t per_image = image2 ? rows / 2 : rows;
-  const int4* src0 = image + b * per_image;
-  const int4* src1 = image2 ? image2 + b * per_image : nullptr;
+  const size_t px_bytes = U8 ? 4 : 16;
+  const void* src0 = static_cast<const char*>(image) + (size_t)b * per_image * px_bytes;
+  const void* src1 = image2 ? static_cast<const char*>(image2) + (size_t)b * per_image * px_bytes : nullptr;
   const bool reversed = ordering == PH_ORDER_BOTTOM2TOP;
 
-  const int64_t rows_padded = (rows + 31) / 32 * 32;
-  for (int64_t r = tid; r < rows_padded; r += PAL_THREADS) {
-    const bool active = r < rows;
-    unsigned key = 0;
-    unsigned pos = 0xffffffffu;
-    if (active) {
-      int4 c;
-      if (src1) c = __ldg(((r & 1) ? src1 : src0) + (r >> 1));
-      else c = __ldg(src0 + r);
-      if (!in_byte_range(c)) s_bad = 1;
-      key = pack_rgba(c);
-      pos = (unsigned)(reversed ? rows - 1 - r : r);
+  unsigned kept[CACHED ? PAL_KEEP : 1];
+  bool bad = false;
+  // one batch: PAL_INFLIGHT independent loads per thread, then the match / hash step of each row
+  auto insert_batch = [&](const int64_t bt, unsigned* keep) {
+    unsigned key[PAL_INFLIGHT];
+#pragma unroll
+    for (int k = 0; k < PAL_INFLIGHT; ++k) {
+      const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
+      key[k] = r < rows ? load_pixel_key<U8>(src0, src1, r, bad) : 0u;
+      if (keep != nullptr) keep[k] = key[k];
     }
-    // warp de-duplication: among lanes with the same colour keep the one with the earliest row
-    const unsigned amask = __ballot_sync(0xffffffffu, active);
-    if (!active) continue;
-    const unsigned peers = __match_any_sync(amask, key);
-    const int leader = reversed ? 31 - __clz(peers) : __ffs(peers) - 1;
-    if (lane != leader) continue;
-    if (*(volatile int*)&s_count > PAL_MAX) continue;  // already overflowed: result is "too many"
-
-    const unsigned long long word = ((unsigned long long)key << 32) | pos;
-    unsigned h = hash_slot<PAL_HASH_BITS>(key);
-    for (int probe = 0; probe < PAL_HASH_SIZE; ++probe) {
-      unsigned long long cur = *(volatile unsigned long long*)&table[h];
-      if (cur == SLOT_EMPTY) {
-        cur = atomicCAS(&table[h], SLOT_EMPTY, word);
-        if (cur == SLOT_EMPTY) { atomicAdd(&s_count, 1); break; }
+#pragma unroll
+    for (int k = 0; k < PAL_INFLIGHT; ++k) {
+      const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
+      const bool active = r < rows;
+      // warp de-duplication: among lanes with the same colour keep the one with the earliest row
+      const unsigned amask = __ballot_sync(0xffffffffu, active);
+      if (!active) continue;
+      const unsigned peers = __match_any_sync(amask, key[k]);
+      const int leader = reversed ? 31 - __clz(peers) : __ffs(peers) - 1;
+      if (lane != leader) continue;
+      if (*(volatile int*)&s_count > PAL_MAX) continue;  // already overflowed: result is "too many"
+      const unsigned pos = (unsigned)(reversed ? rows - 1 - r : r);
+      const unsigned long long word = ((unsigned long long)key[k] << 32) | pos;
+      unsigned h = hash_slot<PAL_HASH_BITS>(key[k]);
+      for (int probe = 0; probe < PAL_HASH_SIZE; ++probe) {
+        unsigned long long cur = *(volatile unsigned long long*)&table[h];
+        if (cur == SLOT_EMPTY) {
+          cur = atomicCAS(&table[h], SLOT_EMPTY, word);
+          if (cur == SLOT_EMPTY) { atomicAdd(&s_count, 1); break; }
+        }
+        if ((unsigned)(cur >> 32) == key[k]) {
+          if ((unsigned)cur > pos) atomicMin(&table[h], word);
+          break;
+        }
+        h = (h + 1) & (PAL_HASH_SIZE - 1);
       }
-      if ((unsigned)(cur >> 32) == key) {
-        if ((unsigned)cur > pos) atomicMin(&table[h], word);
-        break;
-      }
-      h = (h + 1) & (PAL_HASH_SIZE - 1);
     }
+  };
+  if (CACHED) {
+#pragma unroll
+    for (int bt = 0; bt < PAL_KEEP / PAL_INFLIGHT; ++bt) insert_batch(bt, &kept[bt * PAL_INFLIGHT]);  // rows beyond the image: inactive
+  } else {
+    const int64_t nbatch = (rows + PAL_BATCH - 1) / PAL_BATCH;
+#pragma unroll 1
+    for (int64_t bt = 0; bt < nbatch; ++bt) insert_batch(bt, nullptr);
   }
+  if (bad) s_bad = 1;
   __syncthreads();
 
   const int count = s_count;
@@ -131,65 +165,84 @@ __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
     for (int e = 0; e < n; ++e) rank += ((unsigned)entries[e] < mypos) ? 1 : 0;
     const unsigned key = (unsigned)(me >> 32);
     first_order[rank] = key;
-    const int4 c = unpack_rgba(key);
-    // float32, non-fused, left to right: the (n,4)x(4,1) product of io_utils.py:51-52
-    float g = __fmul_rn((float)c.x, 0.2989f);
-    g = __fadd_rn(g, __fmul_rn((float)c.y, 0.5870f));
-    g = __fadd_rn(g, __fmul_rn((float)c.z, 0.1140f));
-    g = __fadd_rn(g, __fmul_rn((float)c.w, 0.0f));
+    float g = 0.f;
+    if (ordering == PH_ORDER_GRAYNESS) {
+      const int4 c = unpack_rgba(key);
+      // float32, non-fused, left to right: the (n,4)x(4,1) product of io_utils.py:51-52
+      g = __fmul_rn((float)c.x, 0.2989f);
+      g = __fadd_rn(g, __fmul_rn((float)c.y, 0.5870f));
+      g = __fadd_rn(g, __fmul_rn((float)c.z, 0.1140f));
+      g = __fadd_rn(g, __fmul_rn((float)c.w, 0.0f));
+    } else if (ordering == PH_ORDER_SHUFFLED) {
+      // tf.random.shuffle(colors): rank by independent uniform keys = a uniformly random permutation of the rows
+      g = __ldg(shuffle_keys + b * PAL_MAX + rank);
+    }
     gray[rank] = g;
   }
   __syncthreads();
 
   const int4 filler = make_int4(255, 0, 220, 255);
   int4* out = palette + b * PAL_MAX;
-  if (ordering == PH_ORDER_GRAYNESS && n > 1) {
-    if (tid < n) {
+  if (tid < n) {
+    int rank = tid;
+    if ((ordering == PH_ORDER_GRAYNESS || ordering == PH_ORDER_SHUFFLED) && n > 1) {
       const float mine = gray[tid];
-      int rank = 0;
+      rank = 0;
       for (int e = 0; e < n; ++e) {
         const float other = gray[e];
-        rank += (other < mine || (other == mine && e < tid)) ? 1 : 0;
+        rank += (other < mine || (other == mine && e < tid)) ? 1 : 0;  // stable
       }
-      out[rank] = unpack_rgba(first_order[tid]);
     }
-  } else {
-    if (tid < n) out[tid] = unpack_rgba(first_order[tid]);
+    out[rank] = unpack_rgba(first_order[tid]);
+    final_rank[tid] = rank;
   }
   for (int k = n + tid; k < PAL_MAX; k += PAL_THREADS) out[k] = filler;
   if (tid == 0) ncolors[b] = n;
 
   if (FUSED_INDEX) {
-    // final index of each colour -> its table slot (low word); first_order[] is reused as scratch
+    // final index of each colour -> its table slot (low word)
     __syncthreads();
     if (tid < n) {
-      int final_rank = tid;
-      if (ordering == PH_ORDER_GRAYNESS && n > 1) {
-        const float mine = gray[tid];
-        final_rank = 0;
-        for (int e = 0; e < n; ++e) {
-          const float other = gray[e];
-          final_rank += (other < mine || (other == mine && e < tid)) ? 1 : 0;
-        }
-      }
       const unsigned key = first_order[tid];
       unsigned h = hash_slot<PAL_HASH_BITS>(key);
       while ((unsigned)(table[h] >> 32) != key || table[h] == SLOT_EMPTY) h = (h + 1) & (PAL_HASH_SIZE - 1);
-      table[h] = ((unsigned long long)key << 32) | (unsigned)final_rank;
+      table[h] = ((unsigned long long)key << 32) | (unsigned)final_rank[tid];
     }
     __syncthreads();
     // a pixel equal to the filler colour also matches every padding row: scatter_nd adds them (io_utils.py:84-91)
     const unsigned filler_key = pack_rgba(filler);
     const int filler_extra = (PAL_MAX * (PAL_MAX - 1) - n * (n - 1)) / 2;  // sum of n..255
-    for (int64_t r = tid; r < rows; r += PAL_THREADS) {
-      const int4 c = __ldg(((r & 1) ? src1 : src0) + (r >> 1));
-      const unsigned key = pack_rgba(c);
+    auto lookup = [&](unsigned key) {
       unsigned h = hash_slot<PAL_HASH_BITS>(key);
       unsigned long long w = table[h];
       while ((unsigned)(w >> 32) != key || w == SLOT_EMPTY) { h = (h + 1) & (PAL_HASH_SIZE - 1); w = table[h]; }
       int idx = (int)(unsigned)w;
       if (key == filler_key) idx += filler_extra;
-      ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = idx;
+      return idx;
+    };
+    if (CACHED) {
+#pragma unroll
+      for (int i = 0; i < PAL_KEEP; ++i) {
+        const int64_t r = (int64_t)(i / PAL_INFLIGHT) * PAL_BATCH + (i % PAL_INFLIGHT) * PAL_THREADS + tid;
+        if (r < rows) ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(kept[i]);
+      }
+    } else {
+      bool ignore = false;
+      const int64_t nbatch = (rows + PAL_BATCH - 1) / PAL_BATCH;
+#pragma unroll 1
+      for (int64_t bt = 0; bt < nbatch; ++bt) {  // the second read of the pixels (L2), four loads in flight again
+        unsigned key[PAL_INFLIGHT];
+#pragma unroll
+        for (int k = 0; k < PAL_INFLIGHT; ++k) {
+          const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
+          key[k] = r < rows ? load_pixel_key<U8>(src0, src1, r, ignore) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < PAL_INFLIGHT; ++k) {
+          const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
+          if (r < rows) ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(key[k]);
+        }
+      }
     }
   }
 }
@@ -459,25 +512,51 @@ __global__ void __launch_bounds__(256) u8_to_float_image_kernel(const uchar4* __
   }
 }
 
-// decoded PNG pixels (uint8 RGBA) -> the int32 pixels the palette kernels read (`tf.cast(image, "int32")`,
-// dataset_utils.py:140-141): lets a host caller upload 4 B per pixel instead of 16
-__global__ void __launch_bounds__(256) u8_to_i32_image_kernel(const uchar4* __restrict__ src, int64_t npixels,
-                                                              int4* __restrict__ dst) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npixels; i += stride) {
-    const uchar4 q = __ldg(src + i);
-    dst[i] = make_int4(q.x, q.y, q.z, q.w);
+// The loader's pixel helpers as standalone tensor ops (dataset_utils.py:11-20 blacken_transparent_pixels, :39-48
+// normalize, :51-60 denormalize): float32 RGBA pixels, 16 B in and 16 B out per thread and iteration.
+template <int OP>
+__device__ __forceinline__ float4 pixel_map_op(float4 q) {
+  if (OP == PH_MAP_BLACKEN) {
+    if (q.w == 0.f) q = make_float4(0.f, 0.f, 0.f, 0.f);  // tf.where(alpha == 0, zeros, image); -0.0 == 0 as in TF
+  } else if (OP == PH_MAP_NORMALIZE) {
+    q.x = __fsub_rn(__fdiv_rn(q.x, 127.5f), 1.0f); q.y = __fsub_rn(__fdiv_rn(q.y, 127.5f), 1.0f);
+    q.z = __fsub_rn(__fdiv_rn(q.z, 127.5f), 1.0f); q.w = __fsub_rn(__fdiv_rn(q.w, 127.5f), 1.0f);
+  } else {
+    q.x = __fmul_rn(__fadd_rn(q.x, 1.0f), 127.5f); q.y = __fmul_rn(__fadd_rn(q.y, 1.0f), 127.5f);
+    q.z = __fmul_rn(__fadd_rn(q.z, 1.0f), 127.5f); q.w = __fmul_rn(__fadd_rn(q.w, 1.0f), 127.5f);
+  }
+  return q;
+}
+template <int OP>
+__global__ void __launch_bounds__(256) pixel_map_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ out) {
+  const int64_t n4 = n >> 2, stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) {
+    for (int64_t i = t; i < n4; i += stride)
+      reinterpret_cast<float4*>(out)[i] = pixel_map_op<OP>(__ldg(reinterpret_cast<const float4*>(in) + i));
+  } else {
+    for (int64_t i = t; i < n4; i += stride) {
+      const float4 q = pixel_map_op<OP>(make_float4(in[4 * i], in[4 * i + 1], in[4 * i + 2], in[4 * i + 3]));
+      out[4 * i] = q.x; out[4 * i + 1] = q.y; out[4 * i + 2] = q.z; out[4 * i + 3] = q.w;
+    }
+  }
+  if (OP != PH_MAP_BLACKEN && t < (n & 3)) {  // tail of an element count that is not a multiple of four
+    const float4 q = pixel_map_op<OP>(make_float4(in[4 * n4 + t], 0.f, 0.f, 1.f));
+    out[4 * n4 + t] = q.x;
   }
 }
 
-int launch_u8_to_i32_image(const uint8_t* src, int64_t npixels, int32_t* dst, cudaStream_t st) {
-  if (npixels == 0) return PH_OK;
-  int64_t grid = ceil_div(npixels, 256 * 4);
+int launch_pixel_map(const float* in, int64_t n, int op, float* out, cudaStream_t st) {
+  if (n == 0) return PH_OK;
+  int64_t grid = ceil_div(ceil_div(n, 4), 256 * 4);
   const int64_t cap = (int64_t)cached_sm_count() * 16;
   if (grid > cap) grid = cap;
-  u8_to_i32_image_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const uchar4*>(src), npixels,
-                                                         reinterpret_cast<int4*>(dst));
-  PH_LAUNCH_OK("u8_to_i32_image_kernel");
+  if (grid < 1) grid = 1;
+  if (op == PH_MAP_BLACKEN) pixel_map_kernel<PH_MAP_BLACKEN><<<(unsigned)grid, 256, 0, st>>>(in, n, out);
+  else if (op == PH_MAP_NORMALIZE) pixel_map_kernel<PH_MAP_NORMALIZE><<<(unsigned)grid, 256, 0, st>>>(in, n, out);
+  else pixel_map_kernel<PH_MAP_DENORMALIZE><<<(unsigned)grid, 256, 0, st>>>(in, n, out);
+  PH_LAUNCH_OK("pixel_map_kernel");
   return PH_OK;
 }
 
@@ -609,30 +688,41 @@ int launch_augment_pair(const float* first, const float* second, int64_t batch, 
 // =============================================================================================
 // launchers
 // =============================================================================================
-int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows,
-                           int ordering, int32_t* palette, int32_t* ncolors, cudaStream_t st) {
+template <bool FUSED, bool U8>
+static int launch_extract_any(const void* image, const void* image2, int64_t batch, int64_t rows, int ordering,
+                              const float* shuffle_keys, int32_t* palette, int32_t* ncolors, int32_t* idx1,
+                              int32_t* idx2, cudaStream_t st) {
   PH_CHECK_ARG(batch < (1ll << 31), "batch too large");
   PH_CHECK_ARG(rows < (1ll << 31), "too many rows per image (%lld)", (long long)rows);
+  PH_CHECK_ARG(ordering != PH_ORDER_SHUFFLED || shuffle_keys != nullptr, "'shuffled' ordering needs shuffle keys");
   if (batch == 0) return PH_OK;
-  extract_palette_kernel<false><<<(unsigned)batch, PAL_THREADS, 0, st>>>(
-      reinterpret_cast<const int4*>(image), reinterpret_cast<const int4*>(image2), rows, ordering,
-      reinterpret_cast<int4*>(palette), ncolors, nullptr, nullptr);
-  PH_LAUNCH_OK("extract_palette_kernel");
+  if (rows <= (int64_t)PAL_THREADS * PAL_KEEP)
+    extract_palette_kernel<FUSED, U8, true><<<(unsigned)batch, PAL_THREADS, 0, st>>>(
+        image, image2, rows, ordering, shuffle_keys, reinterpret_cast<int4*>(palette), ncolors, idx1, idx2);
+  else
+    extract_palette_kernel<FUSED, U8, false><<<(unsigned)batch, PAL_THREADS, 0, st>>>(
+        image, image2, rows, ordering, shuffle_keys, reinterpret_cast<int4*>(palette), ncolors, idx1, idx2);
+  PH_LAUNCH_OK(FUSED ? "extract_palette_kernel<fused index>" : "extract_palette_kernel");
   return PH_OK;
 }
 
-// dataset_utils.py:138-151 in ONE launch: shared palette of source||target and both index images.
-int launch_load_indexed_fused(const int32_t* source, const int32_t* target, int64_t batch, int64_t npix,
-                              int ordering, int32_t* source_indexed, int32_t* target_indexed, int32_t* palette,
-                              int32_t* ncolors, cudaStream_t st) {
-  PH_CHECK_ARG(batch < (1ll << 31), "batch too large");
+int launch_extract_palette(const int32_t* image, const int32_t* image2, int64_t batch, int64_t rows, int ordering,
+                           const float* shuffle_keys, int32_t* palette, int32_t* ncolors, cudaStream_t st) {
+  return launch_extract_any<false, false>(image, image2, batch, rows, ordering, shuffle_keys, palette, ncolors, nullptr,
+                                          nullptr, st);
+}
+
+// dataset_utils.py:138-151 in ONE launch: shared palette of source||target and both index images.  elem_bytes 4:
+// int32 RGBA pixels; 1: the decoded PNG's uint8 RGBA (a quarter of the bytes, same results)
+int launch_load_indexed_fused(const void* source, const void* target, int elem_bytes, int64_t batch, int64_t npix,
+                              int ordering, const float* shuffle_keys, int32_t* source_indexed,
+                              int32_t* target_indexed, int32_t* palette, int32_t* ncolors, cudaStream_t st) {
   PH_CHECK_ARG(2 * npix < (1ll << 31), "too many pixels per image (%lld)", (long long)npix);
-  if (batch == 0) return PH_OK;
-  extract_palette_kernel<true><<<(unsigned)batch, PAL_THREADS, 0, st>>>(
-      reinterpret_cast<const int4*>(source), reinterpret_cast<const int4*>(target), 2 * npix, ordering,
-      reinterpret_cast<int4*>(palette), ncolors, source_indexed, target_indexed);
-  PH_LAUNCH_OK("extract_palette_kernel<fused index>");
-  return PH_OK;
+  if (elem_bytes == 1)
+    return launch_extract_any<true, true>(source, target, batch, 2 * npix, ordering, shuffle_keys, palette, ncolors,
+                                          source_indexed, target_indexed, st);
+  return launch_extract_any<true, false>(source, target, batch, 2 * npix, ordering, shuffle_keys, palette, ncolors,
+                                         source_indexed, target_indexed, st);
 }
 
 int launch_rgba_to_indexed(const int32_t* image, int64_t batch, int64_t npix, const int32_t* palette,

@@ -19,22 +19,38 @@ from ._tensor import from_any, ptr, require_cuda, stream_ptr, to_caller_framewor
 from .configuration import MAX_PALETTE_SIZE
 
 
+def _pixel_map(image, op, name):
+    """One launch of `ph_pixel_map` over a float32 CUDA tensor (integer tensors are cast first, as the reference's
+    callers do with `tf.cast(image, "float32")`, dataset_utils.py:72)."""
+    img = from_any(image, name=name)
+    if not img.is_cuda:
+        raise ValueError(f"{name} must live on a CUDA device (got {img.device}); there is no CPU fallback")
+    src = require_cuda(img if img.dtype == torch.float32 else img.to(torch.float32), torch.float32, name=name)
+    if op == "blacken" and (src.dim() == 0 or src.shape[-1] != 4):
+        raise ValueError(f"{name} must be RGBA (last dimension 4), got {tuple(src.shape)}")
+    out = torch.empty_like(src)
+    if src.numel():
+        with torch.cuda.device(src.device):
+            _lib.call("ph_pixel_map", ptr(src), src.numel(), _lib.MAP_OPS[op], ptr(out), stream_ptr(src.device))
+    if op == "blacken" and img.dtype != torch.float32:
+        out = out.to(img.dtype)  # blacken keeps the dtype of its argument (tf.where)
+    return to_caller_framework(out, image)
+
+
 def blacken_transparent_pixels(image):
-    """dataset_utils.py:11-20: pixels whose alpha is 0 become (0,0,0,0). (…,4) any dtype."""
-    img = from_any(image)
-    return to_caller_framework(torch.where(img[..., 3:4] == 0, torch.zeros_like(img), img), image)
+    """dataset_utils.py:11-20: pixels whose alpha is 0 become (0,0,0,0).  (…,4) CUDA tensor."""
+    return _pixel_map(image, "blacken", "image")
 
 
 def normalize(image):
-    """dataset_utils.py:39-48: [0,255] -> [-1,1].  The divisor is a device tensor: torch turns a division by a
-    python scalar into a multiplication by its reciprocal, which is 1 ulp away from TensorFlow's true division."""
-    img = from_any(image)
-    return to_caller_framework(img / torch.full((), 127.5, dtype=img.dtype, device=img.device) - 1, image)
+    """dataset_utils.py:39-48: [0,255] -> [-1,1] as a true division by 127.5 and a subtraction (TensorFlow's two
+    roundings; a multiplication by the reciprocal is 1 ulp away)."""
+    return _pixel_map(image, "normalize", "image")
 
 
 def denormalize(image):
     """dataset_utils.py:51-60: [-1,1] -> [0,255]."""
-    return to_caller_framework((from_any(image) + 1) * 127.5, image)
+    return _pixel_map(image, "denormalize", "image")
 
 
 def load_image(image_u8, should_normalize=True):
@@ -196,12 +212,16 @@ def create_augmentation_with_prob(prob=0.8, *, generator=None, should_normalize=
     return augmentation_wrapper
 
 
-def load_indexed_images(source_image, target_image, palette_ordering="grayness", *, check=True):
+def load_indexed_images(source_image, target_image, palette_ordering="grayness", *, check=True, generator=None):
     """dataset_utils.py:138-151 for decoded images: `concat([source, target], -1)` -> `extract_palette`
-    -> `rgba_to_indexed` twice with the shared palette.  (H,W,4) or (B,H,W,4) int32 CUDA tensors.
-    Returns (source_indexed (…,H,W,1), target_indexed (…,H,W,1), palette (…,256,4))."""
-    src = require_cuda(from_any(source_image, name="source_image"), torch.int32, name="source_image")
-    tgt = require_cuda(from_any(target_image, name="target_image"), torch.int32, name="target_image")
+    -> `rgba_to_indexed` twice with the shared palette, in ONE launch.  (H,W,4) or (B,H,W,4) CUDA tensors, int32
+    (the reference's `tf.cast(image, "int32")`) or uint8 (the decoded PNG as it is: a quarter of the bytes read).
+    `palette_ordering="shuffled"` (io_utils.py:56-58) draws its permutation from `generator`.
+    Returns (source_indexed (…,H,W,1), target_indexed (…,H,W,1), palette (…,256,4)), all int32."""
+    src0 = from_any(source_image, name="source_image")
+    dt = torch.uint8 if src0.dtype == torch.uint8 else torch.int32
+    src = require_cuda(src0, dt, name="source_image")
+    tgt = require_cuda(from_any(target_image, name="target_image"), dt, name="target_image")
     if src.shape != tgt.shape:
         raise ValueError("source and target images must have the same shape")
     batched = src.dim() == 4
@@ -209,25 +229,20 @@ def load_indexed_images(source_image, target_image, palette_ordering="grayness",
         src, tgt = src.unsqueeze(0), tgt.unsqueeze(0)
     if src.dim() != 4 or src.shape[-1] != 4:
         raise ValueError(f"images must be (H,W,4) or (B,H,W,4), got {tuple(src.shape)}")
-    if palette_ordering == "shuffled":
-        # nondeterministic in the reference as well (io_utils.py:56-58): extract, permute, then index
-        cat = torch.cat([src, tgt], dim=-1)
-        palette = io_utils.extract_palette(cat, "shuffled", batched=True, check=True)
-        s_idx = io_utils.rgba_to_indexed(src, palette)
-        t_idx = io_utils.rgba_to_indexed(tgt, palette)
-    else:
-        b, h, w, _ = src.shape
-        s_idx = torch.empty((b, h, w, 1), dtype=torch.int32, device=src.device)
-        t_idx = torch.empty((b, h, w, 1), dtype=torch.int32, device=src.device)
-        palette = torch.empty((b, MAX_PALETTE_SIZE, 4), dtype=torch.int32, device=src.device)
-        ncolors = torch.empty((b,), dtype=torch.int32, device=src.device)
-        if b:
-            with torch.cuda.device(src.device):
-                _lib.call("ph_load_indexed_images", ptr(src), ptr(tgt), b, h * w,
-                          io_utils._ordering_id(palette_ordering), ptr(s_idx), ptr(t_idx), ptr(palette),
-                          ptr(ncolors), stream_ptr(src.device))
-        if check:
-            io_utils._check_ncolors(ncolors)
+    order = io_utils._ordering_id(palette_ordering)
+    b, h, w, _ = src.shape
+    keys = io_utils._shuffle_keys(b, src.device, generator) if palette_ordering == "shuffled" else None
+    s_idx = torch.empty((b, h, w, 1), dtype=torch.int32, device=src.device)
+    t_idx = torch.empty((b, h, w, 1), dtype=torch.int32, device=src.device)
+    palette = torch.empty((b, MAX_PALETTE_SIZE, 4), dtype=torch.int32, device=src.device)
+    ncolors = torch.empty((b,), dtype=torch.int32, device=src.device)
+    if b:
+        with torch.cuda.device(src.device):
+            _lib.call("ph_load_indexed_images_u8" if dt == torch.uint8 else "ph_load_indexed_images", ptr(src), ptr(tgt),
+                      b, h * w, order, ptr(keys), ptr(s_idx), ptr(t_idx), ptr(palette), ptr(ncolors),
+                      stream_ptr(src.device))
+    if check:
+        io_utils._check_ncolors(ncolors)
     if not batched:
         s_idx, t_idx, palette = s_idx[0], t_idx[0], palette[0]
     return (to_caller_framework(s_idx, source_image), to_caller_framework(t_idx, source_image),

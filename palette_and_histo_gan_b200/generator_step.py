@@ -137,11 +137,14 @@ class Pix2PixHistogramStep:
         self.g_opt = torch.optim.Adam(self.generator.parameters(), lr=2e-4, betas=(0.5, 0.999), eps=1e-7)
         self.d_opt = torch.optim.Adam(self.discriminator.parameters(), lr=2e-4, betas=(0.5, 0.999), eps=1e-7)
 
-    def generator_loss(self, fake_predicted, fake_image, real_image):
+    def generator_loss(self, fake_predicted, fake_image, real_image, global_batch=None):
+        """`global_batch`: the whole batch over all ranks; None = equal shards (local batch x world size)."""
         adversarial = F.binary_cross_entropy_with_logits(fake_predicted, torch.ones_like(fake_predicted))
         l1 = (real_image - fake_image).abs().mean()
+        if global_batch is None:
+            global_batch = real_image.shape[0] * self.world
         hist = histogram.histogram_loss(real_image, fake_image, group=True if self.distributed else None,
-                                        impl=self.impl)
+                                        global_batch=global_batch, impl=self.impl)
         total = adversarial + self.lambda_l1 * l1 + self.lambda_histogram * hist
         return total, adversarial, l1, hist
 
@@ -151,8 +154,9 @@ class Pix2PixHistogramStep:
         fake = F.binary_cross_entropy_with_logits(fake_predicted, torch.zeros_like(fake_predicted))
         return fake + real, real, fake
 
-    def train_step(self, source_image, real_image):
-        """One optimisation step on a (source, real) batch of NHWC float32 images in [-1, 1].  Returns the loss
+    def train_step(self, source_image, real_image, global_batch=None):
+        """One optimisation step on a (source, real) batch of NHWC float32 images in [-1, 1] (`global_batch`: the
+        whole batch over all ranks when the shards are unequal, e.g. the last batch of an epoch).  Returns the loss
         terms as python floats-to-be (0-dim tensors, no host synchronisation)."""
         self.generator.train()
         self.discriminator.train()
@@ -162,7 +166,7 @@ class Pix2PixHistogramStep:
         for p in self.discriminator.parameters():
             p.requires_grad_(False)
         fake_predicted = self.discriminator(fake_image, source_image)
-        g_total, g_adv, g_l1, g_hist = self.generator_loss(fake_predicted, fake_image, real_image)
+        g_total, g_adv, g_l1, g_hist = self.generator_loss(fake_predicted, fake_image, real_image, global_batch)
         # the histogram term is one function of every rank's shard; DDP averages gradients (module docstring)
         backward_total = g_total + (self.world - 1) * self.lambda_histogram * g_hist
         self.g_opt.zero_grad(set_to_none=True)

@@ -12,8 +12,9 @@ Inputs are CUDA tensors of any DLPack-speaking framework (see `_tensor.py`); out
 tensors (TensorFlow tensors when the input was one).  Gradients flow through torch autograd:
 `calculate_rgbuv_histogram` and `hellinger_loss` are `autograd.Function`s whose backward passes are
 the analytic kernels of libpalhist (the reference relies on TF autodiff, pix2pix_model.py:78).
-When the batch is sharded over ranks (`group=`), the only exchange is the all-reduce of the scalar
-sum of squares that the Hellinger distance takes over the whole batch (histogram.py:88-89).
+When the batch is sharded over ranks (`group=`), the only exchange is the sum over ranks of the scalar
+sum of squares that the Hellinger distance takes over the whole batch (histogram.py:88-89): one 32-thread
+kernel over NVLink peer memory (`_comm.py`; an NCCL all-reduce where the ranks cannot map each other's memory).
 """
 from __future__ import annotations
 
@@ -134,13 +135,24 @@ def _finish(ssum, global_batch):
 
 
 def _reduce_over_ranks(ssum, local_batch, group, global_batch):
-    """All-reduce the one scalar that couples the shards; returns the whole-batch size."""
+    """Sum the one scalar that couples the shards over the ranks (in place); returns the whole-batch size.
+    On CUDA tensors of an NCCL group this is the peer-memory kernel of `_comm.py`; otherwise (gloo on the CPU in
+    the tests, ranks without P2P access) `torch.distributed.all_reduce`.  Without `global_batch` the shards are
+    taken to be equal (pass it when they are not: the last partial batch of an epoch)."""
     if group is None or group is False:
         return local_batch if global_batch is None else int(global_batch)
     import torch.distributed as dist
 
     pg = None if group is True else group
-    dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=pg)
+    comm = None
+    if ssum.is_cuda:
+        from ._comm import peer_comm
+
+        comm = peer_comm(group, ssum.device)
+    if comm is not None:
+        comm.allreduce_(ssum)
+    else:
+        dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=pg)
     if global_batch is not None:
         return int(global_batch)
     return local_batch * dist.get_world_size(pg)  # equal shards
@@ -188,46 +200,21 @@ class _HellingerFn(torch.autograd.Function):
 class _HistogramLossFn(torch.autograd.Function):
     """fwd(real) + fwd(fake) + Hellinger, backward to the fake image only (pix2pix_model.py:243-245).
 
-    Sharded batches: the only exchange is the all-reduce of the sum of squares S.  The gradient is
-    (S-independent per-pixel terms) / (2*sqrt2*B*sqrt(S)), so the backward kernels are launched right away
-    with this rank's S while the all-reduce is in flight, and the result is corrected by sqrt(S_local/S_global)
-    in the single elementwise pass that also applies the upstream scalar: the NVLink latency of the
-    collective hides behind the contraction instead of idling the GPU."""
+    Sharded batches: the only exchange is the sum over ranks of the sum of squares S, enqueued on the same stream
+    right behind the forward kernel that produced this rank's share (a ~3 us peer-memory kernel), so the backward
+    kernels read the whole-batch S like the single-device path does — same arithmetic, no correction pass."""
 
     @staticmethod
     def forward(ctx, real, fake, dom, method_id, sigma_sqr, impl, group, global_batch, dedup_real):
         hist_real, _ = _forward(real, dom, method_id, sigma_sqr, impl | (DEDUP_FLAG if dedup_real else 0))
         hist_fake, denom_fake, ssum = _forward_ssum(fake, dom, method_id, sigma_sqr, impl, hist_real)
-        sharded = group is not None and group is not False
-        overlap = False
-        if sharded and ctx.needs_input_grad[1]:
-            import torch.distributed as dist
-
-            pg = None if group is True else group
-            # worth one extra elementwise pass over the gradient once the collective's latency exceeds it
-            overlap = dist.get_world_size(pg) >= OVERLAP_MIN_WORLD
-        if overlap:
-            gb = int(global_batch) if global_batch is not None else real.shape[0] * dist.get_world_size(pg)
-            ssum_global = ssum.clone()
-            work = dist.all_reduce(ssum_global, op=dist.ReduceOp.SUM, group=pg, async_op=True)
-            grad = _backward(fake, dom, method_id, sigma_sqr, impl, hist_fake, denom_fake, hist_true=hist_real,
-                             ssum=ssum, global_batch=gb, loss_scale=None)  # overlaps the collective
-            work.wait()
-            corr = torch.sqrt(ssum / ssum_global).to(torch.float32)
-            ctx.save_for_backward(grad, corr)
-            ctx.eager = True
-            return _finish(ssum_global, gb)
         gb = _reduce_over_ranks(ssum, real.shape[0], group, global_batch)
         ctx.save_for_backward(fake, dom, hist_real, hist_fake, denom_fake, ssum)
         ctx.conf = (method_id, sigma_sqr, impl, gb)
-        ctx.eager = False
         return _finish(ssum, gb)
 
     @staticmethod
     def backward(ctx, grad_loss):
-        if ctx.eager:
-            grad, corr = ctx.saved_tensors
-            return None, grad * (grad_loss.to(torch.float32) * corr), None, None, None, None, None, None, None
         fake, dom, hist_real, hist_fake, denom_fake, ssum = ctx.saved_tensors
         method_id, sigma_sqr, impl, gb = ctx.conf
         scale = grad_loss.to(torch.float32).contiguous()
@@ -240,7 +227,6 @@ class _HistogramLossFn(torch.autograd.Function):
 # public API — reference signatures
 # ------------------------------------------------------------------------------------------------
 DEDUP_FLAG = 8  # PH_IMPL_DEDUP
-OVERLAP_MIN_WORLD = 4  # ranks from which the all-reduce of S is overlapped with the backward kernels
 
 
 def calculate_rgbuv_histogram(image_batch, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",

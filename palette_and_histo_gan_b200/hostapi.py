@@ -127,18 +127,35 @@ def histogram_loss_finish(ssum_global: float, global_batch: int, out_grad=None, 
     return float(loss[0]), grad
 
 
+def histogram_loss_finish_comm(comm, global_batch: int, out_grad=None, *, out_grad_device=None, ctx=None, device=0):
+    """Phase 2 for ranks connected by a `_comm.PeerComm`: the shard's sum of squares that `histogram_loss_begin`
+    left on the device is summed over the ranks by one kernel over peer memory (NVLink) — no host round trip and
+    no library collective between the phases."""
+    loss = np.zeros((1,), np.float32)
+    grad = _np(out_grad, np.float32, "out_grad") if out_grad is not None else None
+    dptr = None
+    if out_grad_device is not None:
+        if not (out_grad_device.is_cuda and out_grad_device.is_contiguous() and out_grad_device.dtype.is_floating_point
+                and out_grad_device.element_size() == 4):
+            raise ValueError("out_grad_device must be a contiguous float32 CUDA tensor")
+        dptr = out_grad_device.data_ptr()
+    ctx = ctx or default_context(device)
+    _lib.call("ph_host_hist_finish_comm", ctx._h, comm.handle, int(global_batch), loss.ctypes.data,
+              grad.ctypes.data if grad is not None else None, dptr)
+    return float(loss[0]), grad
+
+
 def load_indexed_images(source_image, target_image, palette_ordering="grayness", *, with_one_hot=False,
-                        out=None, ctx=None, device=0):
+                        out=None, ctx=None, device=0, seed=None):
     """dataset_utils.py:138-151 for host images (B,H,W,4), int32 (values 0..255) or uint8 (the decoded PNG as it
     is: a quarter of the upload, widened on the device).  Returns (source_indexed, target_indexed, palette
     [, target_one_hot]) as numpy arrays.  `out=(source_indexed, target_indexed, palette)`: caller-owned int32 result
     buffers of shapes (B,H,W,1), (B,H,W,1), (B,256,4) — numpy arrays or pinned CPU torch tensors (page-locked
-    results download at PCIe speed; fresh pageable arrays take a staged copy)."""
+    results download at PCIe speed; fresh pageable arrays take a staged copy).  `palette_ordering="shuffled"`
+    (io_utils.py:56-58) permutes each palette with numpy's `default_rng(seed)`."""
     from .io_utils import PaletteOverflowError, _ordering_id
     from .configuration import MAX_PALETTE_SIZE
 
-    if palette_ordering == "shuffled":
-        raise ValueError("'shuffled' is nondeterministic; use the tensor API (dataset_utils.load_indexed_images)")
     def _is_u8(x):
         return str(getattr(x, "dtype", "")).endswith("uint8")  # numpy or (pinned) CPU torch tensor
 
@@ -161,10 +178,14 @@ def load_indexed_images(source_image, target_image, palette_ordering="grayness",
         pal = np.empty((b, MAX_PALETTE_SIZE, 4), np.int32)
     nc = np.empty((b,), np.int32)
     oh = np.empty((b, h, w, MAX_PALETTE_SIZE), np.float32) if with_one_hot else None
+    order = _ordering_id(palette_ordering)
+    keys = None
+    if palette_ordering == "shuffled":  # independent uniform keys; the kernel ranks the first n of each row
+        keys = np.random.default_rng(seed).random((b, MAX_PALETTE_SIZE), dtype=np.float32)
     ctx = ctx or default_context(device)
-    _lib.call("ph_host_load_indexed_images_u8" if as_u8 else "ph_host_load_indexed_images", ctx._h, src.ctypes.data, tgt.ctypes.data, b, h * w,
-              _ordering_id(palette_ordering), s_idx.ctypes.data, t_idx.ctypes.data, pal.ctypes.data,
-              nc.ctypes.data, oh.ctypes.data if oh is not None else None)
+    _lib.call("ph_host_load_indexed_images_u8" if as_u8 else "ph_host_load_indexed_images", ctx._h, src.ctypes.data,
+              tgt.ctypes.data, b, h * w, order, keys.ctypes.data if keys is not None else None, s_idx.ctypes.data,
+              t_idx.ctypes.data, pal.ctypes.data, nc.ctypes.data, oh.ctypes.data if oh is not None else None)
     if (nc == _lib.PALETTE_BAD_VALUE).any():
         raise ValueError("colour values must lie in [0, 255]")
     if (nc > MAX_PALETTE_SIZE).any():

@@ -24,8 +24,6 @@ class PaletteOverflowError(ValueError):
 
 
 def _ordering_id(palette_ordering) -> int:
-    if palette_ordering == "shuffled":
-        return _lib.ORDERINGS["top2bottom"]  # then permuted on the host side of the call
     try:
         return _lib.ORDERINGS[palette_ordering]
     except KeyError:
@@ -46,13 +44,12 @@ def _check_ncolors(ncolors: torch.Tensor):
     return nc
 
 
-def _shuffle_rows(palette: torch.Tensor, ncolors_host: torch.Tensor, generator=None):
-    """`tf.random.shuffle(colors)` (io_utils.py:58): permute the first n rows of each palette."""
-    for b in range(palette.shape[0]):
-        n = int(ncolors_host[b])
-        perm = torch.randperm(n, generator=generator).to(palette.device)
-        palette[b, :n] = palette[b, :n][perm]
-    return palette
+def _shuffle_keys(batch: int, device, generator=None) -> torch.Tensor:
+    """`tf.random.shuffle(colors)` (io_utils.py:58): independent uniform keys, one per palette row; the kernel ranks
+    the first n of them, which permutes the n colours uniformly at random.  Drawn on the host from `generator`
+    (reproducible), 1 KiB per image uploaded."""
+    keys = torch.rand((batch, MAX_PALETTE_SIZE), generator=generator, dtype=torch.float32)
+    return keys.to(device, non_blocking=True)
 
 
 def extract_palette(image, palette_ordering, channels=OUTPUT_CHANNELS, *, batched=None, return_counts=False,
@@ -77,14 +74,14 @@ def extract_palette(image, palette_ordering, channels=OUTPUT_CHANNELS, *, batche
     rows = per_image // 4
     palette = torch.empty((b, MAX_PALETTE_SIZE, 4), dtype=torch.int32, device=img.device)
     ncolors = torch.empty((b,), dtype=torch.int32, device=img.device)
+    order = _ordering_id(palette_ordering)
+    keys = _shuffle_keys(b, img.device, generator) if palette_ordering == "shuffled" else None
     if b:
         with torch.cuda.device(img.device):
-            _lib.call("ph_extract_palette", ptr(img), b, rows, _ordering_id(palette_ordering), ptr(palette),
-                      ptr(ncolors), stream_ptr(img.device))
-    if check or palette_ordering == "shuffled":
-        nc_host = _check_ncolors(ncolors)
-        if palette_ordering == "shuffled":
-            _shuffle_rows(palette, nc_host, generator)
+            _lib.call("ph_extract_palette", ptr(img), b, rows, order, ptr(keys), ptr(palette), ptr(ncolors),
+                      stream_ptr(img.device))
+    if check:
+        _check_ncolors(ncolors)
     out = palette if batched else palette[0]
     out = to_caller_framework(out, image)
     if return_counts:

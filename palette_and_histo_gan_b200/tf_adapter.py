@@ -6,6 +6,12 @@ import-safe without it (TensorFlow is imported on first use) and is exercised on
 (tests/test_abi.py); the torch path it wraps is what the GPU tests cover.  `tf.experimental.dlpack` works on eager
 tensors only: call these from an eager `train_step` (as `Pix2PixIndexedModel.train_step` already is) or through
 `tf.py_function` inside the reference's `@tf.function train_step` (pix2pix_model.py:62).
+
+Stream ordering: TensorFlow runs its GPU kernels on its own compute stream and DLPack carries no stream.  Every
+hand-over is therefore fenced: before a TensorFlow tensor is borrowed, TensorFlow's device work is drained
+(`tf.test.experimental.sync_devices()`, a scalar read-back on versions without it), and before a result goes back,
+torch's current stream is synchronised.  Two host synchronisations per call — the price of crossing frameworks
+without a shared stream; UNTESTED in the build image (no TensorFlow), see INTEGRATION.md.
 """
 from __future__ import annotations
 
@@ -23,14 +29,26 @@ def _tf():
     return tf
 
 
+def _sync_tf(tf, t):
+    """All TensorFlow GPU work that produces `t` has finished when this returns."""
+    sync = getattr(getattr(tf.test, "experimental", None), "sync_devices", None)
+    if sync is not None:
+        sync()
+    else:  # TF < 2.11: a host read-back of one element orders TensorFlow's stream
+        tf.reshape(t, [-1])[:1].numpy()
+
+
 def _to_torch(t):
     tf = _tf()
+    _sync_tf(tf, t)  # the kernels of libpalhist run on torch's stream: TensorFlow must be done writing `t`
     return torch.utils.dlpack.from_dlpack(tf.experimental.dlpack.to_dlpack(t))
 
 
 def _to_tf(t):
     tf = _tf()
-    return tf.experimental.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(t.contiguous()))
+    t = t.contiguous()
+    torch.cuda.current_stream(t.device).synchronize()  # TensorFlow must not read before our kernels are done
+    return tf.experimental.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(t))
 
 
 def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", sigma=0.02):

@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg._lib.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in palhist.h but not exported"
-    assert lib.ph_abi_version() == 1
+    assert lib.ph_abi_version() == pkg._lib.ABI_VERSION == 2
 
 
 def test_ctypes_prototypes_match_header(pkg):
@@ -104,7 +104,12 @@ def test_host_argument_validation(pkg):
         pkg.hostapi.load_indexed_images(img8, img8, out=(np.zeros((2, 8, 8, 1), np.int32), np.zeros((2, 8, 8, 1), np.int32),
                                                          np.zeros((2, 255, 4), np.int32)))
     with pytest.raises(ValueError):
-        pkg.hostapi.load_indexed_images(img8, img8, "shuffled")
+        pkg.hostapi.load_indexed_images(img8, img8, "by-count")
+    # P6: the pixel helpers refuse CPU tensors (no eager / CPU fallback) and non-RGBA input to blacken
+    for fn in (pkg.dataset_utils.blacken_transparent_pixels, pkg.dataset_utils.normalize, pkg.dataset_utils.denormalize):
+        with pytest.raises(ValueError):
+            fn(torch.zeros(4, 4, 4))
+    assert pkg._lib.ORDERINGS["shuffled"] == 3 and pkg._lib.async_status() == 0
     # augmentation: CPU tensors and out-of-range hue shifts are refused
     d = pkg.dataset_utils
     with pytest.raises(ValueError):
