@@ -28,6 +28,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "histogram-loss fwd+bwd images/s at 64x64"
+# share of hist_bwd_tc_kernel + its prologue in the step's launch list under ncu (profiles/README.md, this round's capture)
+NCU_BWD_SHARE = 0.514
 GLOBAL_BATCH = int(os.environ.get("PH_BENCH_BATCH", "4096"))  # cfgC (override only for tuning runs)
 HW = 64
 BINS = 64
@@ -39,6 +41,11 @@ def shard_bounds(total: int, world: int, rank: int):
     base, rem = divmod(total, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+REFERENCE_SAMPLE = 32  # image pairs per step of the CPU reference arm (= cfgA, the reference's own CPU-runnable case)
+WORKLOAD = ("cfgC: histogram loss fwd(real)+fwd(fake)+Hellinger+bwd, 64x64 RGBA, 64 bins, global batch 4096 "
+            f"(the CPU reference arm times a bounded sample of {REFERENCE_SAMPLE} of these pairs per step, rate in images/s)")
 
 
 def load_peaks():
@@ -186,7 +193,7 @@ def run_reference(args, rank):
     import torch
 
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; use every host core
-    sample = 32
+    sample = REFERENCE_SAMPLE
     real, fake = make_hist_inputs(sample, 47)
     real_t, fake_t = torch.from_numpy(real), torch.from_numpy(fake)
     from oracle import torch_port as tp
@@ -202,8 +209,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfgC histogram loss fwd+bwd, 64x64 RGBA, 64 bins (CPU arm: bounded sample of "
-                               f"{sample} image pairs per step)", "global_batch": GLOBAL_BATCH, "bins": BINS},
+        "config": {"workload": WORKLOAD, "global_batch": GLOBAL_BATCH, "bins": BINS, "sample_pairs_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{args.steps} steps x {sample} image pairs, torch-CPU op-for-op port of "
                                    "histogram.py + autograd (TensorFlow not installable here)"},
@@ -235,7 +241,9 @@ def run_ours(args, rank, world, local_rank):
 
     lo, hi = shard_bounds(GLOBAL_BATCH, world, rank)
     local_b = hi - lo
-    real_np, fake_np, real_u8_np = make_hist_inputs(local_b, 47 + rank, with_u8=True)
+    # ONE global batch, the same 4096 pairs at every N (drawn from the global image index); a rank keeps its slice:
+    # loss and gradient of the N-GPU run must then equal the 1-GPU run's, which the line reports
+    real_np, fake_np, real_u8_np = (a[lo:hi].copy() for a in make_hist_inputs(GLOBAL_BATCH, 47, with_u8=True))
     real = torch.from_numpy(real_np).to(dev)
     fake = torch.from_numpy(fake_np).to(dev).requires_grad_(True)
 
@@ -276,6 +284,10 @@ def run_ours(args, rank, world, local_rank):
     t1 = time.time()
     launches = _lib.launch_count()
     loss_val = float(step().detach())
+    # 64-bit checksum (sum of the float32 bit patterns) of the gradient of global image 0 (rank 0's first image):
+    # together with the loss it is the cross-N parity evidence — equal up to the last bits of S at every N
+    grad0_checksum = int(fake.grad[0].contiguous().view(torch.int32).to(torch.int64).sum().item())
+    grad0_norm = float(fake.grad[0].double().norm())
     value = GLOBAL_BATCH * args.steps / (ms / 1e3)
 
     # ---- per-phase breakdown (same kernels, CUDA events between phases on the launching stream) ----
@@ -301,8 +313,10 @@ def run_ours(args, rank, world, local_rank):
     flops_fwd = 6.0 * BINS * BINS * npix * local_b   # 3 GEMMs SxN . NxS
     flops_bwd = 12.0 * BINS * BINS * npix * local_b  # 2 GEMMs per channel, N x S x S
     # the tensor-core engine contracts on kind::f16 (fp16 hi+lo operand split, fp32 accumulate): the pipe's measured
-    # dense rate is the bf16/fp16 figure; sustained, because the kernels are timed inside a long step
-    f16_peak = peaks["bf16_tflops_sustained"]
+    # dense rate is the bf16/fp16 figure — the burst one while the timed region is short (< 1 s at full clock),
+    # the sustained one for a long region
+    burst = ms < 1000.0
+    f16_peak = peaks["bf16_tflops"] if burst else peaks["bf16_tflops_sustained"]
     bwd_tflops = flops_bwd / (phase_ms[3] * 1e-3) / 1e12
     fwd_tflops = flops_fwd / (phase_ms[1] * 1e-3) / 1e12
     step_tflops = 24.0 * BINS * BINS * npix * local_b / (ms / args.steps * 1e-3) / 1e12
@@ -314,13 +328,18 @@ def run_ours(args, rank, world, local_rank):
         "traffic": 711.2e6 * local_b / 4096.0,
         "traffic_source": "profiles/r1_prof_hist_f16_raw.csv (ncu, 4096 images/launch), scaled by local batch",
         "algorithmic_bytes": float(local_b) * npix * 4 * 4 * 2 + float(local_b) * 3 * BINS * BINS * 4,
-        "peak_source": f"{peaks['source']}: bf16_tflops_sustained (kind::f16 runs at the bf16 dense rate)",
+        "peak_source": f"{peaks['source']}: {'bf16_tflops (burst: timed region %.2f s)' % (ms / 1e3) if burst else 'bf16_tflops_sustained'} "
+                       "(kind::f16 runs at the bf16 dense rate)",
+        # duration of the dominant kernel (+ its 0.1 ms prologue) per launch, CUDA events on the launching stream, and
+        # its share of the step under ncu (profiles/r2_launches_step_summary.csv) — the two must agree
+        "kernel_ms": float(phase_ms[3]), "kernel_share_of_step": float(phase_ms[3] / (ms / args.steps)),
+        "kernel_ncu_share": NCU_BWD_SHARE,
         # fp32-accurate results need three fp16 products per algorithmic product (hi.hi + hi.lo + lo.hi): the
         # attainable ceiling of the emulation is peak / 3 (the forward's single N=128 instruction computes four)
         "frac_of_emulation_ceiling": bwd_tflops / (f16_peak / 3.0),
         "frac_of_tf32_peak": bwd_tflops / (f16_peak / 2.0),
         "forward": {"achieved": fwd_tflops, "frac": fwd_tflops / f16_peak,
-                    "frac_of_emulation_ceiling": fwd_tflops / (f16_peak / 4.0)},
+                    "frac_of_emulation_ceiling": fwd_tflops / (f16_peak / 3.0), "kernel_ms": float(phase_ms[1])},
         "whole_step": {"achieved": step_tflops, "frac": step_tflops / f16_peak},
         "phase_ms": {"fwd_real": phase_ms[0], "fwd_fake+hellinger_sum": phase_ms[1], "allreduce+loss": phase_ms[2],
                      "bwd": phase_ms[3]},
@@ -336,8 +355,15 @@ def run_ours(args, rank, world, local_rank):
     ctx = hostapi.HostContext(local_rank)
     gpu_scalar = torch.zeros(1, dtype=torch.float64, device=dev)
 
+    comm = None
+    if distributed:
+        from palette_and_histo_gan_b200 import _comm
+        comm = _comm.peer_comm(True, dev)
+
     def e2e_step():
         ssum = hostapi.histogram_loss_begin(real_h, fake_h, BINS, impl=impl, ctx=ctx)
+        if comm is not None:  # the shard's sum stays on the device and is summed over the ranks there (NVLink)
+            return hostapi.histogram_loss_finish_comm(comm, GLOBAL_BATCH, None, out_grad_device=grad_d, ctx=ctx)
         if distributed:
             gpu_scalar.fill_(ssum)
             dist.all_reduce(gpu_scalar)
@@ -397,14 +423,16 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (tcgen05 kind::f16 with fp16 hi+lo operand split = fp32-accurate 3-product emulation, fp32 accumulate, when engine=tc; fp32 FFMA when simt)",
             "data": "synthetic",
-            "config": {"workload": "cfgC: histogram loss fwd(real)+fwd(fake)+Hellinger+bwd, 64x64 RGBA, 64 bins",
+            "config": {"workload": WORKLOAD,
                        "global_batch": GLOBAL_BATCH, "per_gpu_batch": local_b, "bins": BINS,
-                       "parallelism": f"batch-sharded x{world}, all-reduce of one fp64 scalar",
+                       "parallelism": f"batch-sharded x{world}, one fp64 scalar summed over the ranks "
+                                      + ("by a peer-memory kernel over NVLink (ph_comm_allreduce_sum_f64)" if comm is not None
+                                         else "by NCCL all-reduce" if distributed else "(single rank: no exchange)"),
                        "l2": "inputs larger than L2 (real+fake+grad = %.0f MiB per GPU)" % (3 * img_bytes / 2 ** 20),
                        "engine": impl,
                        "real_images": "palette sprites, contracted over their unique colours (PH_IMPL_DEDUP, exact); "
                                       "fake images dense"},
-            "loss": loss_val, "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
+            "loss": loss_val, "grad0_checksum": grad0_checksum, "grad0_norm": grad0_norm, "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "palette": palette, "generator_step": generator_step, "scale_sweep": scale_sweep,
         }
         if cpu_baseline is not None:

@@ -229,15 +229,37 @@ class _HistogramLossFn(torch.autograd.Function):
 DEDUP_FLAG = 8  # PH_IMPL_DEDUP
 
 
+def _range_checked(run, impl, device, range_check):
+    """`range_check="sync"`: evaluate, wait for the kernels, and if the tensor-core forward flagged pixels outside
+    its operand range (images far outside [-1, 1], which the reference accepts, histogram.py:58) evaluate again on
+    the CUDA-core engine.  `"async"` (default, no synchronisation): such a launch sets the sticky status word
+    (`_lib.async_status`) and the next histogram call raises."""
+    if range_check not in ("async", "sync"):
+        raise ValueError("range_check must be 'async' or 'sync'")
+    if range_check == "async" or impl == "simt":
+        return run(impl)
+    with torch.cuda.device(device):
+        torch.cuda.current_stream(device).synchronize()
+        _lib.async_status(clear=True)
+        out = run(impl)
+        torch.cuda.current_stream(device).synchronize()
+        if _lib.async_status(clear=True) & _lib.ASYNC_RANGE:
+            out = run("simt")
+    return out
+
+
 def calculate_rgbuv_histogram(image_batch, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",
-                              dedup=False):
+                              dedup=False, range_check="async"):
     """histogram.py:36-81.  image_batch (B,H,W,3|4) float32 in [-1,1] -> (B,size,size,3), sums to 1 per image.
     `dedup=True`: contract each image's unique colours with their multiplicities (exact; pays off for
-    palette images such as dataset sprites, falls back to the dense contraction per image otherwise)."""
+    palette images such as dataset sprites, falls back to the dense contraction per image otherwise).
+    `range_check`: see `_range_checked` (images outside [-1, 1] on the tensor-core engine)."""
     image = require_cuda(from_any(image_batch, name="image_batch"), torch.float32, name="image_batch")
     dom = histogram_domain(size, image.device)
-    out = _RgbuvHistogramFn.apply(image, dom, _method_id(method), _sigma_sqr(sigma),
-                                  _lib.IMPLS[impl] | (DEDUP_FLAG if dedup else 0))
+    mid, s2 = _method_id(method), _sigma_sqr(sigma)
+    out = _range_checked(lambda eng: _RgbuvHistogramFn.apply(image, dom, mid, s2,
+                                                             _lib.IMPLS[eng] | (DEDUP_FLAG if dedup else 0)),
+                         impl, image.device, range_check)
     return to_caller_framework(out, image_batch)
 
 
@@ -294,7 +316,7 @@ def l2_loss(y_true, y_pred):
 
 
 def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", sigma=0.02, *, group=None,
-                   global_batch=None, impl="auto", dedup_real=True):
+                   global_batch=None, impl="auto", dedup_real=True, range_check="async"):
     """`hellinger_loss(calculate_rgbuv_histogram(real), calculate_rgbuv_histogram(fake))` as one call
     (pix2pix_model.py:243-245); differentiable with respect to `fake_image`.  `dedup_real`: the real images
     come from the dataset and are palette sprites, so their histogram is contracted over unique colours
@@ -303,7 +325,12 @@ def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", 
     fake = require_cuda(from_any(fake_image, name="fake_image"), torch.float32, name="fake_image")
     if real.shape != fake.shape:
         raise ValueError("real_image and fake_image must have the same shape")
+    if range_check == "sync" and group is not None and group is not False:
+        raise ValueError("range_check='sync' re-runs a flagged call on this rank alone; with a sharded batch check "
+                         "`_lib.async_status()` after the step instead")
     dom = histogram_domain(size, fake.device)
-    out = _HistogramLossFn.apply(real, fake, dom, _method_id(method), _sigma_sqr(sigma), _lib.IMPLS[impl], group,
-                                 global_batch, bool(dedup_real))
+    mid, s2 = _method_id(method), _sigma_sqr(sigma)
+    out = _range_checked(lambda eng: _HistogramLossFn.apply(real, fake, dom, mid, s2, _lib.IMPLS[eng], group,
+                                                            global_batch, bool(dedup_real)),
+                         impl, fake.device, range_check)
     return to_caller_framework(out, fake_image)

@@ -305,3 +305,92 @@ def test_concurrent_host_threads(P, cuda, sprites, palette_golden):
             assert np.array_equal(t_idx[k], po.rgba_to_indexed(right[lo + k].astype(np.int32), ep))
             assert np.array_equal(back[k], right[lo + k].astype(np.int32))
         assert oh_sum == 4 * 64 * 64
+
+
+def test_shuffled_ordering_in_the_kernel_is_seeded_and_consistent(P, cuda, sprites):
+    """`palette_ordering="shuffled"` (io_utils.py:56-58) runs inside the fused kernel: the first-occurrence colours are
+    permuted by ranking seeded uniform keys.  Same generator seed -> same palettes; the indices refer to the shuffled
+    palette (round trip); the permutation is the argsort of the keys the host drew; host API likewise with `seed=`."""
+    s, t = sprites["front"][:6].astype(np.int32), sprites["right"][:6].astype(np.int32)
+    runs = []
+    for _ in range(2):
+        g = torch.Generator().manual_seed(123)
+        runs.append(P.dataset_utils.load_indexed_images(dev_i32(s, cuda), dev_i32(t, cuda), "shuffled", generator=g))
+    assert all(torch.equal(a, b) for a, b in zip(runs[0], runs[1]))
+    s_idx, t_idx, pal = runs[0]
+    keys = torch.rand((6, 256), generator=torch.Generator().manual_seed(123), dtype=torch.float32).numpy()
+    moved = 0
+    for i in range(6):
+        ep, n = po.extract_palette(np.concatenate([s[i], t[i]], -1), "top2bottom")
+        expect = ep.copy()
+        expect[:n] = ep[:n][np.argsort(keys[i, :n], kind="stable")]
+        assert np.array_equal(pal[i].cpu().numpy(), expect)
+        moved += int(not np.array_equal(expect, ep))
+    assert moved >= 5  # it is a real permutation
+    assert torch.equal(P.io_utils.indexed_to_rgba(s_idx, pal), dev_i32(s, cuda))
+    assert torch.equal(P.io_utils.indexed_to_rgba(t_idx, pal), dev_i32(t, cuda))
+    # standalone extract_palette and the host-buffer API
+    cat = torch.cat([dev_i32(s, cuda), dev_i32(t, cuda)], dim=-1)
+    pal2 = P.io_utils.extract_palette(cat, "shuffled", generator=torch.Generator().manual_seed(123))
+    assert torch.equal(pal2, pal)
+    hs, ht, hp = P.hostapi.load_indexed_images(s, t, "shuffled", seed=7)
+    hs2, ht2, hp2 = P.hostapi.load_indexed_images(s.astype(np.uint8), t.astype(np.uint8), "shuffled", seed=7)
+    assert np.array_equal(hp, hp2) and np.array_equal(hs, hs2) and np.array_equal(ht, ht2)
+    hkeys = np.random.default_rng(7).random((6, 256), dtype=np.float32)
+    for i in range(6):
+        ep, n = po.extract_palette(np.concatenate([s[i], t[i]], -1), "top2bottom")
+        expect = ep.copy()
+        expect[:n] = ep[:n][np.argsort(hkeys[i, :n], kind="stable")]
+        assert np.array_equal(hp[i], expect)
+        assert np.array_equal(po.indexed_to_rgba(hs[i], hp[i]), s[i])
+
+
+@pytest.mark.parametrize("ordering", ["grayness", "top2bottom", "bottom2top"])
+def test_uint8_device_entry_and_large_images(P, cuda, sprites, ordering):
+    """`ph_load_indexed_images_u8`: the decoded PNG's uint8 pixels read by the kernel as they are — identical outputs
+    to the int32 entry.  Images above 8 192 rows per pair take the kernel variant that re-reads the pixels for the
+    index pass instead of keeping their keys in registers; ragged sizes exercise the partially filled batches."""
+    s8, t8 = torch.from_numpy(sprites["front"][:20]).to(cuda), torch.from_numpy(sprites["right"][:20]).to(cuda)
+    a = P.dataset_utils.load_indexed_images(s8, t8, ordering)
+    b = P.dataset_utils.load_indexed_images(s8.to(torch.int32), t8.to(torch.int32), ordering)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    rng = np.random.default_rng(11)
+    for hw in ((96, 96), (70, 61), (3, 5)):
+        src = sprite_like_batch(rng, 3, hw=96)[:, :hw[0], :hw[1]].copy()
+        tgt = src[:, ::-1].copy()
+        for dt in (torch.uint8, torch.int32):
+            s_idx, t_idx, pal = P.dataset_utils.load_indexed_images(torch.from_numpy(src).to(cuda).to(dt),
+                                                                    torch.from_numpy(tgt).to(cuda).to(dt), ordering)
+            for i in range(3):
+                es, et, ep = po.load_indexed_images(src[i].astype(np.int32), tgt[i].astype(np.int32), ordering)
+                assert np.array_equal(pal[i].cpu().numpy(), ep), (hw, dt)
+                assert np.array_equal(s_idx[i].cpu().numpy(), es) and np.array_equal(t_idx[i].cpu().numpy(), et), (hw, dt)
+
+
+def test_pixel_helpers_are_kernels_and_bit_exact(P, cuda, sprites):
+    """dataset_utils.py:11-20, :39-60 as `ph_pixel_map` launches (P6): bit-exact against the numpy restatement, the
+    launch counter proves they ran in libpalhist, CPU tensors are refused."""
+    D = P.dataset_utils
+    raw = sprites["right"][:5].copy()
+    raw[0, :3, :3] = [200, 10, 30, 0]                      # non-black transparent pixels
+    x = torch.from_numpy(raw.astype(np.float32)).to(cuda)
+    P._lib.reset_launch_count()
+    blk = D.blacken_transparent_pixels(x)
+    nrm = D.normalize(blk)
+    den = D.denormalize(nrm)
+    assert P._lib.launch_count() == 3
+    eb = po.blacken_transparent_pixels(raw.astype(np.float32))
+    assert np.array_equal(blk.cpu().numpy(), eb)
+    assert np.array_equal(nrm.cpu().numpy(), po.normalize(eb))
+    assert np.array_equal(den.cpu().numpy(), po.denormalize(po.normalize(eb)))
+    # integer input keeps its dtype through blacken (tf.where), odd element counts through normalize
+    bi = D.blacken_transparent_pixels(torch.from_numpy(raw).to(cuda))
+    assert bi.dtype == torch.uint8 and np.array_equal(bi.cpu().numpy(), po.blacken_transparent_pixels(raw))
+    odd = torch.arange(0, 7, dtype=torch.float32, device=cuda) * 36.5
+    assert np.array_equal(D.normalize(odd).cpu().numpy(), po.normalize(odd.cpu().numpy()))
+    neg0 = torch.tensor([[5.0, 6.0, 7.0, -0.0]], device=cuda)
+    assert float(D.blacken_transparent_pixels(neg0).abs().sum()) == 0.0       # -0.0 == 0 as in tf.where
+    with pytest.raises(ValueError):
+        D.normalize(torch.zeros(4, 4, 4))
+    # same result as the fused uint8 loader
+    assert torch.equal(D.load_image(torch.from_numpy(raw).to(cuda)), nrm)
