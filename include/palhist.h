@@ -299,6 +299,14 @@ PH_API int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t glo
  * phases (the host value `begin` returned is not needed). */
 PH_API int ph_host_hist_finish_comm(ph_host_ctx* ctx, ph_comm* comm, int64_t global_batch, float* loss_host,
                              float* grad_fake_host, float* grad_fake_device);
+/* Both phases in one call for a shard of a batch spread over the ranks of `comm`: upload, forwards, unit-scale
+ * backward, sum of the shards' sums of squares over peer memory, loss, gradient — one host synchronisation, at the
+ * end.  real_host: float32 (batch,npix,channels) or, with real_is_u8 != 0, uint8 RGBA sprites. */
+PH_API int ph_host_hist_loss_sharded(ph_host_ctx* ctx, ph_comm* comm, const void* real_host, int real_is_u8,
+                              const float* fake_host, int64_t batch, int64_t npix, int channels,
+                              const float* bin_centers_host, int bins, int method, float sigma_sqr, float epsilon,
+                              int impl, int64_t global_batch, float* loss_host, float* grad_fake_host,
+                              float* grad_fake_device);
 
 /* dataset_utils.py:138-151 for host images (+ optional one-hot of the target indices). */
 PH_API int ph_host_load_indexed_images(ph_host_ctx* ctx, const int32_t* source_host, const int32_t* target_host,

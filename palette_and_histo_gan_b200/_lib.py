@@ -80,6 +80,8 @@ PROTOTYPES = {
     "ph_host_hist_begin_u8real": (_int, [_p, _p, _p, _i64, _i64, _p, _int, _int, _f, _f, _int, _p]),
     "ph_host_hist_finish": (_int, [_p, C.c_double, _i64, _p, _p, _p]),
     "ph_host_hist_finish_comm": (_int, [_p, _p, _i64, _p, _p, _p]),
+    "ph_host_hist_loss_sharded": (_int, [_p, _p, _p, _int, _p, _i64, _i64, _int, _p, _int, _int, _f, _f, _int, _i64, _p, _p,
+                                         _p]),
     "ph_host_load_indexed_images": (_int, [_p, _p, _p, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
     "ph_host_load_indexed_images_u8": (_int, [_p, _p, _p, _i64, _i64, _int, _p, _p, _p, _p, _p, _p]),
 }

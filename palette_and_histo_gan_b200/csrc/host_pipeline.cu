@@ -167,7 +167,9 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
                                 int64_t batch, int64_t npix, int channels, const float* bin_centers_host, int bins,
                                 int method, float sigma_sqr, float epsilon, int impl, bool with_grad,
                                 double* ssum_local_host) {
-  PH_CHECK_ARG(ctx && real_host && fake_host && bin_centers_host && ssum_local_host, "NULL pointer argument");
+  // ssum_local_host == NULL: the shard's sum is not read back (no stream synchronisation here): the caller goes on
+  // to the peer all-reduce on the device (ph_host_hist_loss_sharded)
+  PH_CHECK_ARG(ctx && real_host && fake_host && bin_centers_host, "NULL pointer argument");
   PH_CHECK_ARG(batch > 0 && npix > 0 && (channels == 3 || channels == 4), "bad shape");
   PH_CHECK_ARG(bins >= 1 && bins <= 1024, "bins must be in [1,1024]");
   PH_CUDA_OK(cudaSetDevice(ctx->device));
@@ -287,8 +289,10 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   // the shard's sum stays on the device (ph_host_hist_finish_comm all-reduces it there) and is also returned
   sum_parts_kernel<<<1, 1, 0, ctx->s_compute>>>(J.d_ssum2, nchunks > 1 ? 2 : 1, J.d_ssum);
   PH_LAUNCH_OK("sum_parts_kernel");
-  PH_CUDA_OK(cudaMemcpyAsync(ssum_local_host, J.d_ssum, sizeof(double), cudaMemcpyDeviceToHost, ctx->s_compute));
-  PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+  if (ssum_local_host != nullptr) {
+    PH_CUDA_OK(cudaMemcpyAsync(ssum_local_host, J.d_ssum, sizeof(double), cudaMemcpyDeviceToHost, ctx->s_compute));
+    PH_CUDA_OK(cudaStreamSynchronize(ctx->s_compute));
+  }
   ctx->job_valid = true;
   return PH_OK;
 }
@@ -296,6 +300,7 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
 int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fake_host, int64_t batch,
                        int64_t npix, int channels, const float* bin_centers_host, int bins, int method,
                        float sigma_sqr, float epsilon, int impl, double* ssum_local_host) {
+  PH_CHECK_ARG(ssum_local_host != nullptr, "NULL pointer argument");
   return host_hist_begin_impl(ctx, real_host, false, fake_host, batch, npix, channels, bin_centers_host, bins, method,
                               sigma_sqr, epsilon, impl, true, ssum_local_host);
 }
@@ -303,6 +308,7 @@ int ph_host_hist_begin(ph_host_ctx* ctx, const float* real_host, const float* fa
 int ph_host_hist_begin_u8real(ph_host_ctx* ctx, const uint8_t* real_u8_host, const float* fake_host, int64_t batch,
                               int64_t npix, const float* bin_centers_host, int bins, int method, float sigma_sqr,
                               float epsilon, int impl, double* ssum_local_host) {
+  PH_CHECK_ARG(ssum_local_host != nullptr, "NULL pointer argument");
   return host_hist_begin_impl(ctx, real_u8_host, true, fake_host, batch, npix, 4, bin_centers_host, bins, method,
                               sigma_sqr, epsilon, impl, true, ssum_local_host);
 }
@@ -360,6 +366,20 @@ int ph_host_hist_finish(ph_host_ctx* ctx, double ssum_global, int64_t global_bat
 int ph_host_hist_finish_comm(ph_host_ctx* ctx, ph_comm* comm, int64_t global_batch, float* loss_host,
                              float* grad_fake_host, float* grad_fake_device) {
   PH_CHECK_ARG(comm != nullptr, "comm must not be NULL");
+  return host_hist_finish_impl(ctx, comm, 0.0, global_batch, loss_host, grad_fake_host, grad_fake_device);
+}
+
+int ph_host_hist_loss_sharded(ph_host_ctx* ctx, ph_comm* comm, const void* real_host, int real_is_u8,
+                              const float* fake_host, int64_t batch, int64_t npix, int channels,
+                              const float* bin_centers_host, int bins, int method, float sigma_sqr, float epsilon,
+                              int impl, int64_t global_batch, float* loss_host, float* grad_fake_host,
+                              float* grad_fake_device) {
+  PH_CHECK_ARG(comm != nullptr, "comm must not be NULL");
+  PH_CHECK_ARG(!real_is_u8 || channels == 4, "uint8 real images are RGBA");
+  int rc = host_hist_begin_impl(ctx, real_host, real_is_u8 != 0, fake_host, batch, npix, channels, bin_centers_host, bins,
+                                method, sigma_sqr, epsilon, impl, grad_fake_host != nullptr || grad_fake_device != nullptr,
+                                nullptr);
+  if (rc != PH_OK) return rc;
   return host_hist_finish_impl(ctx, comm, 0.0, global_batch, loss_host, grad_fake_host, grad_fake_device);
 }
 

@@ -4,6 +4,8 @@
 //
 // Reference semantics: io_utils.py:25-65 (extract_palette), :78-93 (rgba_to_indexed), :96-103
 // (indexed_to_rgba), pix2pix_model.py:300-301 (one-hot), dataset_utils.py:138-151 (call site).
+#include <type_traits>
+
 #include "common.cuh"
 #include "hist_internal.cuh"
 
@@ -20,6 +22,22 @@ __device__ __forceinline__ unsigned pack_rgba(const int4& c) {
 __device__ __forceinline__ int4 unpack_rgba(unsigned k) {
   return make_int4((int)(k & 255u), (int)((k >> 8) & 255u), (int)((k >> 16) & 255u), (int)(k >> 24));
 }
+// x / 127.5f, correctly rounded like TensorFlow's true division (dataset_utils.py:39-48), without the ~10-instruction
+// IEEE division: q = x y, r = fma(-q, 127.5, x) (exact), q' = fma(r, y, q) with y = RN(1 / 127.5) is the correctly
+// rounded quotient (Markstein); tools/div127_5_check.c compares it with x / 127.5f for ALL 2^32 bit patterns: identical
+// for 1e-30 <= |x| < 1e38, so zeros (sign kept) are handled apart and anything else takes the IEEE division.
+__device__ __forceinline__ float div_127_5(float x) {
+  const float y = 1.0f / 127.5f;  // constant-folded, correctly rounded
+  const float q = __fmul_rn(x, y);
+  const float r = __fmaf_rn(-q, 127.5f, x);
+  const float q2 = __fmaf_rn(r, y, q);
+  const float ax = fabsf(x);
+  if (ax >= 1e-30f && ax < 1e38f) return q2;
+  if (x == 0.f) return x;
+  return __fdiv_rn(x, 127.5f);
+}
+__device__ __forceinline__ float normalize_px(float x) { return __fsub_rn(div_127_5(x), 1.0f); }
+
 template <int BITS>
 __device__ __forceinline__ unsigned hash_slot(unsigned key) {
   return (key * 2654435761u) >> (32 - BITS);
@@ -36,15 +54,16 @@ __device__ __forceinline__ unsigned hash_slot(unsigned key) {
 //      (io_utils.py:51-55); "shuffled" (io_utils.py:56-58) re-ranks by caller-provided random keys the same way;
 //   4. rows n..255 are INVALID_INDEX_COLOR (io_utils.py:61-63, configuration.py:32).
 // The pass is a chain load -> match -> hash per row, so what bounds it is how many loads are in flight: every thread
-// issues FOUR independent loads before it touches the table (a batch of 2048 rows per CTA), and when the image fits
-// (rows <= 512 x 16 = 8192: a 64 x 64 source||target pair exactly) the packed keys stay in registers, so the index
-// pass of the fused variant reads no pixel a second time.
+// issues EIGHT independent loads before it touches the table (a batch of 4096 rows per CTA; 64 registers per thread
+// keep two CTAs per SM, so the 256 pairs of a cfgB batch are resident together), and when the image fits in two
+// batches (rows <= 512 x 16 = 8192: a 64 x 64 source||target pair exactly) the packed keys stay in registers, so the
+// index pass of the fused variant reads no pixel a second time.
 // =============================================================================================
 constexpr int PAL_THREADS = 512;
 constexpr int PAL_HASH_BITS = 11;
 constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;
 constexpr int PAL_MAX = PH_MAX_PALETTE_SIZE;
-constexpr int PAL_INFLIGHT = 4;                           // loads in flight per thread
+constexpr int PAL_INFLIGHT = 8;                           // loads in flight per thread
 constexpr int PAL_BATCH = PAL_THREADS * PAL_INFLIGHT;     // rows per batch
 constexpr int PAL_KEEP = 16;                              // keys a thread keeps in registers (cached variant)
 
@@ -65,7 +84,7 @@ __device__ __forceinline__ unsigned load_pixel_key(const void* src0, const void*
 // rewritten to (key, final palette index) and every pixel is looked up with one probe.
 // CACHED: rows <= PAL_THREADS * PAL_KEEP, the keys of the thread's rows stay in registers.
 template <bool FUSED_INDEX, bool U8, bool CACHED>
-__global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
+__global__ void __launch_bounds__(PAL_THREADS, 2) extract_palette_kernel(
     const void* __restrict__ image, const void* __restrict__ image2, int64_t rows, int ordering,
     const float* __restrict__ shuffle_keys, int4* __restrict__ palette, int* __restrict__ ncolors,
     int* __restrict__ indexed, int* __restrict__ indexed2) {
@@ -91,17 +110,18 @@ __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
   unsigned kept[CACHED ? PAL_KEEP : 1];
   bool bad = false;
   // one batch: PAL_INFLIGHT independent loads per thread, then the match / hash step of each row
-  auto insert_batch = [&](const int64_t bt, unsigned* keep) {
-    unsigned key[PAL_INFLIGHT];
+  auto insert_batch = [&](auto nc, const int64_t row0, unsigned* keep) {
+    constexpr int NC = decltype(nc)::value;  // rows per thread in this batch = independent loads in flight
+    unsigned key[NC];
 #pragma unroll
-    for (int k = 0; k < PAL_INFLIGHT; ++k) {
-      const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
+    for (int k = 0; k < NC; ++k) {
+      const int64_t r = row0 + k * PAL_THREADS + tid;
       key[k] = r < rows ? load_pixel_key<U8>(src0, src1, r, bad) : 0u;
       if (keep != nullptr) keep[k] = key[k];
     }
 #pragma unroll
-    for (int k = 0; k < PAL_INFLIGHT; ++k) {
-      const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
+    for (int k = 0; k < NC; ++k) {
+      const int64_t r = row0 + k * PAL_THREADS + tid;
       const bool active = r < rows;
       // warp de-duplication: among lanes with the same colour keep the one with the earliest row
       const unsigned amask = __ballot_sync(0xffffffffu, active);
@@ -127,13 +147,17 @@ __global__ void __launch_bounds__(PAL_THREADS) extract_palette_kernel(
       }
     }
   };
-  if (CACHED) {
+  if (CACHED && U8) {
+    // 4-byte pixels: the whole image (16 loads of one register each per thread) is in flight at once
+    insert_batch(std::integral_constant<int, PAL_KEEP>{}, 0, &kept[0]);
+  } else if (CACHED) {
 #pragma unroll
-    for (int bt = 0; bt < PAL_KEEP / PAL_INFLIGHT; ++bt) insert_batch(bt, &kept[bt * PAL_INFLIGHT]);  // rows beyond the image: inactive
+    for (int bt = 0; bt < PAL_KEEP / PAL_INFLIGHT; ++bt)  // rows beyond the image: inactive
+      insert_batch(std::integral_constant<int, PAL_INFLIGHT>{}, (int64_t)bt * PAL_BATCH, &kept[bt * PAL_INFLIGHT]);
   } else {
     const int64_t nbatch = (rows + PAL_BATCH - 1) / PAL_BATCH;
 #pragma unroll 1
-    for (int64_t bt = 0; bt < nbatch; ++bt) insert_batch(bt, nullptr);
+    for (int64_t bt = 0; bt < nbatch; ++bt) insert_batch(std::integral_constant<int, PAL_INFLIGHT>{}, bt * PAL_BATCH, nullptr);
   }
   if (bad) s_bad = 1;
   __syncthreads();
@@ -503,10 +527,10 @@ __global__ void __launch_bounds__(256) u8_to_float_image_kernel(const uchar4* __
     float4 o = make_float4((float)q.x, (float)q.y, (float)q.z, (float)q.w);
     if (normalize) {
       // same two roundings as the reference: (image / 127.5) - 1
-      o.x = __fsub_rn(__fdiv_rn(o.x, 127.5f), 1.0f);
-      o.y = __fsub_rn(__fdiv_rn(o.y, 127.5f), 1.0f);
-      o.z = __fsub_rn(__fdiv_rn(o.z, 127.5f), 1.0f);
-      o.w = __fsub_rn(__fdiv_rn(o.w, 127.5f), 1.0f);
+      o.x = normalize_px(o.x);
+      o.y = normalize_px(o.y);
+      o.z = normalize_px(o.z);
+      o.w = normalize_px(o.w);
     }
     dst[i] = o;
   }
@@ -519,8 +543,8 @@ __device__ __forceinline__ float4 pixel_map_op(float4 q) {
   if (OP == PH_MAP_BLACKEN) {
     if (q.w == 0.f) q = make_float4(0.f, 0.f, 0.f, 0.f);  // tf.where(alpha == 0, zeros, image); -0.0 == 0 as in TF
   } else if (OP == PH_MAP_NORMALIZE) {
-    q.x = __fsub_rn(__fdiv_rn(q.x, 127.5f), 1.0f); q.y = __fsub_rn(__fdiv_rn(q.y, 127.5f), 1.0f);
-    q.z = __fsub_rn(__fdiv_rn(q.z, 127.5f), 1.0f); q.w = __fsub_rn(__fdiv_rn(q.w, 127.5f), 1.0f);
+    q.x = normalize_px(q.x); q.y = normalize_px(q.y);
+    q.z = normalize_px(q.z); q.w = normalize_px(q.w);
   } else {
     q.x = __fmul_rn(__fadd_rn(q.x, 1.0f), 127.5f); q.y = __fmul_rn(__fadd_rn(q.y, 1.0f), 127.5f);
     q.z = __fmul_rn(__fadd_rn(q.z, 1.0f), 127.5f); q.w = __fmul_rn(__fadd_rn(q.w, 1.0f), 127.5f);
@@ -660,10 +684,10 @@ __global__ void __launch_bounds__(256) augment_pair_kernel(const float4* __restr
     if (px >= npix) continue;
     if (rotate && inside[k]) adjust_hue_pixel(q[k].x, q[k].y, q[k].z, shift6);
     if (normalize) {
-      q[k].x = __fsub_rn(__fdiv_rn(q[k].x, 127.5f), 1.0f);
-      q[k].y = __fsub_rn(__fdiv_rn(q[k].y, 127.5f), 1.0f);
-      q[k].z = __fsub_rn(__fdiv_rn(q[k].z, 127.5f), 1.0f);
-      q[k].w = __fsub_rn(__fdiv_rn(q[k].w, 127.5f), 1.0f);
+      q[k].x = normalize_px(q[k].x);
+      q[k].y = normalize_px(q[k].y);
+      q[k].z = normalize_px(q[k].z);
+      q[k].w = normalize_px(q[k].w);
     }
     __stcs(dst + px, q[k]);
   }

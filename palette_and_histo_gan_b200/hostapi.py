@@ -145,6 +145,34 @@ def histogram_loss_finish_comm(comm, global_batch: int, out_grad=None, *, out_gr
     return float(loss[0]), grad
 
 
+def histogram_loss_sharded(comm, real_image, fake_image, global_batch: int, size=64, method="inverse-quadratic",
+                           sigma=0.02, *, impl="auto", out_grad=None, out_grad_device=None, ctx=None, device=0):
+    """One call for this rank's shard of a batch spread over the ranks of `comm` (`_comm.PeerComm`): both phases
+    with the sum over ranks taken on the device over peer memory in between — a single host synchronisation.
+    `real_image`: float32 (B,H,W,3|4) or uint8 RGBA sprites.  Returns (loss, out_grad)."""
+    fake = _np(fake_image, np.float32, "fake_image")
+    real = real_image.numpy() if hasattr(real_image, "numpy") and not isinstance(real_image, np.ndarray) else np.asarray(real_image)
+    is_u8 = real.dtype == np.uint8
+    real = np.ascontiguousarray(real) if is_u8 else _np(real, np.float32, "real_image")
+    if real.shape != fake.shape or real.ndim != 4 or real.shape[-1] not in ((4,) if is_u8 else (3, 4)):
+        raise ValueError("real_image and fake_image must both be (B,H,W,3|4) (uint8 real images: RGBA)")
+    b, h, w, ch = fake.shape
+    dom = tf_linspace(-3.0, 3.0, int(size))
+    loss = np.zeros((1,), np.float32)
+    grad = _np(out_grad, np.float32, "out_grad") if out_grad is not None else None
+    dptr = None
+    if out_grad_device is not None:
+        if not (out_grad_device.is_cuda and out_grad_device.is_contiguous() and out_grad_device.dtype.is_floating_point
+                and out_grad_device.element_size() == 4):
+            raise ValueError("out_grad_device must be a contiguous float32 CUDA tensor")
+        dptr = out_grad_device.data_ptr()
+    ctx = ctx or default_context(device)
+    _lib.call("ph_host_hist_loss_sharded", ctx._h, comm.handle, real.ctypes.data, 1 if is_u8 else 0, fake.ctypes.data, b,
+              h * w, ch, dom.ctypes.data, int(size), _method_id(method), _sigma_sqr(sigma), EPSILON, _lib.IMPLS[impl],
+              int(global_batch), loss.ctypes.data, grad.ctypes.data if grad is not None else None, dptr)
+    return float(loss[0]), grad
+
+
 def load_indexed_images(source_image, target_image, palette_ordering="grayness", *, with_one_hot=False,
                         out=None, ctx=None, device=0, seed=None):
     """dataset_utils.py:138-151 for host images (B,H,W,4), int32 (values 0..255) or uint8 (the decoded PNG as it

@@ -411,19 +411,23 @@ def test_dense_images_in_a_deduplicated_batch_are_bit_identical(H, cuda, sprites
     more than 512 colours inside such a batch is contracted exactly as without `dedup` (same bits), at 64 bins as at
     256."""
     rng = np.random.default_rng(22)
-    spr = normalize(np.concatenate([sprites["front"], sprites["right"]])[:180].astype(np.float32))
+    spr = normalize(np.concatenate([sprites["front"], sprites["right"], sprites["front"][:60]]).astype(np.float32))  # 276
     dense = np.tanh(rng.standard_normal((20, 64, 64, 4))).astype(np.float32)
-    batch = np.concatenate([spr[:90], dense[:10], spr[90:], dense[10:]]).astype(np.float32)  # 200 images >= 148 SMs
+    # 296 images = two full waves of 148 SMs: every image is contracted whole by one CTA with and without `dedup`
+    # (a partial last wave would be cut into pixel slices in the dense plan only, i.e. summed in a different order)
+    batch = np.concatenate([spr[:90], dense[:10], spr[90:], dense[10:]]).astype(np.float32)
+    assert batch.shape[0] == 296
     x = torch.from_numpy(batch).to(cuda)
     a = H.calculate_rgbuv_histogram(x, impl="tc", dedup=True)
     b = H.calculate_rgbuv_histogram(x, impl="tc", dedup=False)
-    dense_idx = list(range(90, 100)) + list(range(190, 200))
+    dense_idx = list(range(90, 100)) + list(range(286, 296))
     assert torch.equal(a[dense_idx], b[dense_idx])
-    ref, _ = ho.rgbuv_histogram_f64(batch[[95, 195]])
-    assert ho.rel_l2(a[[95, 195]].cpu().numpy(), ref) < HIST_TOL
-    spr_idx = [0, 50, 120, 189]
+    ref, _ = ho.rgbuv_histogram_f64(batch[[95, 290]])
+    assert ho.rel_l2(a[[95, 290]].cpu().numpy(), ref) < HIST_TOL
+    spr_idx = [0, 50, 120, 285]
     ref_s, _ = ho.rgbuv_histogram_f64(batch[spr_idx])
     assert ho.rel_l2(a[spr_idx].cpu().numpy(), ref_s) < HIST_TOL
+    assert ho.rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 3e-6
 
 
 def test_out_of_range_images_are_flagged_not_silent(H, cuda):
