@@ -45,27 +45,32 @@ __device__ __forceinline__ unsigned hash_slot(unsigned key) {
 
 // =============================================================================================
 // extract_palette: one CTA (512 threads) per image.
-//   1. every row (pixel) is packed to a 32-bit key; lanes holding the same key elect the lane with
-//      the earliest row (warp match) and only that lane touches the hash table;
-//   2. the table keeps (key, earliest row) per colour  -> first-occurrence order of
-//      UniqueWithCountsV2 (io_utils.py:46-57);
-//   3. entries are ranked by earliest row, and for "grayness" re-ranked by the float32 key
+//   1. every row (pixel) is packed to a 32-bit key; rows are visited in "stream order" (bottom2top: from the last
+//      row backwards, io_utils.py:47-49) so that the position in the stream is what UniqueWithCountsV2 ranks by;
+//      lanes holding the same key elect the lane with the earliest position (warp vote / match) and only that
+//      lane touches the hash table;
+//   2. the table keeps (key, earliest position) per colour -> first-occurrence order (io_utils.py:46-57);
+//   3. entries are ranked by earliest position, and for "grayness" re-ranked by the float32 key
 //      ((r*0.2989+g*0.5870)+b*0.1140)+a*0 with ties broken by first occurrence = stable argsort
 //      (io_utils.py:51-55); "shuffled" (io_utils.py:56-58) re-ranks by caller-provided random keys the same way;
 //   4. rows n..255 are INVALID_INDEX_COLOR (io_utils.py:61-63, configuration.py:32).
-// The pass is a chain load -> match -> hash per row, so what bounds it is how many loads are in flight: every thread
-// issues EIGHT independent loads before it touches the table (a batch of 4096 rows per CTA; 64 registers per thread
-// keep two CTAs per SM, so the 256 pairs of a cfgB batch are resident together), and when the image fits in two
-// batches (rows <= 512 x 16 = 8192: a 64 x 64 source||target pair exactly) the packed keys stay in registers, so the
-// index pass of the fused variant reads no pixel a second time.
+// The pass is a chain load -> vote -> hash per row: what bounds it is the number of loads in flight and the
+// instructions per row (ncu: 120 thread-instructions per pixel before this version, 1.7 issued per clock).  So:
+//   * every thread issues EIGHT independent loads before it touches the table (a batch of 4096 rows per CTA);
+//   * sprites are mostly runs of one colour (83 % transparent black): a warp whose 32 rows all carry the key this
+//     warp inserted last skips the step after one vote — positions only grow along the stream, so the table
+//     cannot change;
+//   * when the image fits (rows <= 512 x 16 = 8192: a 64 x 64 source||target pair exactly) the packed keys are
+//     parked in shared memory, so the index pass of the fused variant reads no pixel a second time; its lookup is
+//     skipped when a thread's key repeats.
 // =============================================================================================
 constexpr int PAL_THREADS = 512;
-constexpr int PAL_HASH_BITS = 11;
-constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;
+constexpr int PAL_HASH_BITS = 10;
+constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;         // 4 x the 256 colours a valid image can have
 constexpr int PAL_MAX = PH_MAX_PALETTE_SIZE;
 constexpr int PAL_INFLIGHT = 8;                           // loads in flight per thread
 constexpr int PAL_BATCH = PAL_THREADS * PAL_INFLIGHT;     // rows per batch
-constexpr int PAL_KEEP = 16;                              // keys a thread keeps in registers (cached variant)
+constexpr int PAL_KEEP = 16;                              // keys per thread parked in shared memory (cached variant)
 
 // U8: pixels are the decoded PNG's uint8 RGBA (4 B, already the packed key); otherwise int32 RGBA (16 B).
 template <bool U8>
@@ -82,9 +87,9 @@ __device__ __forceinline__ unsigned load_pixel_key(const void* src0, const void*
 // FUSED_INDEX: also index both images of the pair from the same CTA-resident table
 // (dataset_utils.py:148-149 in the same launch): after the colours are ranked, each table slot is
 // rewritten to (key, final palette index) and every pixel is looked up with one probe.
-// CACHED: rows <= PAL_THREADS * PAL_KEEP, the keys of the thread's rows stay in registers.
+// CACHED: rows <= PAL_THREADS * PAL_KEEP, the keys of the image stay in shared memory.
 template <bool FUSED_INDEX, bool U8, bool CACHED>
-__global__ void __launch_bounds__(PAL_THREADS, 2) extract_palette_kernel(
+__global__ void __launch_bounds__(PAL_THREADS, 3) extract_palette_kernel(
     const void* __restrict__ image, const void* __restrict__ image2, int64_t rows, int ordering,
     const float* __restrict__ shuffle_keys, int4* __restrict__ palette, int* __restrict__ ncolors,
     int* __restrict__ indexed, int* __restrict__ indexed2) {
@@ -93,6 +98,7 @@ __global__ void __launch_bounds__(PAL_THREADS, 2) extract_palette_kernel(
   __shared__ unsigned first_order[PAL_MAX];  // keys in first-occurrence order
   __shared__ float gray[PAL_MAX];            // secondary sort key in first-occurrence order
   __shared__ int final_rank[PAL_MAX];        // palette row of the colour with first-occurrence rank i
+  __shared__ unsigned keybuf[(CACHED && FUSED_INDEX) ? PAL_KEEP * PAL_THREADS : 1];  // [row slot][thread]: conflict-free
   __shared__ int s_count, s_bad, s_n;
 
   const int64_t b = blockIdx.x;
@@ -106,58 +112,62 @@ __global__ void __launch_bounds__(PAL_THREADS, 2) extract_palette_kernel(
   const void* src0 = static_cast<const char*>(image) + (size_t)b * per_image * px_bytes;
   const void* src1 = image2 ? static_cast<const char*>(image2) + (size_t)b * per_image * px_bytes : nullptr;
   const bool reversed = ordering == PH_ORDER_BOTTOM2TOP;
+  // stream position t -> row of the image
+  auto row_of = [&](int64_t t) { return reversed ? rows - 1 - t : t; };
 
-  unsigned kept[CACHED ? PAL_KEEP : 1];
   bool bad = false;
-  // one batch: PAL_INFLIGHT independent loads per thread, then the match / hash step of each row
-  auto insert_batch = [&](auto nc, const int64_t row0, unsigned* keep) {
-    constexpr int NC = decltype(nc)::value;  // rows per thread in this batch = independent loads in flight
-    unsigned key[NC];
+  bool have_last = false;   // warp-uniform: this warp's previous step inserted (or found) exactly the key `last_key`
+  unsigned last_key = 0;
+  const int64_t nbatch = (rows + PAL_BATCH - 1) / PAL_BATCH;
+#pragma unroll 1
+  for (int64_t bt = 0; bt < nbatch; ++bt) {
+    // one batch: PAL_INFLIGHT independent loads per thread, then the vote / hash step of each row
+    unsigned key[PAL_INFLIGHT];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int64_t r = row0 + k * PAL_THREADS + tid;
-      key[k] = r < rows ? load_pixel_key<U8>(src0, src1, r, bad) : 0u;
-      if (keep != nullptr) keep[k] = key[k];
+    for (int k = 0; k < PAL_INFLIGHT; ++k) {
+      const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
+      key[k] = t < rows ? load_pixel_key<U8>(src0, src1, row_of(t), bad) : 0u;
+      if (CACHED && FUSED_INDEX) keybuf[((int)bt * PAL_INFLIGHT + k) * PAL_THREADS + tid] = key[k];
     }
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      const int64_t r = row0 + k * PAL_THREADS + tid;
-      const bool active = r < rows;
-      // warp de-duplication: among lanes with the same colour keep the one with the earliest row
+    for (int k = 0; k < PAL_INFLIGHT; ++k) {
+      const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
+      const bool active = t < rows;
       const unsigned amask = __ballot_sync(0xffffffffu, active);
-      if (!active) continue;
-      const unsigned peers = __match_any_sync(amask, key[k]);
-      const int leader = reversed ? 31 - __clz(peers) : __ffs(peers) - 1;
-      if (lane != leader) continue;
-      if (*(volatile int*)&s_count > PAL_MAX) continue;  // already overflowed: result is "too many"
-      const unsigned pos = (unsigned)(reversed ? rows - 1 - r : r);
-      const unsigned long long word = ((unsigned long long)key[k] << 32) | pos;
-      unsigned h = hash_slot<PAL_HASH_BITS>(key[k]);
-      for (int probe = 0; probe < PAL_HASH_SIZE; ++probe) {
-        unsigned long long cur = *(volatile unsigned long long*)&table[h];
-        if (cur == SLOT_EMPTY) {
-          cur = atomicCAS(&table[h], SLOT_EMPTY, word);
-          if (cur == SLOT_EMPTY) { atomicAdd(&s_count, 1); break; }
+      if (amask == 0u) break;  // warp-uniform: past the end of the image
+      if (active) {
+        const int first = __ffs(amask) - 1;
+        const unsigned k0 = __shfl_sync(amask, key[k], first);
+        int leader = first;
+        if (__all_sync(amask, key[k] == k0)) {
+          // the whole warp holds one colour; if it is the one this warp dealt with last, its earliest position is
+          // already in the table (positions grow along the stream)
+          if (have_last && k0 == last_key) leader = -1;
+          have_last = true;
+          last_key = k0;
+        } else {
+          // mixed warp: among lanes with the same colour keep the one with the earliest position
+          leader = __ffs(__match_any_sync(amask, key[k])) - 1;
+          have_last = false;
         }
-        if ((unsigned)(cur >> 32) == key[k]) {
-          if ((unsigned)cur > pos) atomicMin(&table[h], word);
-          break;
+        if (lane == leader && *(volatile int*)&s_count <= PAL_MAX) {  // after an overflow the result is "too many"
+          const unsigned long long word = ((unsigned long long)key[k] << 32) | (unsigned)t;
+          unsigned h = hash_slot<PAL_HASH_BITS>(key[k]);
+          for (int probe = 0; probe < PAL_HASH_SIZE; ++probe) {
+            unsigned long long cur = *(volatile unsigned long long*)&table[h];
+            if (cur == SLOT_EMPTY) {
+              cur = atomicCAS(&table[h], SLOT_EMPTY, word);
+              if (cur == SLOT_EMPTY) { atomicAdd(&s_count, 1); break; }
+            }
+            if ((unsigned)(cur >> 32) == key[k]) {
+              if ((unsigned)cur > (unsigned)t) atomicMin(&table[h], word);
+              break;
+            }
+            h = (h + 1) & (PAL_HASH_SIZE - 1);
+          }
         }
-        h = (h + 1) & (PAL_HASH_SIZE - 1);
       }
     }
-  };
-  if (CACHED && U8) {
-    // 4-byte pixels: the whole image (16 loads of one register each per thread) is in flight at once
-    insert_batch(std::integral_constant<int, PAL_KEEP>{}, 0, &kept[0]);
-  } else if (CACHED) {
-#pragma unroll
-    for (int bt = 0; bt < PAL_KEEP / PAL_INFLIGHT; ++bt)  // rows beyond the image: inactive
-      insert_batch(std::integral_constant<int, PAL_INFLIGHT>{}, (int64_t)bt * PAL_BATCH, &kept[bt * PAL_INFLIGHT]);
-  } else {
-    const int64_t nbatch = (rows + PAL_BATCH - 1) / PAL_BATCH;
-#pragma unroll 1
-    for (int64_t bt = 0; bt < nbatch; ++bt) insert_batch(std::integral_constant<int, PAL_INFLIGHT>{}, bt * PAL_BATCH, nullptr);
   }
   if (bad) s_bad = 1;
   __syncthreads();
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(PAL_THREADS, 2) extract_palette_kernel(
   __syncthreads();
   const int n = s_n;  // == count
 
-  // rank by earliest row -> first-occurrence order
+  // rank by earliest position -> first-occurrence order
   if (tid < n) {
     const unsigned long long me = entries[tid];
     const unsigned mypos = (unsigned)me;
@@ -236,35 +246,45 @@ __global__ void __launch_bounds__(PAL_THREADS, 2) extract_palette_kernel(
     // a pixel equal to the filler colour also matches every padding row: scatter_nd adds them (io_utils.py:84-91)
     const unsigned filler_key = pack_rgba(filler);
     const int filler_extra = (PAL_MAX * (PAL_MAX - 1) - n * (n - 1)) / 2;  // sum of n..255
+    bool have_prev = false;  // this thread's previous pixel: same colour -> same index, no probe
+    unsigned prev_key = 0;
+    int prev_idx = 0;
     auto lookup = [&](unsigned key) {
+      if (have_prev && key == prev_key) return prev_idx;
       unsigned h = hash_slot<PAL_HASH_BITS>(key);
       unsigned long long w = table[h];
       while ((unsigned)(w >> 32) != key || w == SLOT_EMPTY) { h = (h + 1) & (PAL_HASH_SIZE - 1); w = table[h]; }
       int idx = (int)(unsigned)w;
       if (key == filler_key) idx += filler_extra;
+      have_prev = true; prev_key = key; prev_idx = idx;
       return idx;
     };
     if (CACHED) {
-#pragma unroll
+#pragma unroll 4
       for (int i = 0; i < PAL_KEEP; ++i) {
-        const int64_t r = (int64_t)(i / PAL_INFLIGHT) * PAL_BATCH + (i % PAL_INFLIGHT) * PAL_THREADS + tid;
-        if (r < rows) ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(kept[i]);
+        const int64_t t = (int64_t)i * PAL_THREADS + tid;
+        if (t < rows) {
+          const int64_t r = row_of(t);
+          ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(keybuf[i * PAL_THREADS + tid]);
+        }
       }
     } else {
       bool ignore = false;
-      const int64_t nbatch = (rows + PAL_BATCH - 1) / PAL_BATCH;
 #pragma unroll 1
-      for (int64_t bt = 0; bt < nbatch; ++bt) {  // the second read of the pixels (L2), four loads in flight again
+      for (int64_t bt = 0; bt < nbatch; ++bt) {  // the second read of the pixels (L2), eight loads in flight again
         unsigned key[PAL_INFLIGHT];
 #pragma unroll
         for (int k = 0; k < PAL_INFLIGHT; ++k) {
-          const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
-          key[k] = r < rows ? load_pixel_key<U8>(src0, src1, r, ignore) : 0u;
+          const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
+          key[k] = t < rows ? load_pixel_key<U8>(src0, src1, row_of(t), ignore) : 0u;
         }
 #pragma unroll
         for (int k = 0; k < PAL_INFLIGHT; ++k) {
-          const int64_t r = bt * PAL_BATCH + k * PAL_THREADS + tid;
-          if (r < rows) ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(key[k]);
+          const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
+          if (t < rows) {
+            const int64_t r = row_of(t);
+            ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(key[k]);
+          }
         }
       }
     }
