@@ -4,8 +4,6 @@
 //
 // Reference semantics: io_utils.py:25-65 (extract_palette), :78-93 (rgba_to_indexed), :96-103
 // (indexed_to_rgba), pix2pix_model.py:300-301 (one-hot), dataset_utils.py:138-151 (call site).
-#include <type_traits>
-
 #include "common.cuh"
 #include "hist_internal.cuh"
 
@@ -45,52 +43,68 @@ __device__ __forceinline__ unsigned hash_slot(unsigned key) {
 
 // =============================================================================================
 // extract_palette: one CTA (512 threads) per image.
-//   1. every row (pixel) is packed to a 32-bit key; rows are visited in "stream order" (bottom2top: from the last
-//      row backwards, io_utils.py:47-49) so that the position in the stream is what UniqueWithCountsV2 ranks by;
-//      lanes holding the same key elect the lane with the earliest position (warp vote / match) and only that
-//      lane touches the hash table;
-//   2. the table keeps (key, earliest position) per colour -> first-occurrence order (io_utils.py:46-57);
-//   3. entries are ranked by earliest position, and for "grayness" re-ranked by the float32 key
+//   1. every row (pixel) is packed to a 32-bit key; lanes holding the same key elect the lane with
+//      the earliest row (warp match) and only that lane touches the hash table;
+//   2. the table keeps (key, earliest row) per colour  -> first-occurrence order of
+//      UniqueWithCountsV2 (io_utils.py:46-57);
+//   3. entries are ranked by earliest row, and for "grayness" re-ranked by the float32 key
 //      ((r*0.2989+g*0.5870)+b*0.1140)+a*0 with ties broken by first occurrence = stable argsort
 //      (io_utils.py:51-55); "shuffled" (io_utils.py:56-58) re-ranks by caller-provided random keys the same way;
 //   4. rows n..255 are INVALID_INDEX_COLOR (io_utils.py:61-63, configuration.py:32).
-// The pass is a chain load -> vote -> hash per row: what bounds it is the number of loads in flight and the
-// instructions per row (ncu: 120 thread-instructions per pixel before this version, 1.7 issued per clock).  So:
-//   * every thread issues EIGHT independent loads before it touches the table (a batch of 4096 rows per CTA);
-//   * sprites are mostly runs of one colour (83 % transparent black): a warp whose 32 rows all carry the key this
-//     warp inserted last skips the step after one vote — positions only grow along the stream, so the table
-//     cannot change;
-//   * when the image fits (rows <= 512 x 16 = 8192: a 64 x 64 source||target pair exactly) the packed keys are
-//     parked in shared memory, so the index pass of the fused variant reads no pixel a second time; its lookup is
-//     skipped when a thread's key repeats.
+// The pass is a chain load -> match -> hash per row (~100 instructions per pixel), i.e. bound by latency and issue
+// rate, not by bytes: every thread issues four independent loads before it touches the table, and when the image
+// fits (rows <= 512 x 16 = 8192: a 64 x 64 source||target pair exactly) the packed keys stay in registers, so the
+// index pass of the fused variant reads no pixel a second time.  Measured (bench.py, tools/gpu_r2_d.sh): 4096 pairs
+// 186 us = 3.6 TB/s of the 20 B per pixel that move (55 % of the HBM copy rate); a cfgB batch of 256 pairs is one
+// CTA per pair = 28 warps per SM and takes 24.6 us, of which the dependent chain of one CTA is ~16 us.  Splitting a
+// pair over a cluster of 2 or 4 CTAs (tables merged into rank 0's through distributed shared memory, finished
+// table copied back for the index pass) was built and measured SLOWER — 28.7 us and 36.9 us: three cluster barriers
+// and the merge cost more than the halved row loop saves — and removed again.
 // =============================================================================================
 constexpr int PAL_THREADS = 512;
-constexpr int PAL_HASH_BITS = 10;
-constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;         // 4 x the 256 colours a valid image can have
+constexpr int PAL_HASH_BITS = 11;
+constexpr int PAL_HASH_SIZE = 1 << PAL_HASH_BITS;
 constexpr int PAL_MAX = PH_MAX_PALETTE_SIZE;
-constexpr int PAL_INFLIGHT = 8;                           // loads in flight per thread
-constexpr int PAL_BATCH = PAL_THREADS * PAL_INFLIGHT;     // rows per batch
-constexpr int PAL_KEEP = 16;                              // keys per thread parked in shared memory (cached variant)
+constexpr int PAL_INFLIGHT = 4;                           // loads in flight per thread
+constexpr int PAL_KEEP = 16;                              // keys a thread keeps in registers (cached variant)
 
 // U8: pixels are the decoded PNG's uint8 RGBA (4 B, already the packed key); otherwise int32 RGBA (16 B).
 template <bool U8>
-__device__ __forceinline__ unsigned load_pixel_key(const void* src0, const void* src1, int64_t r, bool& bad) {
+__device__ __forceinline__ unsigned load_pixel_key(const void* src0, const void* src1, int r, bool& bad) {
   // src1 != nullptr: rows interleave source/target pixels (dataset_utils.py:142-145)
   const void* base = (src1 != nullptr && (r & 1)) ? src1 : src0;
-  const int64_t i = src1 != nullptr ? (r >> 1) : r;
+  const int i = src1 != nullptr ? (r >> 1) : r;
   if (U8) return __ldg(static_cast<const unsigned*>(base) + i);
   const int4 c = __ldg(static_cast<const int4*>(base) + i);
   if (!in_byte_range(c)) bad = true;
   return pack_rgba(c);
 }
 
+// (key, position) into an open-addressing table that keeps the smallest position per key
+__device__ __forceinline__ void palette_table_insert(unsigned long long* table, int* count, unsigned key, unsigned pos) {
+  const unsigned long long word = ((unsigned long long)key << 32) | pos;
+  unsigned h = hash_slot<PAL_HASH_BITS>(key);
+  for (int probe = 0; probe < PAL_HASH_SIZE; ++probe) {
+    unsigned long long cur = *(volatile unsigned long long*)&table[h];
+    if (cur == SLOT_EMPTY) {
+      cur = atomicCAS(&table[h], SLOT_EMPTY, word);
+      if (cur == SLOT_EMPTY) { atomicAdd(count, 1); return; }
+    }
+    if ((unsigned)(cur >> 32) == key) {
+      if ((unsigned)cur > pos) atomicMin(&table[h], word);
+      return;
+    }
+    h = (h + 1) & (PAL_HASH_SIZE - 1);
+  }
+}
+
 // FUSED_INDEX: also index both images of the pair from the same CTA-resident table
 // (dataset_utils.py:148-149 in the same launch): after the colours are ranked, each table slot is
 // rewritten to (key, final palette index) and every pixel is looked up with one probe.
-// CACHED: rows <= PAL_THREADS * PAL_KEEP, the keys of the image stay in shared memory.
+// CACHED: rows <= PAL_THREADS * PAL_KEEP = 8192, the keys of the thread's rows stay in registers.
 template <bool FUSED_INDEX, bool U8, bool CACHED>
 __global__ void __launch_bounds__(PAL_THREADS, 3) extract_palette_kernel(
-    const void* __restrict__ image, const void* __restrict__ image2, int64_t rows, int ordering,
+    const void* __restrict__ image, const void* __restrict__ image2, int64_t rows64, int ordering,
     const float* __restrict__ shuffle_keys, int4* __restrict__ palette, int* __restrict__ ncolors,
     int* __restrict__ indexed, int* __restrict__ indexed2) {
   __shared__ unsigned long long table[PAL_HASH_SIZE];
@@ -98,194 +112,165 @@ __global__ void __launch_bounds__(PAL_THREADS, 3) extract_palette_kernel(
   __shared__ unsigned first_order[PAL_MAX];  // keys in first-occurrence order
   __shared__ float gray[PAL_MAX];            // secondary sort key in first-occurrence order
   __shared__ int final_rank[PAL_MAX];        // palette row of the colour with first-occurrence rank i
-  __shared__ unsigned keybuf[(CACHED && FUSED_INDEX) ? PAL_KEEP * PAL_THREADS : 1];  // [row slot][thread]: conflict-free
-  __shared__ int s_count, s_bad, s_n;
+  __shared__ int s_count, s_bad, s_n, s_fail;
 
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
+  const int rows = (int)rows64;  // < 2^31 (checked by the launcher): 32-bit row arithmetic throughout
   for (int i = tid; i < PAL_HASH_SIZE; i += PAL_THREADS) table[i] = SLOT_EMPTY;
-  if (tid == 0) { s_count = 0; s_bad = 0; s_n = 0; }
+  if (tid == 0) { s_count = 0; s_bad = 0; s_n = 0; s_fail = 0; }
   __syncthreads();
 
-  const int64_t per_image = image2 ? rows / 2 : rows;
+  const int per_image = image2 ? rows / 2 : rows;
   const size_t px_bytes = U8 ? 4 : 16;
   const void* src0 = static_cast<const char*>(image) + (size_t)b * per_image * px_bytes;
   const void* src1 = image2 ? static_cast<const char*>(image2) + (size_t)b * per_image * px_bytes : nullptr;
+  int* const idx0 = FUSED_INDEX ? indexed + b * per_image : nullptr;
+  int* const idx1 = FUSED_INDEX ? indexed2 + b * per_image : nullptr;
   const bool reversed = ordering == PH_ORDER_BOTTOM2TOP;
-  // stream position t -> row of the image
-  auto row_of = [&](int64_t t) { return reversed ? rows - 1 - t : t; };
+  auto row_at = [&](int j) { return j * PAL_THREADS + tid; };  // row handled by this thread in its slot j
 
+  unsigned kept[CACHED ? PAL_KEEP : 1];
   bool bad = false;
-  bool have_last = false;   // warp-uniform: this warp's previous step inserted (or found) exactly the key `last_key`
-  unsigned last_key = 0;
-  const int64_t nbatch = (rows + PAL_BATCH - 1) / PAL_BATCH;
-#pragma unroll 1
-  for (int64_t bt = 0; bt < nbatch; ++bt) {
-    // one batch: PAL_INFLIGHT independent loads per thread, then the vote / hash step of each row
+  // one batch: PAL_INFLIGHT independent loads per thread, then the match / hash step of each row
+  auto insert_batch = [&](const int bt, unsigned* keep) {
     unsigned key[PAL_INFLIGHT];
 #pragma unroll
     for (int k = 0; k < PAL_INFLIGHT; ++k) {
-      const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
-      key[k] = t < rows ? load_pixel_key<U8>(src0, src1, row_of(t), bad) : 0u;
-      if (CACHED && FUSED_INDEX) keybuf[((int)bt * PAL_INFLIGHT + k) * PAL_THREADS + tid] = key[k];
+      const int r = row_at(bt * PAL_INFLIGHT + k);
+      key[k] = r < rows ? load_pixel_key<U8>(src0, src1, r, bad) : 0u;
+      if (keep != nullptr) keep[k] = key[k];
     }
 #pragma unroll
     for (int k = 0; k < PAL_INFLIGHT; ++k) {
-      const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
-      const bool active = t < rows;
+      const int r = row_at(bt * PAL_INFLIGHT + k);
+      const bool active = r < rows;
+      // warp de-duplication: among lanes with the same colour keep the one with the earliest row
       const unsigned amask = __ballot_sync(0xffffffffu, active);
-      if (amask == 0u) break;  // warp-uniform: past the end of the image
-      if (active) {
-        const int first = __ffs(amask) - 1;
-        const unsigned k0 = __shfl_sync(amask, key[k], first);
-        int leader = first;
-        if (__all_sync(amask, key[k] == k0)) {
-          // the whole warp holds one colour; if it is the one this warp dealt with last, its earliest position is
-          // already in the table (positions grow along the stream)
-          if (have_last && k0 == last_key) leader = -1;
-          have_last = true;
-          last_key = k0;
-        } else {
-          // mixed warp: among lanes with the same colour keep the one with the earliest position
-          leader = __ffs(__match_any_sync(amask, key[k])) - 1;
-          have_last = false;
-        }
-        if (lane == leader && *(volatile int*)&s_count <= PAL_MAX) {  // after an overflow the result is "too many"
-          const unsigned long long word = ((unsigned long long)key[k] << 32) | (unsigned)t;
-          unsigned h = hash_slot<PAL_HASH_BITS>(key[k]);
-          for (int probe = 0; probe < PAL_HASH_SIZE; ++probe) {
-            unsigned long long cur = *(volatile unsigned long long*)&table[h];
-            if (cur == SLOT_EMPTY) {
-              cur = atomicCAS(&table[h], SLOT_EMPTY, word);
-              if (cur == SLOT_EMPTY) { atomicAdd(&s_count, 1); break; }
-            }
-            if ((unsigned)(cur >> 32) == key[k]) {
-              if ((unsigned)cur > (unsigned)t) atomicMin(&table[h], word);
-              break;
-            }
-            h = (h + 1) & (PAL_HASH_SIZE - 1);
-          }
-        }
-      }
+      if (!active) continue;
+      const unsigned peers = __match_any_sync(amask, key[k]);
+      const int leader = reversed ? 31 - __clz(peers) : __ffs(peers) - 1;
+      if (lane != leader) continue;
+      if (*(volatile int*)&s_count > PAL_MAX) continue;  // already overflowed: result is "too many"
+      palette_table_insert(table, &s_count, key[k], (unsigned)(reversed ? rows - 1 - r : r));
     }
+  };
+  if (CACHED) {
+#pragma unroll
+    for (int bt = 0; bt < PAL_KEEP / PAL_INFLIGHT; ++bt) insert_batch(bt, &kept[bt * PAL_INFLIGHT]);  // rows beyond the image: inactive
+  } else {
+    const int nbatch = (rows + PAL_THREADS * PAL_INFLIGHT - 1) / (PAL_THREADS * PAL_INFLIGHT);
+#pragma unroll 1
+    for (int bt = 0; bt < nbatch; ++bt) insert_batch(bt, nullptr);
   }
   if (bad) s_bad = 1;
   __syncthreads();
 
-  const int count = s_count;
-  if (s_bad || count > PAL_MAX) {
-    if (tid == 0) ncolors[b] = s_bad ? PH_PALETTE_BAD_VALUE : count;
+  {
+    const int count = s_count;
+    const bool fail = s_bad || count > PAL_MAX;
     const int4 filler = make_int4(255, 0, 220, 255);
-    for (int k = tid; k < PAL_MAX; k += PAL_THREADS) palette[b * PAL_MAX + k] = filler;
-    if (FUSED_INDEX) {  // the host raises for this image; keep the outputs defined
-      for (int64_t r = tid; r < per_image; r += PAL_THREADS) { indexed[b * per_image + r] = 0; indexed2[b * per_image + r] = 0; }
-    }
-    return;
-  }
-
-  // compact occupied slots
-  for (int i = tid; i < PAL_HASH_SIZE; i += PAL_THREADS) {
-    const unsigned long long w = table[i];
-    if (w != SLOT_EMPTY) entries[atomicAdd(&s_n, 1)] = w;
-  }
-  __syncthreads();
-  const int n = s_n;  // == count
-
-  // rank by earliest position -> first-occurrence order
-  if (tid < n) {
-    const unsigned long long me = entries[tid];
-    const unsigned mypos = (unsigned)me;
-    int rank = 0;
-    for (int e = 0; e < n; ++e) rank += ((unsigned)entries[e] < mypos) ? 1 : 0;
-    const unsigned key = (unsigned)(me >> 32);
-    first_order[rank] = key;
-    float g = 0.f;
-    if (ordering == PH_ORDER_GRAYNESS) {
-      const int4 c = unpack_rgba(key);
-      // float32, non-fused, left to right: the (n,4)x(4,1) product of io_utils.py:51-52
-      g = __fmul_rn((float)c.x, 0.2989f);
-      g = __fadd_rn(g, __fmul_rn((float)c.y, 0.5870f));
-      g = __fadd_rn(g, __fmul_rn((float)c.z, 0.1140f));
-      g = __fadd_rn(g, __fmul_rn((float)c.w, 0.0f));
-    } else if (ordering == PH_ORDER_SHUFFLED) {
-      // tf.random.shuffle(colors): rank by independent uniform keys = a uniformly random permutation of the rows
-      g = __ldg(shuffle_keys + b * PAL_MAX + rank);
-    }
-    gray[rank] = g;
-  }
-  __syncthreads();
-
-  const int4 filler = make_int4(255, 0, 220, 255);
-  int4* out = palette + b * PAL_MAX;
-  if (tid < n) {
-    int rank = tid;
-    if ((ordering == PH_ORDER_GRAYNESS || ordering == PH_ORDER_SHUFFLED) && n > 1) {
-      const float mine = gray[tid];
-      rank = 0;
-      for (int e = 0; e < n; ++e) {
-        const float other = gray[e];
-        rank += (other < mine || (other == mine && e < tid)) ? 1 : 0;  // stable
-      }
-    }
-    out[rank] = unpack_rgba(first_order[tid]);
-    final_rank[tid] = rank;
-  }
-  for (int k = n + tid; k < PAL_MAX; k += PAL_THREADS) out[k] = filler;
-  if (tid == 0) ncolors[b] = n;
-
-  if (FUSED_INDEX) {
-    // final index of each colour -> its table slot (low word)
-    __syncthreads();
-    if (tid < n) {
-      const unsigned key = first_order[tid];
-      unsigned h = hash_slot<PAL_HASH_BITS>(key);
-      while ((unsigned)(table[h] >> 32) != key || table[h] == SLOT_EMPTY) h = (h + 1) & (PAL_HASH_SIZE - 1);
-      table[h] = ((unsigned long long)key << 32) | (unsigned)final_rank[tid];
-    }
-    __syncthreads();
-    // a pixel equal to the filler colour also matches every padding row: scatter_nd adds them (io_utils.py:84-91)
-    const unsigned filler_key = pack_rgba(filler);
-    const int filler_extra = (PAL_MAX * (PAL_MAX - 1) - n * (n - 1)) / 2;  // sum of n..255
-    bool have_prev = false;  // this thread's previous pixel: same colour -> same index, no probe
-    unsigned prev_key = 0;
-    int prev_idx = 0;
-    auto lookup = [&](unsigned key) {
-      if (have_prev && key == prev_key) return prev_idx;
-      unsigned h = hash_slot<PAL_HASH_BITS>(key);
-      unsigned long long w = table[h];
-      while ((unsigned)(w >> 32) != key || w == SLOT_EMPTY) { h = (h + 1) & (PAL_HASH_SIZE - 1); w = table[h]; }
-      int idx = (int)(unsigned)w;
-      if (key == filler_key) idx += filler_extra;
-      have_prev = true; prev_key = key; prev_idx = idx;
-      return idx;
-    };
-    if (CACHED) {
-#pragma unroll 4
-      for (int i = 0; i < PAL_KEEP; ++i) {
-        const int64_t t = (int64_t)i * PAL_THREADS + tid;
-        if (t < rows) {
-          const int64_t r = row_of(t);
-          ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(keybuf[i * PAL_THREADS + tid]);
-        }
-      }
+    int4* out = palette + b * PAL_MAX;
+    if (fail) {
+      if (tid == 0) { ncolors[b] = s_bad ? PH_PALETTE_BAD_VALUE : count; s_fail = 1; }
+      for (int k = tid; k < PAL_MAX; k += PAL_THREADS) out[k] = filler;
     } else {
-      bool ignore = false;
-#pragma unroll 1
-      for (int64_t bt = 0; bt < nbatch; ++bt) {  // the second read of the pixels (L2), eight loads in flight again
-        unsigned key[PAL_INFLIGHT];
-#pragma unroll
-        for (int k = 0; k < PAL_INFLIGHT; ++k) {
-          const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
-          key[k] = t < rows ? load_pixel_key<U8>(src0, src1, row_of(t), ignore) : 0u;
+      // compact occupied slots
+      for (int i = tid; i < PAL_HASH_SIZE; i += PAL_THREADS) {
+        const unsigned long long w = table[i];
+        if (w != SLOT_EMPTY) entries[atomicAdd(&s_n, 1)] = w;
+      }
+      __syncthreads();
+      const int n = s_n;  // == count
+      // rank by earliest row -> first-occurrence order
+      if (tid < n) {
+        const unsigned long long me = entries[tid];
+        const unsigned mypos = (unsigned)me;
+        int rank = 0;
+        for (int e = 0; e < n; ++e) rank += ((unsigned)entries[e] < mypos) ? 1 : 0;
+        const unsigned key = (unsigned)(me >> 32);
+        first_order[rank] = key;
+        float g = 0.f;
+        if (ordering == PH_ORDER_GRAYNESS) {
+          const int4 c = unpack_rgba(key);
+          // float32, non-fused, left to right: the (n,4)x(4,1) product of io_utils.py:51-52
+          g = __fmul_rn((float)c.x, 0.2989f);
+          g = __fadd_rn(g, __fmul_rn((float)c.y, 0.5870f));
+          g = __fadd_rn(g, __fmul_rn((float)c.z, 0.1140f));
+          g = __fadd_rn(g, __fmul_rn((float)c.w, 0.0f));
+        } else if (ordering == PH_ORDER_SHUFFLED) {
+          // tf.random.shuffle(colors): rank by independent uniform keys = a uniformly random permutation of the rows
+          g = __ldg(shuffle_keys + b * PAL_MAX + rank);
         }
-#pragma unroll
-        for (int k = 0; k < PAL_INFLIGHT; ++k) {
-          const int64_t t = bt * PAL_BATCH + k * PAL_THREADS + tid;
-          if (t < rows) {
-            const int64_t r = row_of(t);
-            ((r & 1) ? indexed2 : indexed)[b * per_image + (r >> 1)] = lookup(key[k]);
+        gray[rank] = g;
+      }
+      __syncthreads();
+      if (tid < n) {
+        int rank = tid;
+        if ((ordering == PH_ORDER_GRAYNESS || ordering == PH_ORDER_SHUFFLED) && n > 1) {
+          const float mine = gray[tid];
+          rank = 0;
+          for (int e = 0; e < n; ++e) {
+            const float other = gray[e];
+            rank += (other < mine || (other == mine && e < tid)) ? 1 : 0;  // stable
           }
         }
+        out[rank] = unpack_rgba(first_order[tid]);
+        final_rank[tid] = rank;
+      }
+      for (int k = n + tid; k < PAL_MAX; k += PAL_THREADS) out[k] = filler;
+      if (tid == 0) ncolors[b] = n;
+      if (FUSED_INDEX) {
+        // final index of each colour -> its table slot (low word)
+        __syncthreads();
+        if (tid < n) {
+          const unsigned key = first_order[tid];
+          unsigned h = hash_slot<PAL_HASH_BITS>(key);
+          while ((unsigned)(table[h] >> 32) != key || table[h] == SLOT_EMPTY) h = (h + 1) & (PAL_HASH_SIZE - 1);
+          table[h] = ((unsigned long long)key << 32) | (unsigned)final_rank[tid];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!FUSED_INDEX) return;
+  if (s_fail) {  // the host raises for this image; keep the outputs defined
+    for (int j = 0; row_at(j) < rows; ++j) { const int r = row_at(j); ((r & 1) ? idx1 : idx0)[r >> 1] = 0; }
+    return;
+  }
+  // a pixel equal to the filler colour also matches every padding row: scatter_nd adds them (io_utils.py:84-91)
+  const int n = s_n;
+  const unsigned filler_key = pack_rgba(make_int4(255, 0, 220, 255));
+  const int filler_extra = (PAL_MAX * (PAL_MAX - 1) - n * (n - 1)) / 2;  // sum of n..255
+  auto lookup = [&](unsigned key) {
+    unsigned h = hash_slot<PAL_HASH_BITS>(key);
+    unsigned long long w = table[h];
+    while ((unsigned)(w >> 32) != key || w == SLOT_EMPTY) { h = (h + 1) & (PAL_HASH_SIZE - 1); w = table[h]; }
+    int idx = (int)(unsigned)w;
+    if (key == filler_key) idx += filler_extra;
+    return idx;
+  };
+  if (CACHED) {
+#pragma unroll
+    for (int j = 0; j < PAL_KEEP; ++j) {
+      const int r = row_at(j);
+      if (r < rows) ((r & 1) ? idx1 : idx0)[r >> 1] = lookup(kept[j]);
+    }
+  } else {
+    bool ignore = false;
+    const int nbatch = (rows + PAL_THREADS * PAL_INFLIGHT - 1) / (PAL_THREADS * PAL_INFLIGHT);
+#pragma unroll 1
+    for (int bt = 0; bt < nbatch; ++bt) {  // the second read of the pixels (L2), four loads in flight again
+      unsigned key[PAL_INFLIGHT];
+#pragma unroll
+      for (int k = 0; k < PAL_INFLIGHT; ++k) {
+        const int r = row_at(bt * PAL_INFLIGHT + k);
+        key[k] = r < rows ? load_pixel_key<U8>(src0, src1, r, ignore) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < PAL_INFLIGHT; ++k) {
+        const int r = row_at(bt * PAL_INFLIGHT + k);
+        if (r < rows) ((r & 1) ? idx1 : idx0)[r >> 1] = lookup(key[k]);
       }
     }
   }
@@ -737,7 +722,7 @@ static int launch_extract_any(const void* image, const void* image2, int64_t bat
                               const float* shuffle_keys, int32_t* palette, int32_t* ncolors, int32_t* idx1,
                               int32_t* idx2, cudaStream_t st) {
   PH_CHECK_ARG(batch < (1ll << 31), "batch too large");
-  PH_CHECK_ARG(rows < (1ll << 31), "too many rows per image (%lld)", (long long)rows);
+  PH_CHECK_ARG(rows < (1ll << 31) - 2 * PAL_THREADS * PAL_INFLIGHT, "too many rows per image (%lld)", (long long)rows);
   PH_CHECK_ARG(ordering != PH_ORDER_SHUFFLED || shuffle_keys != nullptr, "'shuffled' ordering needs shuffle keys");
   if (batch == 0) return PH_OK;
   if (rows <= (int64_t)PAL_THREADS * PAL_KEEP)
