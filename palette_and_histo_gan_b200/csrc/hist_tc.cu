@@ -151,6 +151,99 @@ __device__ __forceinline__ ItemRange item_range(const Params& p, int64_t w) {
   return r;
 }
 
+// ---- item epilogue of the forward kernels (all 16 producer warps; named barrier 5).  A whole image is normalised
+//      here; a slice of a tail image delivers its raw sums, and the CTA that delivers the last slice adds them up (in
+//      slice order: deterministic) and normalises — no second kernel, no partials left for the host side to combine.
+//      `S.acc[c][j][i]` holds the raw sums of the item (scaled by 1 / inv_scale). ----
+template <bool FUSE_SSUM, typename SmemT>
+__device__ __forceinline__ void finish_item(SmemT& S, const Params& p, const ItemRange& ir, int tid, int warp, int lane) {
+  named_bar_sync(5, PROD_WARPS * 32);
+  const int t = tid;  // 0..511
+  const int64_t b = ir.b;
+  bool finish = ir.whole;
+  const float item_inv_scale = ir.dedup ? p.inv_scale : p.inv_scale_dense;
+  float dscale = item_inv_scale;  // raw sum -> true scale of the normaliser D
+  if (!ir.whole) {
+    float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
+    for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+      const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
+      dst[e] = S.acc[c][j][i] * item_inv_scale;
+    }
+    __threadfence();
+    named_bar_sync(5, PROD_WARPS * 32);
+    if (t == 0) S.last_flag = atomicAdd(p.tail_counter + (b - p.n_whole), 1) == p.splits - 1;
+    named_bar_sync(5, PROD_WARPS * 32);
+    finish = S.last_flag != 0;
+    if (finish) {
+      __threadfence();
+      const float* src = p.partial + (b - p.n_whole) * (int64_t)p.splits * (3 * BINS * BINS);
+      for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+        float v = 0.f;
+        for (int sidx = 0; sidx < p.splits; ++sidx) v += __ldcg(src + (int64_t)sidx * (3 * BINS * BINS) + e);
+        S.acc[e >> 12][e & 63][(e >> 6) & 63] = v;
+      }
+      dscale = 1.0f;
+      named_bar_sync(5, PROD_WARPS * 32);
+    }
+  }
+  if (finish && p.raw_out != nullptr) {
+    float* dst = p.raw_out + b * (int64_t)(3 * BINS * BINS);
+    for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+      const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
+      dst[e] = S.acc[c][j][i] * dscale;
+    }
+  } else if (finish) {
+    float s = 0.f;
+    for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
+    s = warp_sum(s);
+    if (lane == 0) S.red[warp] = s;
+    named_bar_sync(5, PROD_WARPS * 32);
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < PROD_WARPS; ++k) d += S.red[k];
+    if (t == 0) p.denom[b] = d * dscale;
+    const float inv_d = 1.0f / d;
+    float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
+    if (!FUSE_SSUM) {
+      for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
+        const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
+        dst[e] = S.acc[c][j][i] * inv_d;
+      }
+    } else {
+      // fused Hellinger partial: sum (sqrt(Hp) - sqrt(Ht))^2 of this image (histogram.py:88) while Hp is
+      // on chip; the real image's histogram arrives in two batches of 12 independent loads per thread
+      constexpr int HALF = 3 * BINS * BINS / (PROD_WARPS * 32) / 2;  // 12
+      const float* ht = p.hist_true + b * (int64_t)(3 * BINS * BINS);
+      float part = 0.f;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        float htv[HALF];
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) htv[k] = __ldg(ht + t + (half * HALF + k) * (PROD_WARPS * 32));
+#pragma unroll
+        for (int k = 0; k < HALF; ++k) {
+          const int e = t + (half * HALF + k) * (PROD_WARPS * 32);
+          const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
+          const float h = S.acc[c][j][i] * inv_d;
+          dst[e] = h;
+          const float df = fast_sqrt(h) - fast_sqrt(htv[k]);
+          part = fmaf(df, df, part);
+        }
+      }
+      double dpart = warp_sum((double)part);
+      if (lane == 0) S.red2[warp] = dpart;
+      named_bar_sync(5, PROD_WARPS * 32);
+      if (t == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < PROD_WARPS; ++k) tot += S.red2[k];
+        atomicAdd(p.ssum, tot);
+      }
+    }
+  }
+  named_bar_sync(5, PROD_WARPS * 32);
+}
+
 template <int METHOD, bool FUSE_SSUM>
 __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
   // no-swizzle operand tiles need only 16 B alignment; keeping the pointer derived from the
@@ -324,93 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         }
         if (kb + 1 != nkb) { named_bar_sync(5, PROD_WARPS * 32); continue; }  // acc is read-modified by the next chain
 
-        // ---- item epilogue: all 16 warps.  A whole image is normalised here; a slice of a tail image delivers
-        //      its raw sums, and the CTA that delivers the last slice adds them up (in slice order: deterministic)
-        //      and normalises — no second kernel, no partials left for the host side to combine ----
-        named_bar_sync(5, PROD_WARPS * 32);
-        const int t = tid;  // 0..511
-        bool finish = ir.whole;
-        const float item_inv_scale = ir.dedup ? p.inv_scale : p.inv_scale_dense;
-        float dscale = item_inv_scale;  // raw sum -> true scale of the normaliser D
-        if (!ir.whole) {
-          float* dst = p.partial + ir.pidx * (int64_t)(3 * BINS * BINS);
-          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
-            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
-            dst[e] = S.acc[c][j][i] * item_inv_scale;
-          }
-          __threadfence();
-          named_bar_sync(5, PROD_WARPS * 32);
-          if (t == 0) S.last_flag = atomicAdd(p.tail_counter + (b - p.n_whole), 1) == p.splits - 1;
-          named_bar_sync(5, PROD_WARPS * 32);
-          finish = S.last_flag != 0;
-          if (finish) {
-            __threadfence();
-            const float* src = p.partial + (b - p.n_whole) * (int64_t)p.splits * (3 * BINS * BINS);
-            for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
-              float v = 0.f;
-              for (int sidx = 0; sidx < p.splits; ++sidx) v += __ldcg(src + (int64_t)sidx * (3 * BINS * BINS) + e);
-              S.acc[e >> 12][e & 63][(e >> 6) & 63] = v;
-            }
-            dscale = 1.0f;
-            named_bar_sync(5, PROD_WARPS * 32);
-          }
-        }
-        if (finish && p.raw_out != nullptr) {
-          float* dst = p.raw_out + b * (int64_t)(3 * BINS * BINS);
-          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
-            const int c = e >> 12, i = (e >> 6) & 63, j = e & 63;
-            dst[e] = S.acc[c][j][i] * dscale;
-          }
-        } else if (finish) {
-          float s = 0.f;
-          for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
-          s = warp_sum(s);
-          if (lane == 0) S.red[warp] = s;
-          named_bar_sync(5, PROD_WARPS * 32);
-          float d = 0.f;
-#pragma unroll
-          for (int k = 0; k < PROD_WARPS; ++k) d += S.red[k];
-          if (t == 0) p.denom[b] = d * dscale;
-          const float inv_d = 1.0f / d;
-          float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
-          if (!FUSE_SSUM) {
-            for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
-              const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-              dst[e] = S.acc[c][j][i] * inv_d;
-            }
-          } else {
-            // fused Hellinger partial: sum (sqrt(Hp) - sqrt(Ht))^2 of this image (histogram.py:88) while Hp is
-            // on chip; the real image's histogram arrives in two batches of 12 independent loads per thread
-            constexpr int HALF = 3 * BINS * BINS / (PROD_WARPS * 32) / 2;  // 12
-            const float* ht = p.hist_true + b * (int64_t)(3 * BINS * BINS);
-            float part = 0.f;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-              float htv[HALF];
-#pragma unroll
-              for (int k = 0; k < HALF; ++k) htv[k] = __ldg(ht + t + (half * HALF + k) * (PROD_WARPS * 32));
-#pragma unroll
-              for (int k = 0; k < HALF; ++k) {
-                const int e = t + (half * HALF + k) * (PROD_WARPS * 32);
-                const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-                const float h = S.acc[c][j][i] * inv_d;
-                dst[e] = h;
-                const float df = fast_sqrt(h) - fast_sqrt(htv[k]);
-                part = fmaf(df, df, part);
-              }
-            }
-            double dpart = warp_sum((double)part);
-            if (lane == 0) S.red2[warp] = dpart;
-            named_bar_sync(5, PROD_WARPS * 32);
-            if (t == 0) {
-              double tot = 0.0;
-#pragma unroll
-              for (int k = 0; k < PROD_WARPS; ++k) tot += S.red2[k];
-              atomicAdd(p.ssum, tot);
-            }
-          }
-        }
-        named_bar_sync(5, PROD_WARPS * 32);
+        finish_item<FUSE_SSUM>(S, p, ir, tid, warp, lane);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -448,6 +455,288 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         }
         if (elect_one_sync()) mma_commit(&S.d_full);
         // the accumulators are free again once the epilogue warps have drained this chain
+        mbar_wait(&S.d_empty, chain_par);
+        tc_fence_after_sync();
+        chain_par ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+
+// =============================================================================================
+// Variant with the A operand in TENSOR MEMORY (default; PH_FWD_A=smem selects the kernel above).
+//
+// ncu on the kernel above: the shared-memory pipe is the scarcest resource (operand tiles written once by the
+// producers — 443 store wavefronts per 32-pixel stage — and read once by the MMAs, ~85 % busy); removing 14 % of the
+// weight-generation instructions did not change its run time, leaving out the A tiles' stores (timing experiment)
+// took 8 % off.  Here the u-side operand never touches shared memory:
+//   * M = 64: a row per u-bin.  Row m of an M = 64 tile lives in TMEM lane 32 (m / 16) + m % 16 (+ 16 for a second,
+//     interleaved tile of the same columns; an instruction's A and D must use the same lane offset —
+//     tools/m64_layout_test.cu).  A producer thread = (bin, 16 pixels): lanes 0-15 of a warp hold the bins
+//     16 q .. 16 q + 15 for pixels 0-15 of the stage, lanes 16-31 the same bins for pixels 16-31, and every thread
+//     writes [hi (8 columns) | lo (8 columns)] of its own row with one tcgen05.st per channel: no exchange between
+//     threads, hi and lo stacked along K instead of M.
+//   * per channel, 16-pixel half h and stage:  D_h += A_hi[h] . [B_hi | B_lo]^T  (M64 N128 K16, 64 cycles) and
+//     D_h[:, 0:64] += A_lo[h] . B_hi^T  (M64 N64 K16, 44 cycles): the three products of the emulation (the M = 128
+//     kernel's single instruction also computes lo.lo); D_0 and D_1 (lane offsets 0 / 16) are partial sums over the two
+//     pixel halves and are added in the epilogue.  Tensor pipe 648 cycles per stage instead of 384.
+//   * the eight A warps alternate stages (set 0: even, set 1: odd), two 48-column A slots in TMEM; the v side is
+//     produced into shared memory as before (24 KB per stage instead of 48).
+// Shared-memory traffic per stage: 192 + ~60 store, ~290 load wavefronts, 288 cycles of MMA operand reads
+// (B_hi | B_lo once, B_hi once more, per half and channel) instead of 443 / ~290 / 384.
+// =============================================================================================
+constexpr int NSB = 3;                      // B operand stages in shared memory
+constexpr int NSA = 2;                      // A operand slots in tensor memory (one per A warp set)
+constexpr int B_STAGE_BYTES = 3 * TILE_BYTES;  // B tiles of the three channels
+constexpr int A_COL0 = 3 * D_COLS;          // 384: first A column
+constexpr int A_SLOT_COLS = 3 * 16;         // per slot: three channels x [hi 8 | lo 8] columns
+static_assert(A_COL0 + NSA * A_SLOT_COLS <= TMEM_COLS, "TMEM budget");
+
+struct SmemA {
+  alignas(128) unsigned char bt[NSB][B_STAGE_BYTES];  // 72 KB
+  float acc[3][BINS][BINS + 1];
+  PxSlot px[PR];
+  float dom[2][BINS];
+  float red[PROD_WARPS];
+  double red2[PROD_WARPS];
+  int last_flag;
+  alignas(8) uint64_t px_full[PR], px_empty[PR], b_full[NSB], b_empty[NSB], a_full[NSA], a_empty[NSA], d_full, d_empty;
+  uint32_t tmem_base;
+};
+
+template <int METHOD, bool FUSE_SSUM>
+__global__ void __launch_bounds__(THREADS, 1) hist_fwd_tca_kernel(Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemA& S = *reinterpret_cast<SmemA*>(smem_raw);
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+
+  if (tid == 0) {
+    // a pixel slot is read by the four A warps of one set and the eight B warps
+    for (int i = 0; i < PR; ++i) { mbar_init(&S.px_full[i], 1); mbar_init(&S.px_empty[i], A_WARPS / 2 + B_WARPS); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(&S.b_full[i], B_WARPS); mbar_init(&S.b_empty[i], 1); }
+    for (int i = 0; i < NSA; ++i) { mbar_init(&S.a_full[i], A_WARPS / 2); mbar_init(&S.a_empty[i], 1); }
+    mbar_init(&S.d_full, 1);
+    mbar_init(&S.d_empty, PROD_WARPS);
+    fence_mbar_init();
+  }
+  if (tid < BINS) { S.dom[0][tid] = p.dom_u[tid] * p.coord_scale; S.dom[1][tid] = p.dom_v[tid] * p.coord_scale; }
+  if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+
+  const int64_t first = blockIdx.x, step = gridDim.x;
+
+  if (warp >= PX_WARP0) {
+    // ===================== pixel pass (as in the kernel above) =====================
+    const int me = warp - PX_WARP0;
+    uint32_t it = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const int64_t b = ir.b;
+      const uint32_t px0 = ir.px0, px1 = ir.px1;
+      for (uint32_t base = px0; base < px1; base += KB, ++it) {
+        if ((int)(it % PXW) != me) continue;
+        const int slot = it % PR;
+        const uint32_t px = base + lane;
+        float r = 0.f, g = 0.f, bl = 0.f, mult = 1.f;
+        const bool valid = px < px1;
+        if (valid && ir.dedup) {
+          const float4 q = __ldg(p.ulist + b * DEDUP_MAX + px);
+          r = q.x; g = q.y; bl = q.z; mult = q.w;
+        } else if (valid) {
+          const float* src = p.image + (b * p.npix + px) * p.channels;
+          if (p.channels == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+            r = q.x; g = q.y; bl = q.z;
+          } else {
+            r = __ldg(src); g = __ldg(src + 1); bl = __ldg(src + 2);
+          }
+        }
+        const float x0 = fmaf(r, 0.5f, 0.5f), x1 = fmaf(g, 0.5f, 0.5f), x2 = fmaf(bl, 0.5f, 0.5f);
+        const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
+        const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
+        const float d_rg = logf(e0 / e1) * p.coord_scale, d_rb = logf(e0 / e2) * p.coord_scale,
+                    d_gb = logf(e1 / e2) * p.coord_scale;
+        mbar_wait_relaxed(&S.px_empty[slot], ((it / PR) & 1) ^ 1, 400);
+        PxSlot& o = S.px[slot];
+        o.u[0][lane] = d_rg;  o.v[0][lane] = d_rb;
+        o.u[1][lane] = -d_rg; o.v[1][lane] = d_gb;
+        o.u[2][lane] = -d_rb; o.v[2][lane] = -d_gb;
+        const float a_iy = valid ? iy * mult * (ir.dedup ? p.iy_scale : 1.0f) : 0.f;
+        if (a_iy > tcgen::IY_OPERAND_LIMIT) *reinterpret_cast<volatile int*>(p.status) = PH_ASYNC_RANGE;
+        o.iy[lane] = a_iy;
+        mbar_arrive_warp(&S.px_full[slot]);
+      }
+    }
+  } else if (warp < PROD_WARPS) {
+    // ===================== operand producers (A -> TMEM: warps 0-7, B -> smem: warps 8-15) + epilogue ==========
+    const int side = warp >> 3;                 // warp-uniform
+    const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
+    // A side: quadrant q = warp % 4 (the TMEM lanes this warp may touch), set = stages it handles; thread = (bin, 16 px)
+    const int quad = warp & 3, aset = (warp >> 2) & 1;
+    const int a_bin = quad * 16 + (lane & 15), a_half = lane >> 4;
+    // B side: thread = (bin, 8 px) as in the kernel above
+    const int b_bin = tid & 63, po = (tid >> 6) & 3;
+    const float c_bin = side == 0 ? S.dom[0][a_bin] : S.dom[1][b_bin];
+    const f32x2 negc = pack2(-c_bin, -c_bin);
+    const uint32_t row_off = (uint32_t)(po * T_KB_BYTES + (b_bin >> 3) * 128 + (b_bin & 7) * 16);
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    // epilogue role: lanes 32 quad .. (u-bins 16 quad .. + 15, tile = lane / 16), column block cs = warp / 4
+    const int cs = warp >> 2;
+    uint32_t it = 0, chain = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
+      for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+        const int slot = it % PR;
+        if (side == 1) {
+          // ---------------- B operand of this stage -> shared memory ----------------
+          const int stage = it % NSB;
+          mbar_wait(&S.px_full[slot], (it / PR) & 1);
+          const PxSlot& in = S.px[slot];
+          ulonglong2 xx[3][2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            xx[c][0] = *reinterpret_cast<const ulonglong2*>(&in.v[c][po * 8]);
+            xx[c][1] = *reinterpret_cast<const ulonglong2*>(&in.v[c][po * 8 + 4]);
+          }
+          mbar_arrive_warp(&S.px_empty[slot]);
+          uint4 hi[3], lo[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            f32x2 w0, w1, w2, w3;
+            weight4<METHOD>(xx[c][0].x, xx[c][0].y, negc, wa2, wb2, w0, w1);
+            weight4<METHOD>(xx[c][1].x, xx[c][1].y, negc, wa2, wb2, w2, w3);
+            split_f16x2(w0, mone2, hi[c].x, lo[c].x);
+            split_f16x2(w1, mone2, hi[c].y, lo[c].y);
+            split_f16x2(w2, mone2, hi[c].z, lo[c].z);
+            split_f16x2(w3, mone2, hi[c].w, lo[c].w);
+          }
+          mbar_wait(&S.b_empty[stage], ((it / NSB) & 1) ^ 1);  // the MMAs that read this stage are done
+          unsigned char* tile = &S.bt[stage][row_off];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            *reinterpret_cast<uint4*>(tile + c * TILE_BYTES) = hi[c];
+            *reinterpret_cast<uint4*>(tile + c * TILE_BYTES + 1024) = lo[c];
+          }
+          fence_proxy_async_smem();
+          mbar_arrive_warp(&S.b_full[stage]);
+        } else if ((int)(it & 1) == aset) {
+          // ---------------- A operand of this stage -> tensor memory (this warp set's slot) ----------------
+          mbar_wait(&S.px_full[slot], (it / PR) & 1);
+          const PxSlot& in = S.px[slot];
+          ulonglong2 iw[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) iw[q4] = *reinterpret_cast<const ulonglong2*>(&in.iy[a_half * 16 + q4 * 4]);
+          // the MMAs that read this slot two stages ago are done
+          mbar_wait(&S.a_empty[aset], ((it >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            ulonglong2 xx[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) xx[q4] = *reinterpret_cast<const ulonglong2*>(&in.u[c][a_half * 16 + q4 * 4]);
+            uint32_t r[16];  // [hi: pixel pairs 0..7 | lo: pixel pairs 0..7] of this thread's row
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              f32x2 w0, w1;
+              weight4<METHOD>(xx[q4].x, xx[q4].y, negc, wa2, wb2, w0, w1);
+              w0 = mul2(w0, iw[q4].x);
+              w1 = mul2(w1, iw[q4].y);
+              split_f16x2(w0, mone2, r[2 * q4], r[8 + 2 * q4]);
+              split_f16x2(w1, mone2, r[2 * q4 + 1], r[8 + 2 * q4 + 1]);
+            }
+            tmem_st16(tmem + lane_addr + A_COL0 + aset * A_SLOT_COLS + c * 16, r);
+          }
+          mbar_arrive_warp(&S.px_empty[slot]);
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive_warp(&S.a_full[aset]);
+        }
+
+        const bool chain_end = ((kb + 1) % CHAIN_KB == 0) || (kb + 1 == nkb);
+        if (!chain_end) continue;
+        // ---- chain epilogue: D (TMEM: two pixel-half tiles x [.B_hi | .B_lo] columns) += into the fp32 accumulator ----
+        mbar_wait(&S.d_full, chain & 1);
+        ++chain;
+        tc_fence_after_sync();
+        const bool first_chain = kb < CHAIN_KB;
+        float val[3][16];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t v1[16], v2[16];
+          tmem_ld16(tmem + lane_addr + c * D_COLS + cs * 16, v1);
+          tmem_ld16(tmem + lane_addr + c * D_COLS + 64 + cs * 16, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) val[c][i] = __uint_as_float(v1[i]) + __uint_as_float(v2[i]);
+        }
+        tc_fence_before_sync();
+        mbar_arrive_warp(&S.d_empty);  // the accumulators are in registers: the next chain may start
+        // lanes l and l + 16 hold the same u-bin for the two pixel halves
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) val[c][i] += __shfl_xor_sync(0xffffffffu, val[c][i], 16);
+        if (lane < 16) {
+          const int ebin = quad * 16 + lane;
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float* a = &S.acc[c][cs * 16 + i][ebin];
+              *a = first_chain ? val[c][i] : *a + val[c][i];
+            }
+        }
+        if (kb + 1 != nkb) continue;  // every (c, j, i) is owned by one thread: no barrier between chains
+        finish_item<FUSE_SSUM>(S, p, ir, tid, warp, lane);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issue: uniform loop, one elected lane issues =====================
+    constexpr uint32_t IDESC_FULL = idesc_f16(64, 128);  // . [B_hi | B_lo]
+    constexpr uint32_t IDESC_HI = idesc_f16(64, 64);     // . B_hi only (the first 64 rows of the tile)
+    const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(&S.bt[0][0]), T_KB_BYTES, 128);
+    const uint32_t dlo0 = (uint32_t)desc0, dhi = (uint32_t)(desc0 >> 32);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);  // provably uniform copy
+    uint32_t stage = 0, bphase = 0, aslot = 0, aphase = 0, chain_par = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const uint32_t nkb = (ir.px1 - ir.px0 + KB - 1) >> 5;
+      for (uint32_t kb0 = 0; kb0 < nkb; kb0 += CHAIN_KB) {
+        const uint32_t n_this = min((uint32_t)CHAIN_KB, nkb - kb0);
+        for (uint32_t k = 0; k < n_this; ++k) {
+          mbar_wait(&S.b_full[stage], bphase);
+          mbar_wait(&S.a_full[aslot], aphase);
+          tc_fence_after_sync();
+          const uint32_t dstage = dlo0 + stage * (B_STAGE_BYTES >> 4);
+          const uint32_t acol = tm + A_COL0 + aslot * A_SLOT_COLS;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // pixel half h: K step h of the B tile, TMEM lane offset 16 h for A and D
+              const uint32_t b_d = dstage + ((c * TILE_BYTES + h * 2 * T_KB_BYTES) >> 4);
+              const uint32_t lanes = (uint32_t)(16 * h) << 16;
+              const uint32_t acc0 = k == 0 ? 0u : 1u;
+              if (elect_one_sync()) {
+                mma_f16_ts2(tm + lanes + c * D_COLS, acol + lanes + c * 16, b_d, dhi, IDESC_FULL, acc0);
+                mma_f16_ts2(tm + lanes + c * D_COLS, acol + lanes + c * 16 + 8, b_d, dhi, IDESC_HI, 1u);
+              }
+            }
+          }
+          if (elect_one_sync()) { mma_commit(&S.b_empty[stage]); mma_commit(&S.a_empty[aslot]); }
+          if (++stage == NSB) { stage = 0; bphase ^= 1; }
+          aslot ^= 1;
+          if (aslot == 0) aphase ^= 1;
+        }
+        if (elect_one_sync()) mma_commit(&S.d_full);
         mbar_wait(&S.d_empty, chain_par);
         tc_fence_after_sync();
         chain_par ^= 1;
@@ -716,14 +1005,22 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   const bool fuse = ssum != nullptr && nb == 1;
   p.hist_true = fuse ? hist_true : nullptr;
   p.ssum = fuse ? ssum : nullptr;
-  const size_t smem = sizeof(Smem);
+  static const bool a_in_smem = getenv("PH_FWD_A") && getenv("PH_FWD_A")[0] == 's';  // tuning knob: PH_FWD_A=smem
+  const size_t smem = a_in_smem ? sizeof(Smem) : sizeof(SmemA);
   int grid = cached_sm_count();
   if (grid > p.items) grid = (int)p.items;
   void (*kern)(Params) = nullptr;
-  if (method == PH_METHOD_INVERSE_QUADRATIC)
-    kern = fuse ? hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
-  else
-    kern = fuse ? hist_fwd_tc_kernel<PH_METHOD_RBF, true> : hist_fwd_tc_kernel<PH_METHOD_RBF, false>;
+  if (a_in_smem) {
+    if (method == PH_METHOD_INVERSE_QUADRATIC)
+      kern = fuse ? hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
+    else
+      kern = fuse ? hist_fwd_tc_kernel<PH_METHOD_RBF, true> : hist_fwd_tc_kernel<PH_METHOD_RBF, false>;
+  } else {
+    if (method == PH_METHOD_INVERSE_QUADRATIC)
+      kern = fuse ? hist_fwd_tca_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_tca_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
+    else
+      kern = fuse ? hist_fwd_tca_kernel<PH_METHOD_RBF, true> : hist_fwd_tca_kernel<PH_METHOD_RBF, false>;
+  }
   PH_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // one launch per 64 x 64 block of the histogram (a single one at 64 bins)
   for (int blk = 0; blk < nb * nb; ++blk) {
