@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 
 METRIC = "histogram-loss fwd+bwd images/s at 64x64"
 # share of hist_bwd_tc_kernel + its prologue in the step's launch list under ncu (profiles/README.md, this round's capture)
-NCU_BWD_SHARE = 0.514
+NCU_BWD_SHARE = 0.532
 GLOBAL_BATCH = int(os.environ.get("PH_BENCH_BATCH", "4096"))  # cfgC (override only for tuning runs)
 HW = 64
 BINS = 64
@@ -324,9 +324,9 @@ def run_ours(args, rank, world, local_rank):
         "bound": "tensor", "kernel": "hist backward (prologue + contraction kernel)",
         "achieved": bwd_tflops, "peak": f16_peak, "unit": "TFLOP/s", "frac": bwd_tflops / f16_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of hist_bwd_tc_kernel, one `ncu --set full` capture at 4096
-        # images per launch (profiles/r1_prof_hist_f16_raw.csv: 470.0 MB + 241.1 MB), scaled to this rank's share
-        "traffic": 711.2e6 * local_b / 4096.0,
-        "traffic_source": "profiles/r1_prof_hist_f16_raw.csv (ncu, 4096 images/launch), scaled by local batch",
+        # images per launch (profiles/r2_prof_hist_raw.csv: 471.0 MB + 239.8 MB), scaled to this rank's share
+        "traffic": 710.8e6 * local_b / 4096.0,
+        "traffic_source": "profiles/r2_prof_hist_raw.csv (ncu, 4096 images/launch), scaled by local batch",
         "algorithmic_bytes": float(local_b) * npix * 4 * 4 * 2 + float(local_b) * 3 * BINS * BINS * 4,
         "peak_source": f"{peaks['source']}: {'bf16_tflops (burst: timed region %.2f s)' % (ms / 1e3) if burst else 'bf16_tflops_sustained'} "
                        "(kind::f16 runs at the bf16 dense rate)",
@@ -344,8 +344,9 @@ def run_ours(args, rank, world, local_rank):
         "phase_ms": {"fwd_real": phase_ms[0], "fwd_fake+hellinger_sum": phase_ms[1], "allreduce+loss": phase_ms[2],
                      "bwd": phase_ms[3]},
         "engine": impl,
-        "note": "both contraction kernels are bound by the CUDA-core generation of their operands (issue slots 65-73 % "
-                "busy, tensor pipe 27-35 % active under ncu, profiles/README.md), not by the tensor pipe or HBM",
+        "note": "both contraction kernels are bound by the CUDA-core generation of their operands (issue slots 65 % busy; "
+                "tensor pipe 44 % active in the forward — A operand in tensor memory — and 37 % in the backward under ncu, "
+                "profiles/README.md), not by the tensor pipe or HBM",
     }
 
     # ---- e2e: host buffers through the C ABI (pinned in, loss + gradient out) ----
@@ -385,10 +386,12 @@ def run_ours(args, rank, world, local_rank):
     img_bytes = local_b * npix * 4 * 4
     e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": (img_bytes + img_bytes // 4) * world,
            "d2h_bytes_per_step": (4 + 8) * world, "steps": e2e_steps,
-           "api": "hostapi.histogram_loss_begin/finish -> ph_host_hist_begin_u8real/finish: real (uint8 RGBA sprites, "
-                  "blackened + normalised on the device) + fake (float32) from pinned host memory every step, chunked so that "
-                  "upload, forward and (unit-scale) backward kernels overlap; loss (and the shard's sum of squares) read "
-                  "back, gradient (rescaled by 1/(B sqrt(S)) in finish) left on the device for the generator's backward",
+           "api": ("hostapi.histogram_loss_sharded -> ph_host_hist_loss_sharded (one call, one host synchronisation; the shards' "
+                   "sums of squares are added over NVLink peer memory on the device)" if comm is not None else
+                   "hostapi.histogram_loss_begin/finish -> ph_host_hist_begin_u8real/finish")
+                  + ": real (uint8 RGBA sprites, blackened + normalised on the device) + fake (float32) from pinned host "
+                    "memory every step, chunked so that upload, forward and (unit-scale) backward kernels overlap; loss read "
+                    "back, gradient (rescaled by 1/(B sqrt(S))) left on the device for the generator's backward",
            "loss": e2e_loss}
     ctx.close()
 
@@ -699,7 +702,7 @@ def bench_palette(torch, dev, peaks, args, _lib, io_utils, dataset_utils, hostap
                 "d2h_bytes_per_step": int(npx * 4 + PALETTE_BATCH * (256 * 16 + 4)),
                 "api": "hostapi.load_indexed_images(out=pinned buffers) -> ph_host_load_indexed_images (no one-hot download)",
                 "uint8_input": {"value": npx / e2e_u8_s / 1e9, "h2d_bytes_per_step": int(2 * src_np.size),
-                                "api": "ph_host_load_indexed_images_u8: decoded PNG bytes in, widened on the device"}},
+                                "api": "ph_host_load_indexed_images_u8: decoded PNG bytes in, read as uint8 by the kernel"}},
         "l2": "256 MiB flush write between timed iterations",
     }
 
