@@ -117,8 +117,6 @@ struct Params {
                      // weights dropped into fp16 subnormals
   float inv_scale;        // 1 / (weight scale^2 * iy_scale): raw sums of a de-duplicated image -> true scale
   float inv_scale_dense;  // 1 / weight scale^2: raw sums of a dense image -> true scale
-  int exp_skip_a;         // tuning experiment (PH_FWD_EXP=1): the A-side producers do not store their tiles (wrong results,
-                          // valid timing): measures what the A tiles' shared-memory stores cost
   int* status;            // mapped host word (ph_async_status): bit PH_ASYNC_RANGE when an A operand would overflow fp16
 };
 
@@ -366,14 +364,10 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tc_kernel(Params p) {
         }
         mbar_wait(&S.ab_empty[stage], ((it / NS) & 1) ^ 1);  // the MMAs that read this stage are done
         unsigned char* tile = &S.ab[stage][row_off];
-        if (side == 1 || !p.exp_skip_a) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            *reinterpret_cast<uint4*>(tile + c * 2 * TILE_BYTES) = hi[c];
-            *reinterpret_cast<uint4*>(tile + c * 2 * TILE_BYTES + 1024) = lo[c];
-          }
-        } else if (hi[0].x == 0x7fff7fffu && lo[1].y == 0x7fff7fffu && hi[2].z == 0x7fff7fffu) {
-          *reinterpret_cast<uint4*>(tile) = lo[2];  // never true: keeps the generation alive
+        for (int c = 0; c < 3; ++c) {
+          *reinterpret_cast<uint4*>(tile + c * 2 * TILE_BYTES) = hi[c];
+          *reinterpret_cast<uint4*>(tile + c * 2 * TILE_BYTES + 1024) = lo[c];
         }
         fence_proxy_async_smem();
         mbar_arrive_warp(&S.ab_full[stage]);
@@ -993,8 +987,6 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.inv_scale_dense = (float)(1.0 / (weight_scale * weight_scale));
   p.status = async_status_word();
   PH_CHECK_ARG(p.status != nullptr, "no mapped status word (cudaHostAlloc failed)");
-  static const int fwd_exp = getenv("PH_FWD_EXP") ? atoi(getenv("PH_FWD_EXP")) : 0;
-  p.exp_skip_a = fwd_exp == 1;
   const int64_t n_tail = batch - p.n_whole;
   if (n_tail > 0) {
     p.partial = reinterpret_cast<float*>(ws + off);
