@@ -762,12 +762,12 @@ __global__ void __launch_bounds__(256) hist_dedup_kernel(const float* __restrict
   using namespace fwdtc;
   __shared__ int owner[DEDUP_SLOTS];
   __shared__ int count[DEDUP_SLOTS];
-  __shared__ int s_n, s_out;
+  __shared__ int s_n;
   const int64_t b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   const float* img = image + b * npix * channels;
   for (int i = tid; i < DEDUP_SLOTS; i += 256) { owner[i] = -1; count[i] = 0; }
-  if (tid == 0) { s_n = 0; s_out = 0; }
+  if (tid == 0) s_n = 0;
   __syncthreads();
   const int64_t padded = (npix + 31) / 32 * 32;
   for (int64_t px = tid; px < padded; px += 256) {
@@ -818,13 +818,32 @@ __global__ void __launch_bounds__(256) hist_dedup_kernel(const float* __restrict
     if (tid == 0) nunique[b] = -1;
     return;
   }
-  float4* out = ulist + b * DEDUP_MAX;
+  // The list is written in the order of the colours' bit patterns (rank by lexicographic (r, g, b) comparison: the
+  // colours are distinct, so the ranks are a permutation), not in the order in which warps happened to claim slots:
+  // the order of the (colour, count) terms — and with it every bit of the contracted histogram — is then the same
+  // from run to run.  n <= 512 entries, a few dozen for a sprite.
+  __shared__ uint4 lst[DEDUP_MAX];
+  __shared__ int s_out;
+  if (tid == 0) s_out = 0;
+  __syncthreads();
   for (int i = tid; i < DEDUP_SLOTS; i += 256) {
     const int o = owner[i];
     if (o >= 0) {
       const float* op = img + (int64_t)o * channels;
-      out[atomicAdd(&s_out, 1)] = make_float4(__ldg(op), __ldg(op + 1), __ldg(op + 2), (float)count[i]);
+      lst[atomicAdd(&s_out, 1)] = make_uint4(__float_as_uint(__ldg(op)), __float_as_uint(__ldg(op + 1)),
+                                             __float_as_uint(__ldg(op + 2)), (unsigned)count[i]);
     }
+  }
+  __syncthreads();
+  float4* out = ulist + b * DEDUP_MAX;
+  for (int k = tid; k < n; k += 256) {
+    const uint4 me = lst[k];
+    int rank = 0;
+    for (int e = 0; e < n; ++e) {
+      const uint4 q = lst[e];
+      rank += (q.x < me.x || (q.x == me.x && (q.y < me.y || (q.y == me.y && q.z < me.z)))) ? 1 : 0;
+    }
+    out[rank] = make_float4(__uint_as_float(me.x), __uint_as_float(me.y), __uint_as_float(me.z), (float)me.w);
   }
   if (tid == 0) nunique[b] = n;
 }

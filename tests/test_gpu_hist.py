@@ -683,3 +683,35 @@ def test_cfgE_full_image_size(H, cuda):
         a, b = h_small[k].double(), h_big[k + 148].double()
         assert float((a - b).norm() / b.norm()) < 1e-6
     assert torch.equal(h_big[:4], h_big[148:152])  # deterministic: same image, same plan, same bits
+
+
+def test_deduplicated_forward_is_bit_reproducible(H, cuda, sprites):
+    """The unique-colour lists are ordered by the colours' bit patterns, not by which warp claimed a hash slot first
+    (two colours that collide in the table swap slots from run to run): the de-duplicated forward gives the same bits
+    every time, at 64 bins and on the 256-bin kernels, whole-image plan (batch >= SM count) and sliced plan alike."""
+    spr = normalize(np.concatenate([sprites["front"], sprites["right"]]).astype(np.float32))   # 216 palette images
+    x = torch.from_numpy(spr).to(cuda)
+    for size, imgs in ((64, x), (64, x[:40]), (256, x[:12])):
+        first = H.calculate_rgbuv_histogram(imgs, size=size, impl="tc", dedup=True)
+        for _ in range(4):
+            assert torch.equal(H.calculate_rgbuv_histogram(imgs, size=size, impl="tc", dedup=True), first), size
+
+
+@pytest.mark.parametrize("impl", impls())
+def test_cfgA_batch_32_sprites_against_oracle(H, cuda, sprites, impl):
+    """BASELINE config 1 at its own shape: batch 32 of 64 x 64 RGBA dataset sprites (real) against perturbed sprites
+    (fake, as a generator in training produces them: near the sprite, every pixel distinct), float64 oracle on the whole
+    batch — histograms, loss, gradient at 1e-5 (histogram.py:36-89, pix2pix_model.py:243-245, :78)."""
+    rng = np.random.default_rng(32)
+    real = normalize(sprites["right"][:32].astype(np.float32))
+    fake = np.clip(normalize(sprites["front"][:32].astype(np.float32)) + 0.05 * rng.standard_normal((32, 64, 64, 4)), -1, 1)
+    fake = fake.astype(np.float32)
+    ref = ho.hist_loss_and_grad_f64(real, fake)
+    f = torch.from_numpy(fake).to(cuda).requires_grad_(True)
+    loss = H.histogram_loss(torch.from_numpy(real).to(cuda), f, impl=impl)
+    loss.backward()
+    hf = H.calculate_rgbuv_histogram(torch.from_numpy(fake).to(cuda), impl=impl).cpu().numpy()
+    hr = H.calculate_rgbuv_histogram(torch.from_numpy(real).to(cuda), impl=impl, dedup=True).cpu().numpy()
+    assert ho.rel_l2(hf, ref["hist_fake"]) < HIST_TOL and ho.rel_l2(hr, ref["hist_real"]) < HIST_TOL
+    assert abs(float(loss.detach()) - ref["loss"]) / ref["loss"] < LOSS_TOL
+    assert ho.rel_l2(f.grad.cpu().numpy(), ref["grad"]) < GRAD_TOL
