@@ -195,3 +195,54 @@ def test_tf_adapter_is_import_safe_without_tensorflow(pkg):
     except ImportError:
         with pytest.raises(ImportError, match="TensorFlow"):
             mod.histogram_loss(None, None)
+
+
+def test_round2_entry_points_validate_before_touching_the_device(pkg):
+    """Argument validation of the ABI v2 additions happens on the host (no GPU needed): NULL pointers, bad enums,
+    misaligned buffers and unconnected communicators are PH_ERR_INVALID with a message, never a crash."""
+    lib = pkg._lib.load()
+    INVALID = pkg._lib.PH_ERR_INVALID
+    buf = ctypes.create_string_buffer(4096)
+    addr = ctypes.addressof(buf)
+    aligned = (addr + 255) // 256 * 256
+    # ph_pixel_map: NULL, unknown op, blacken on a non-RGBA element count
+    assert lib.ph_pixel_map(None, 16, 1, aligned, None) == INVALID
+    assert lib.ph_pixel_map(aligned, 16, 7, aligned, None) == INVALID and "bad op" in pkg._lib.last_error()
+    assert lib.ph_pixel_map(aligned, 6, 0, aligned, None) == INVALID and "multiple of 4" in pkg._lib.last_error()
+    # fused loader from uint8 pixels: NULL outputs, bad ordering, misaligned palette
+    assert lib.ph_load_indexed_images_u8(aligned, aligned, 1, 16, 2, None, None, aligned, aligned, aligned, None) == INVALID
+    assert lib.ph_load_indexed_images_u8(aligned, aligned, 1, 16, 9, None, aligned, aligned, aligned, aligned, None) == INVALID
+    assert lib.ph_load_indexed_images_u8(aligned, aligned, 1, 16, 2, None, aligned, aligned, aligned + 4, aligned, None) == INVALID
+    # 'shuffled' needs its keys (checked before any launch)
+    assert lib.ph_extract_palette(aligned, 0, 16, 3, None, aligned, aligned, None) == INVALID and "shuffle keys" in pkg._lib.last_error()
+    assert lib.ph_extract_palette(aligned, 0, 16, 2, None, aligned, aligned, None) == 0  # empty batch: nothing to do
+    # communicator: bad rank / world, NULL handles; the sharded host call refuses a NULL communicator
+    h = ctypes.c_void_p()
+    assert lib.ph_comm_create(0, 3, 2, ctypes.byref(h)) == INVALID
+    assert lib.ph_comm_create(0, 0, 99, ctypes.byref(h)) == INVALID
+    assert lib.ph_comm_allreduce_sum_f64(None, aligned, 1, None) == INVALID
+    assert lib.ph_comm_export(None, aligned) == INVALID and lib.ph_comm_connect(None, aligned) == INVALID
+    assert lib.ph_host_hist_finish_comm(None, None, 4, aligned, None, None) == INVALID
+    assert lib.ph_host_hist_loss_sharded(None, None, aligned, 0, aligned, 1, 16, 4, aligned, 64, 0, 4e-4, 1e-6, 0, 1, aligned, None,
+                                         None) == INVALID
+    # the sticky status word does not exist before a device was used: 0, and clearing is harmless
+    assert pkg._lib.async_status(0, clear=True) == 0
+
+
+def test_tf_adapter_is_import_safe_and_fences_both_hand_overs(pkg):
+    """TensorFlow is absent here: the adapter must import, raise a clear ImportError on use, and its hand-over helpers
+    must order the streams: a sync before borrowing a TensorFlow tensor, a stream synchronise before
+    handing a result back."""
+    import inspect
+
+    from palette_and_histo_gan_b200 import _tensor, tf_adapter
+
+    try:
+        import tensorflow  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="TensorFlow"):
+            tf_adapter.histogram_loss(None, None)
+    src = inspect.getsource(tf_adapter)
+    assert "sync_devices" in src and "_sync_tf(tf, t)" in inspect.getsource(tf_adapter._to_torch)
+    assert "synchronize()" in inspect.getsource(tf_adapter._to_tf)
+    assert "_sync_tf" in inspect.getsource(_tensor.from_any) and "synchronize()" in inspect.getsource(_tensor.to_caller_framework)
