@@ -1,6 +1,7 @@
 // extern "C" surface of libpalhist.so — argument validation and engine dispatch only.
 // See include/palhist.h for the contract and the reference file:line each entry point replaces.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -21,6 +22,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = !(getenv("PH_PDL") && atoi(getenv("PH_PDL")) == 0);
+  return on;
+}
 
 int cached_sm_count() {
   static int counts[64];

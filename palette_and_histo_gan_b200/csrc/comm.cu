@@ -49,6 +49,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __global__ void __launch_bounds__(32) comm_allreduce_f64_kernel(CommParams P, double* value, int count) {
   const int lane = threadIdx.x;
   const int parity = (int)(P.epoch & 1ull);
+  pdl_wait();  // the value was produced by the kernel before this one in the stream
+  pdl_launch_dependents();
   double a0 = 0.0, a1 = 0.0;
   if (lane < P.world) {
     // publish: this rank's value into slot [parity][rank] of rank `lane`
@@ -158,7 +160,7 @@ int ph_comm_allreduce_sum_f64(ph_comm* comm, double* value, int count, void* str
   P.epoch = ++comm->epoch;
   P.rank = comm->rank;
   P.world = comm->world;
-  comm_allreduce_f64_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(P, value, count);
+  PH_CUDA_OK(launch_pdl(comm_allreduce_f64_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), P, value, count));
   PH_LAUNCH_OK("comm_allreduce_f64_kernel");
   return PH_OK;
 }

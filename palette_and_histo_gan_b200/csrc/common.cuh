@@ -41,6 +41,30 @@ void count_launch(int n = 1);
     ph::count_launch();                                                             \
   } while (0)
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl may become resident while the kernel before
+// it in the stream is still draining (its CTAs start as SMs free up); everything that reads what earlier kernels wrote
+// must come after pdl_wait(), which returns once ALL earlier work of the stream has completed and is visible.  The
+// kernels of the loss step keep only their set-up (shared-memory barriers, tensor-memory allocation) in front of it,
+// and release their own dependents right behind it, so launch latency and set-up overlap the previous kernel's tail.
+// Launched without the attribute both instructions are no-ops.  PH_PDL=0 launches everything the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // abi.cu
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 

@@ -524,6 +524,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tca_kernel(Params p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = S.tmem_base;
+  pdl_wait();               // set-up done; from here on the results of the stream's earlier kernels are read
+  pdl_launch_dependents();  // the next kernel of the stream may move in as this one's CTAs retire
 
   const int64_t first = blockIdx.x, step = gridDim.x;
 
@@ -769,6 +771,8 @@ __global__ void __launch_bounds__(256) hist_dedup_kernel(const float* __restrict
   for (int i = tid; i < DEDUP_SLOTS; i += 256) { owner[i] = -1; count[i] = 0; }
   if (tid == 0) s_n = 0;
   __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t padded = (npix + 31) / 32 * 32;
   for (int64_t px = tid; px < padded; px += 256) {
     const bool active = px < npix;
@@ -996,7 +1000,7 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     // unique colours + multiplicities per image (only worth it when a CTA owns whole images)
     float4* ulist = reinterpret_cast<float4*>(ws);
     int* nunique = reinterpret_cast<int*>(ws + align_up((size_t)batch * DEDUP_MAX * sizeof(float4), 256));
-    hist_dedup_kernel<<<(unsigned)batch, 256, 0, st>>>(image, npix, channels, ulist, nunique);
+    PH_CUDA_OK(launch_pdl(hist_dedup_kernel, dim3((unsigned)batch), dim3(256), 0, st, image, npix, channels, ulist, nunique));
     PH_LAUNCH_OK("hist_dedup_kernel");
     p.ulist = ulist;
     p.nunique = nunique;
@@ -1039,7 +1043,11 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     p.dom_v = dom + (blk % nb) * BINS;
     p.raw_out = raw ? raw + (int64_t)blk * batch * (3 * BINS * BINS) : nullptr;
     if (n_tail > 0) PH_CUDA_OK(cudaMemsetAsync(p.tail_counter, 0, (size_t)n_tail * sizeof(int), st));
-    kern<<<grid, THREADS, smem, st>>>(p);
+    if (a_in_smem) {
+      kern<<<grid, THREADS, smem, st>>>(p);
+    } else {
+      PH_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(THREADS), smem, st, p));
+    }
     PH_LAUNCH_OK("hist_fwd_tc_kernel");
   }
   if (nb > 1) {
