@@ -185,7 +185,26 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   ph_host_ctx::Job& J = ctx->job;
   int nchunks = 0;
   int64_t chunk = 0;
-  {
+  // tuning knob: explicit chunk sizes, e.g. PH_HOST_CHUNK_LIST=148,296,592,1184 (the last size repeats)
+  static const char* list_env = getenv("PH_HOST_CHUNK_LIST");
+  if (list_env != nullptr && list_env[0] != 0) {
+    int64_t pos = 0, sz = base;
+    const char* q = list_env;
+    J.start[0] = 0;
+    while (pos < batch && nchunks < ph_host_ctx::kMaxChunks) {
+      if (*q) {
+        char* end = nullptr;
+        const long long v = strtoll(q, &end, 10);
+        if (v > 0) sz = v;
+        q = (*end == ',') ? end + 1 : end;
+      }
+      int64_t take = sz < batch - pos ? sz : batch - pos;
+      if (nchunks == ph_host_ctx::kMaxChunks - 1) take = batch - pos;
+      pos += take;
+      J.start[++nchunks] = pos;
+      if (take > chunk) chunk = take;
+    }
+  } else {
     int64_t pos = 0;
     J.start[0] = 0;
     while (pos < batch) {
