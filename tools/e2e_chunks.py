@@ -2,8 +2,11 @@
 process, so each schedule runs in a subprocess)."""
 import sys, os, subprocess, time
 sys.path.insert(0, os.getcwd())
-SCHEDULES = ["", "296", "148,296,592,1184", "148,296,592,1184,1184,544,148", "222,444,888,888,888,544,222",
-             "296,592,592,592,592,592,592,248", "148,444,1184,1184,888,248", "148,296,444,592,740,888,592,296,100"]
+SCHEDULES = ["", "148,296", "74,148,296", "148,222,296", "148,296,592,1184", "148,296,592,1184,1184,544,148",
+             "222,444,888,888,888,544,222", "296,592,592,592,592,592,592,248"]
+if len(sys.argv) > 1 and sys.argv[1] != "run":
+    SCHEDULES = sys.argv[1:]
+    sys.argv = sys.argv[:1]
 if len(sys.argv) == 1:
     for sch in SCHEDULES:
         env = dict(os.environ)
