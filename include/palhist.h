@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PH_ABI_VERSION 2
+#define PH_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define PH_API __attribute__((visibility("default")))
@@ -72,6 +72,14 @@ enum ph_impl {
    * colour).  Pays off for palette images such as the reference's real sprites (10-54 colours); an
    * image with more than 512 colours is contracted densely.  Ignored by the CUDA-core engine. */
   PH_IMPL_DEDUP = 8,
+  /* flag, OR-ed into impl for ph_hist_forward / ph_hist_forward_ssum: the caller asserts that the bin centres are
+   * antisymmetric, |c[j] + c[bins-1-j]| <= 2e-5 sigma for every j (tf.linspace(-3, 3, 64), histogram.py:55, is: 3.6e-7).
+   * Dense 64-bin batches on the tensor-core engine then run the mirrored-tile forward: the weight vectors of +x and -x
+   * are bin-reversed copies of each other around the midpoint centres (c[j] - c[63-j]) / 2, three vectors per pixel
+   * instead of six (adds <= 2e-6 to the histogram error at 64 x 64 pixels).  Ignored for every other
+   * configuration (other bin counts, PH_IMPL_DEDUP, the CUDA-core engine, the backward).  A launch whose centres break
+   * the assertion sets PH_ASYNC_MIRROR. */
+  PH_IMPL_MIRROR = 16,
 };
 
 /* per-image status written by ph_extract_palette into ncolors[]: >=0 colour count (may exceed 256 =
@@ -93,6 +101,9 @@ PH_API void ph_reset_launch_count(void);
  * synchronises; it is as current as the last completed kernel.  clear != 0 resets it.  Every ph_hist_* call also
  * checks it on entry and fails with PH_ERR_UNSUPPORTED (clearing it), like CUDA's own asynchronous errors. */
 #define PH_ASYNC_RANGE 1
+/* bit 1 = a forward launched with PH_IMPL_MIRROR found bin centres that are not antisymmetric (its results are off by
+ * the asymmetry / sigma; re-run without the flag). */
+#define PH_ASYNC_MIRROR 2
 PH_API int ph_async_status(int device, int clear);
 /* sm_count / compute capability of `device`; PH_ERR_CUDA without a usable GPU. */
 PH_API int ph_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);

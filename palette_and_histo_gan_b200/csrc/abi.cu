@@ -74,7 +74,13 @@ static int consume_async_status() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PH_OK;
   volatile int* h = g_status_host[dev];
   if (h == nullptr || *h == 0) return PH_OK;
+  const int bits = *h;
   *h = 0;
+  if (bits & PH_ASYNC_MIRROR) {
+    set_error("an earlier histogram forward was launched with PH_IMPL_MIRROR on bin centres that are not antisymmetric; its "
+              "results are off by the asymmetry — re-run that call without the flag");
+    return PH_ERR_UNSUPPORTED;
+  }
   set_error("an earlier histogram launch on the tensor-core engine met pixels outside its operand range (image far "
             "outside [-1, 1]); its results are inf / NaN — re-run that call with the CUDA-core engine (impl = simt)");
   return PH_ERR_UNSUPPORTED;
@@ -158,7 +164,7 @@ static int hist_forward_impl(const float* image, int64_t batch, int64_t npix, in
   if (rc != PH_OK) return rc;
   if ((rc = consume_async_status()) != PH_OK) return rc;
   PH_CHECK_ARG(hist != nullptr && denom != nullptr, "hist / denom must not be NULL");
-  PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
+  PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP | PH_IMPL_MIRROR)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
                "bad impl %d", impl);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (ssum != nullptr && !accumulate) PH_CUDA_OK(cudaMemsetAsync(ssum, 0, sizeof(double), st));
@@ -172,7 +178,7 @@ static int hist_forward_impl(const float* image, int64_t batch, int64_t npix, in
       return PH_ERR_UNSUPPORTED;
     }
     return tc_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist,
-                           denom, workspace, (impl & PH_IMPL_DEDUP) != 0, hist_true, ssum, st);
+                           denom, workspace, (impl & PH_IMPL_DEDUP) != 0, (impl & PH_IMPL_MIRROR) != 0, hist_true, ssum, st);
   }
   rc = simt_hist_forward(image, batch, npix, channels, bin_centers, bins, method, sigma_sqr, epsilon, hist, denom,
                          workspace, st);
@@ -227,7 +233,7 @@ int ph_hist_backward(const float* image, int64_t batch, int64_t npix, int channe
   PH_CHECK_ARG(hist_pred && denom_pred && grad_image, "hist_pred / denom_pred / grad_image must not be NULL");
   PH_CHECK_ARG(grad_hist != nullptr || (hist_true != nullptr && ssum != nullptr && global_batch > 0),
                "either grad_hist or (hist_true, ssum, global_batch>0) must be given");
-  PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
+  PH_CHECK_ARG((impl & ~(PH_IMPL_ENGINE_MASK | PH_IMPL_DEDUP | PH_IMPL_MIRROR)) == 0 && (impl & PH_IMPL_ENGINE_MASK) <= PH_IMPL_TC,
                "bad impl %d", impl);
   PH_CHECK_ARG(channels != 4 || (reinterpret_cast<uintptr_t>(grad_image) & 15) == 0,
                "RGBA gradient pointer must be 16-byte aligned");

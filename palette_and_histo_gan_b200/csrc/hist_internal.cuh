@@ -42,7 +42,7 @@ size_t tc_workspace_bytes(int64_t batch, int64_t npix, int bins);
 size_t tc_bwd_workspace_bytes(int64_t batch, int bins);  // hist_tc_bwd.cu: G^ operand tiles, scales (+ float G^ when bins > 64)
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom,
                     int bins, int method, float sigma_sqr, float eps, float* hist, float* denom,
-                    void* workspace, bool dedup, const float* hist_true, double* ssum, cudaStream_t st);
+                    void* workspace, bool dedup, bool mirror, const float* hist_true, double* ssum, cudaStream_t st);
 // hist_tc_fwd256.cu: dedicated 256-bin forward (whole 256 x 256 histogram of a channel in one CTA's tensor memory)
 size_t tc_fwd256_workspace_bytes(int64_t batch, int64_t npix);
 void tc_fwd256_plan(int64_t batch, int64_t npix, int* slices_per_image, int64_t* px_per_slice);  // host-only work plan

@@ -118,6 +118,7 @@ struct Params {
   float inv_scale;        // 1 / (weight scale^2 * iy_scale): raw sums of a de-duplicated image -> true scale
   float inv_scale_dense;  // 1 / weight scale^2: raw sums of a dense image -> true scale
   int* status;            // mapped host word (ph_async_status): bit PH_ASYNC_RANGE when an A operand would overflow fp16
+  float mirror_tol;       // mirrored-tile kernel: largest |c_j + c_{63-j}| the caller's PH_IMPL_MIRROR may stand for
 };
 
 // Pixel range of a work item.  A de-duplicated image is a list of (colour, multiplicity) entries: the
@@ -745,6 +746,294 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tca_kernel(Params p) {
   if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+
+// =============================================================================================
+// Mirrored-tile forward for DENSE images (default for 64 bins when the bin centres are antisymmetric to within the
+// rounding of `linspace`; PH_FWD_SYM=0 or impl without PH_IMPL_MIRROR selects the kernel above).
+//
+// The six coordinates of a pixel are +-a, +-b, +-c with a = log R/G, b = log R/B, c = log G/B (histogram.py:72-74):
+//     R: (u, v) = (a, b)      G: (-a, c)      B: (-b, -c)
+// and K(-x - c_i) = K(x + c_i) = K(x - c_{63-i}) when c_{63-i} = -c_i: the weight vector of -x is the bin-reversed
+// vector of x.  TensorFlow's `linspace(-3, 3, 64)` is antisymmetric only to 3.6e-7 (start + i * delta in float32), so
+// the vectors are generated once around the MIDPOINT centres t_j = (c_j - c_{63-j}) / 2 and used for both signs: every
+// use is off by at most half the asymmetry, 1.8e-7 — the size of the float32 rounding of the coordinate itself.
+// Measured cost (CPU model oracle/…, tests): histogram 1.8-2.1e-6 from the float64 oracle at 64 x 64 pixels (kernel
+// above: 0.8-1.2e-6), 4.9e-6 for an 8 x 8 image (2.8e-6); gradients move by 0.4-1.9e-6 through G^.  The backward keeps the
+// exact centres (dK/du is ten times as sensitive).
+// With alpha = sqrt(Iy) k(a), beta = sqrt(Iy) k(b), gamma = sqrt(Iy) k(c)  (64 bins each, centres t):
+//     H_R[i, j] = (alpha beta^T)[i, j]     H_G[i, j] = (alpha gamma^T)[63-i, j]     H_B[i, j] = (beta gamma^T)[63-i, 63-j]
+// i.e. THREE weight vectors per pixel instead of six (192 weights instead of 384), and one accumulator
+//     D (128 x 256) = [alpha; beta] . [gamma_hi | beta_hi | gamma_lo | beta_lo]^T
+// A = [alpha; beta] lives in tensor memory (M = 128: lane = row, hi and lo stacked along K as in the kernel above),
+// B in shared memory (256 rows).  Per 16-pixel K step: A_hi . B (M128 N256 K16, 128 cycles, the pipe's full rate) and
+// A_lo . [gamma_hi | beta_hi] (M128 N128 K16, 64 cycles) — the three products of the emulation; the beta.beta
+// quadrant is not used.  192 tensor-pipe cycles per 16 pixels instead of 324, 6 144 generated weights per 32 pixels
+// instead of 12 288.
+// 64-pixel stages; every one of the 16 producer warps does the same work per stage: one TMEM task (32 rows of
+// alpha or beta x 16 pixels: one tcgen05.st.x16 per thread; the beta warps also store their rows to the B tile) and
+// one gamma task (32 bins x 8 pixels -> B tile).
+// =============================================================================================
+constexpr int SKB = 64;                  // pixels per stage
+constexpr int SNS = 3;                   // stages in flight: B tiles in shared memory, A slots in tensor memory
+constexpr int S_CHAIN = 16;              // stages per accumulation chain (1024 pixels, as above)
+constexpr int SPR = 4;                   // pixel ring slots
+constexpr int S_A_COL0 = 256;            // D = columns 0-255, A slots behind it
+constexpr int S_A_SLOT_COLS = 64;        // four K steps x [hi 8 | lo 8] columns
+constexpr int SB_KB_BYTES = 32 * 128;    // 4096: one core-matrix column (8 pixels) of all 256 rows
+constexpr int SB_STAGE_BYTES = (SKB / 8) * SB_KB_BYTES;  // 32768
+constexpr int ROW_G_HI = 0, ROW_B_HI = 64, ROW_G_LO = 128, ROW_B_LO = 192;  // B tile rows / D columns
+static_assert(S_A_COL0 + SNS * S_A_SLOT_COLS <= TMEM_COLS, "TMEM budget");
+
+struct PxSlotS {
+  float a[SKB], b[SKB], c[SKB], siy[SKB];  // scaled log-chroma differences rg, rb, gb; sqrt(intensity)
+};
+
+struct SmemS {
+  alignas(128) unsigned char bt[SNS][SB_STAGE_BYTES];  // 96 KB
+  float acc[3][BINS][BINS + 1];
+  PxSlotS px[SPR];
+  float ctr[BINS];  // scaled midpoint centres
+  float red[PROD_WARPS];
+  double red2[PROD_WARPS];
+  int last_flag;
+  alignas(8) uint64_t px_full[SPR], px_empty[SPR], ab_full[SNS], ab_empty[SNS], d_full, d_empty;
+  uint32_t tmem_base;
+};
+
+template <int METHOD, bool FUSE_SSUM>
+__global__ void __launch_bounds__(THREADS, 1) hist_fwd_sym_kernel(Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemS& S = *reinterpret_cast<SmemS*>(smem_raw);
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < SPR; ++i) { mbar_init(&S.px_full[i], 1); mbar_init(&S.px_empty[i], PROD_WARPS); }
+    for (int i = 0; i < SNS; ++i) { mbar_init(&S.ab_full[i], PROD_WARPS); mbar_init(&S.ab_empty[i], 1); }
+    mbar_init(&S.d_full, 1);
+    mbar_init(&S.d_empty, PROD_WARPS);
+    fence_mbar_init();
+  }
+  if (tid < BINS) {
+    const float cj = p.dom_u[tid], cm = p.dom_u[BINS - 1 - tid];
+    S.ctr[tid] = 0.5f * (cj - cm) * p.coord_scale;
+    // the caller asserted antisymmetric centres (PH_IMPL_MIRROR): never silently wrong if they are not
+    if (!(fabsf(cj + cm) <= p.mirror_tol)) *reinterpret_cast<volatile int*>(p.status) = PH_ASYNC_MIRROR;
+  }
+  if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int64_t first = blockIdx.x, step = gridDim.x;
+
+  if (warp >= PX_WARP0) {
+    // ===================== pixel pass: one warp per 64-pixel stage, two pixels per lane =====================
+    const int me = warp - PX_WARP0;
+    uint32_t it = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const int64_t b = ir.b;
+      const uint32_t px0 = ir.px0, px1 = ir.px1;
+      for (uint32_t base = px0; base < px1; base += SKB, ++it) {
+        if ((int)(it % PXW) != me) continue;
+        const int slot = it % SPR;
+        float va[2], vb[2], vc[2], vs[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint32_t px = base + k * 32 + lane;
+          const bool valid = px < px1;
+          float r = 0.f, g = 0.f, bl = 0.f;
+          if (valid) {
+            const float* src = p.image + (b * p.npix + px) * p.channels;
+            if (p.channels == 4) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+              r = q.x; g = q.y; bl = q.z;
+            } else {
+              r = __ldg(src); g = __ldg(src + 1); bl = __ldg(src + 2);
+            }
+          }
+          // histogram.py:58-66, :13-17 — log of the ratio: one rounding instead of two at magnitude 13.8
+          const float x0 = fmaf(r, 0.5f, 0.5f), x1 = fmaf(g, 0.5f, 0.5f), x2 = fmaf(bl, 0.5f, 0.5f);
+          const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
+          const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
+          va[k] = logf(e0 / e1) * p.coord_scale;
+          vb[k] = logf(e0 / e2) * p.coord_scale;
+          vc[k] = logf(e1 / e2) * p.coord_scale;
+          // every product of two operands carries the intensity once; masked pixels contribute nothing
+          vs[k] = valid ? sqrtf(iy) : 0.f;
+          // operand = sqrt(Iy) x (scaled weight <= 2^14) must stay below fp16's 65504 — flagged, never silent
+          if (vs[k] > tcgen::IY_OPERAND_LIMIT) *reinterpret_cast<volatile int*>(p.status) = PH_ASYNC_RANGE;
+        }
+        mbar_wait_relaxed(&S.px_empty[slot], ((it / SPR) & 1) ^ 1, 400);
+        PxSlotS& o = S.px[slot];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          o.a[k * 32 + lane] = va[k]; o.b[k * 32 + lane] = vb[k]; o.c[k * 32 + lane] = vc[k];
+          o.siy[k * 32 + lane] = vs[k];
+        }
+        mbar_arrive_warp(&S.px_full[slot]);
+      }
+    }
+  } else if (warp < PROD_WARPS) {
+    // ===================== operand producers + epilogue (16 warps, identical work) =====================
+    const f32x2 wa2 = pack2(p.wa, p.wa), wb2 = pack2(p.wb, p.wb), mone2 = pack2(-1.0f, -1.0f);
+    const int quad = warp & 3;   // TMEM lanes 32 quad ..: rows of alpha (quad 0, 1) or beta (quad 2, 3)
+    const int r16 = warp >> 2;   // TMEM task: pixels 16 r16 .. + 15 of the stage = K step r16
+    const int g8 = warp >> 1;    // gamma task: pixels 8 g8 .. + 7 = core-matrix column g8
+    const int bin = (warp & 1) * 32 + lane;  // the same bin in both tasks
+    const float c_bin = S.ctr[bin];
+    const f32x2 negc = pack2(-c_bin, -c_bin);
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t row16 = (uint32_t)((bin >> 3) * 128 + (bin & 7) * 16);  // byte offset of row `bin` in a core-matrix column
+    uint32_t it = 0, chain = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const uint32_t nkb = (ir.px1 - ir.px0 + SKB - 1) / SKB;
+      for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
+        const int slot = it % SPR, stage = it % SNS;
+        mbar_wait(&S.px_full[slot], (it / SPR) & 1);
+        const PxSlotS& in = S.px[slot];
+        ulonglong2 xx[4], iw[4], xc[2], ic[2];
+        {
+          const float* src = (quad < 2 ? in.a : in.b) + r16 * 16;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            xx[q4] = *reinterpret_cast<const ulonglong2*>(src + q4 * 4);
+            iw[q4] = *reinterpret_cast<const ulonglong2*>(&in.siy[r16 * 16 + q4 * 4]);
+          }
+#pragma unroll
+          for (int q2 = 0; q2 < 2; ++q2) {
+            xc[q2] = *reinterpret_cast<const ulonglong2*>(&in.c[g8 * 8 + q2 * 4]);
+            ic[q2] = *reinterpret_cast<const ulonglong2*>(&in.siy[g8 * 8 + q2 * 4]);
+          }
+        }
+        mbar_arrive_warp(&S.px_empty[slot]);
+        uint32_t rr[16];  // this thread's row: [hi: pixel pairs 0..7 | lo: pixel pairs 0..7]
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          f32x2 w0, w1;
+          weight4<METHOD>(xx[q4].x, xx[q4].y, negc, wa2, wb2, w0, w1);
+          w0 = mul2(w0, iw[q4].x);
+          w1 = mul2(w1, iw[q4].y);
+          split_f16x2(w0, mone2, rr[2 * q4], rr[8 + 2 * q4]);
+          split_f16x2(w1, mone2, rr[2 * q4 + 1], rr[8 + 2 * q4 + 1]);
+        }
+        uint4 ghi, glo;
+        {
+          f32x2 w0, w1, w2, w3;
+          weight4<METHOD>(xc[0].x, xc[0].y, negc, wa2, wb2, w0, w1);
+          weight4<METHOD>(xc[1].x, xc[1].y, negc, wa2, wb2, w2, w3);
+          w0 = mul2(w0, ic[0].x); w1 = mul2(w1, ic[0].y); w2 = mul2(w2, ic[1].x); w3 = mul2(w3, ic[1].y);
+          split_f16x2(w0, mone2, ghi.x, glo.x);
+          split_f16x2(w1, mone2, ghi.y, glo.y);
+          split_f16x2(w2, mone2, ghi.z, glo.z);
+          split_f16x2(w3, mone2, ghi.w, glo.w);
+        }
+        // the MMAs that read this stage's A slot and B tile (SNS stages ago) are done
+        mbar_wait(&S.ab_empty[stage], ((it / SNS) & 1) ^ 1);
+        tc_fence_after_sync();
+        tmem_st16(tmem + lane_addr + S_A_COL0 + stage * S_A_SLOT_COLS + r16 * 16, rr);
+        unsigned char* tile = &S.bt[stage][0];
+        if (quad >= 2) {  // beta is also the B operand of alpha . beta^T: rows 64 + bin (hi), 192 + bin (lo)
+          unsigned char* col = tile + (2 * r16) * SB_KB_BYTES + row16;
+          *reinterpret_cast<uint4*>(col + ROW_B_HI * 16) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+          *reinterpret_cast<uint4*>(col + ROW_B_HI * 16 + SB_KB_BYTES) = make_uint4(rr[4], rr[5], rr[6], rr[7]);
+          *reinterpret_cast<uint4*>(col + ROW_B_LO * 16) = make_uint4(rr[8], rr[9], rr[10], rr[11]);
+          *reinterpret_cast<uint4*>(col + ROW_B_LO * 16 + SB_KB_BYTES) = make_uint4(rr[12], rr[13], rr[14], rr[15]);
+        }
+        *reinterpret_cast<uint4*>(tile + g8 * SB_KB_BYTES + row16 + ROW_G_HI * 16) = ghi;
+        *reinterpret_cast<uint4*>(tile + g8 * SB_KB_BYTES + row16 + ROW_G_LO * 16) = glo;
+        fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&S.ab_full[stage]);
+
+        const bool chain_end = ((kb + 1) % S_CHAIN == 0) || (kb + 1 == nkb);
+        if (!chain_end) continue;
+        // ---- chain epilogue: D (128 rows x [. gamma_hi | . beta_hi | . gamma_lo | . beta_lo]) += into the fp32 accumulator.
+        //      Warp (quad, r16): rows 32 quad .., columns 32 r16 .. + 31 of the hi half and of the lo half. ----
+        mbar_wait(&S.d_full, chain & 1);
+        ++chain;
+        tc_fence_after_sync();
+        const bool first_chain = kb < S_CHAIN;
+        const bool used = quad < 2 || r16 < 2;  // the beta . beta^T quadrant is not a histogram
+        float val[32];
+        if (used) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v1[16], v2[16];
+            tmem_ld16(tmem + lane_addr + r16 * 32 + h * 16, v1);
+            tmem_ld16(tmem + lane_addr + ROW_G_LO + r16 * 32 + h * 16, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) val[h * 16 + i] = __uint_as_float(v1[i]) + __uint_as_float(v2[i]);
+          }
+        }
+        tc_fence_before_sync();
+        mbar_arrive_warp(&S.d_empty);  // the accumulators are in registers: the next chain may start
+        if (used) {
+          // row of D = bin i' of alpha (quad < 2) or beta; column = bin j of gamma (r16 < 2) or beta
+          float* dst;
+          int jstride;
+          if (quad >= 2)      { dst = &S.acc[2][BINS - 1 - r16 * 32][BINS - 1 - bin]; jstride = -(BINS + 1); }  // H_B[63-i'][63-j]
+          else if (r16 < 2)   { dst = &S.acc[1][r16 * 32][BINS - 1 - bin];            jstride = BINS + 1; }     // H_G[63-i'][j]
+          else                { dst = &S.acc[0][(r16 - 2) * 32][bin];                 jstride = BINS + 1; }     // H_R[i'][j]
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float* a = dst + i * jstride;
+            *a = first_chain ? val[i] : *a + val[i];
+          }
+        }
+        if (kb + 1 != nkb) continue;  // every (c, j, i) is owned by one thread: no barrier between chains
+        finish_item<FUSE_SSUM>(S, p, ir, tid, warp, lane);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issue: uniform loop, one elected lane issues =====================
+    constexpr uint32_t IDESC_FULL = idesc_f16(128, 256);  // . [gamma_hi | beta_hi | gamma_lo | beta_lo]
+    constexpr uint32_t IDESC_HI = idesc_f16(128, 128);    // . [gamma_hi | beta_hi] (the first 128 rows of the tile)
+    const uint64_t desc0 = smem_desc_kmajor_noswizzle(smem_u32(&S.bt[0][0]), SB_KB_BYTES, 128);
+    const uint32_t dlo0 = (uint32_t)desc0, dhi = (uint32_t)(desc0 >> 32);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);  // provably uniform copy
+    uint32_t stage = 0, phase = 0, chain_par = 0;
+    for (int64_t w = first; w < p.items; w += step) {
+      const ItemRange ir = item_range(p, w);
+      const uint32_t nkb = (ir.px1 - ir.px0 + SKB - 1) / SKB;
+      for (uint32_t kb0 = 0; kb0 < nkb; kb0 += S_CHAIN) {
+        const uint32_t n_this = min((uint32_t)S_CHAIN, nkb - kb0);
+        for (uint32_t k = 0; k < n_this; ++k) {
+          mbar_wait(&S.ab_full[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t dstage = dlo0 + stage * (SB_STAGE_BYTES >> 4);
+          const uint32_t acol = tm + S_A_COL0 + stage * S_A_SLOT_COLS;
+#pragma unroll
+          for (int ks = 0; ks < SKB / 16; ++ks) {
+            const uint32_t b_d = dstage + ((ks * 2 * SB_KB_BYTES) >> 4);
+            const uint32_t acc0 = (k == 0 && ks == 0) ? 0u : 1u;
+            if (elect_one_sync()) {
+              mma_f16_ts2(tm, acol + ks * 16, b_d, dhi, IDESC_FULL, acc0);
+              mma_f16_ts2(tm, acol + ks * 16 + 8, b_d, dhi, IDESC_HI, 1u);
+            }
+          }
+          if (elect_one_sync()) mma_commit(&S.ab_empty[stage]);
+          if (++stage == SNS) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one_sync()) mma_commit(&S.d_full);
+        mbar_wait(&S.d_empty, chain_par);
+        tc_fence_after_sync();
+        chain_par ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+}
+
 }  // namespace fwdtc
 
 
@@ -940,7 +1229,7 @@ __global__ void __launch_bounds__(256) hist_block_finalize_kernel(const float* _
 
 int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channels, const float* dom, int bins,
                     int method, float sigma_sqr, float eps, float* hist, float* denom, void* workspace, bool dedup,
-                    const float* hist_true, double* ssum, cudaStream_t st) {
+                    bool mirror, const float* hist_true, double* ssum, cudaStream_t st) {
   using namespace fwdtc;
   PH_CHECK_ARG(bins >= BINS && bins % BINS == 0, "tensor-core forward needs a multiple of 64 bins");
   const int nb = bins / BINS;
@@ -979,9 +1268,12 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.npix = npix;
   p.channels = channels;
   const FwdPlan pl = tc_fwd_plan(batch, npix, dedup);
+  // mirrored-tile kernel: dense 64-bin batches whose centres the caller declared antisymmetric (PH_IMPL_MIRROR)
+  static const bool sym_off = getenv("PH_FWD_SYM") && atoi(getenv("PH_FWD_SYM")) == 0;  // tuning knob
+  const bool sym = mirror && !dedup && nb == 1 && !sym_off;
   p.n_whole = pl.n_whole;
   p.splits = pl.splits;
-  p.px_per_split = ceil_div(ceil_div(npix, p.splits), KB) * KB;
+  p.px_per_split = ceil_div(ceil_div(npix, p.splits), sym ? SKB : KB) * (sym ? SKB : KB);
   p.items = p.n_whole + (batch - p.n_whole) * p.splits;
   p.eps = eps;
   const tcgen::WeightScales wsc = tcgen::weight_scales(method, sigma_sqr);
@@ -1010,6 +1302,7 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.inv_scale_dense = (float)(1.0 / (weight_scale * weight_scale));
   p.status = async_status_word();
   PH_CHECK_ARG(p.status != nullptr, "no mapped status word (cudaHostAlloc failed)");
+  p.mirror_tol = 2.5e-5f * sqrtf(sigma_sqr);  // the flag's contract is 2e-5 sigma (palhist.h)
   const int64_t n_tail = batch - p.n_whole;
   if (n_tail > 0) {
     p.partial = reinterpret_cast<float*>(ws + off);
@@ -1021,11 +1314,16 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   p.hist_true = fuse ? hist_true : nullptr;
   p.ssum = fuse ? ssum : nullptr;
   static const bool a_in_smem = getenv("PH_FWD_A") && getenv("PH_FWD_A")[0] == 's';  // tuning knob: PH_FWD_A=smem
-  const size_t smem = a_in_smem ? sizeof(Smem) : sizeof(SmemA);
+  const size_t smem = sym ? sizeof(SmemS) : (a_in_smem ? sizeof(Smem) : sizeof(SmemA));
   int grid = cached_sm_count();
   if (grid > p.items) grid = (int)p.items;
   void (*kern)(Params) = nullptr;
-  if (a_in_smem) {
+  if (sym) {
+    if (method == PH_METHOD_INVERSE_QUADRATIC)
+      kern = fuse ? hist_fwd_sym_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_sym_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
+    else
+      kern = fuse ? hist_fwd_sym_kernel<PH_METHOD_RBF, true> : hist_fwd_sym_kernel<PH_METHOD_RBF, false>;
+  } else if (a_in_smem) {
     if (method == PH_METHOD_INVERSE_QUADRATIC)
       kern = fuse ? hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, true> : hist_fwd_tc_kernel<PH_METHOD_INVERSE_QUADRATIC, false>;
     else
@@ -1043,7 +1341,7 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
     p.dom_v = dom + (blk % nb) * BINS;
     p.raw_out = raw ? raw + (int64_t)blk * batch * (3 * BINS * BINS) : nullptr;
     if (n_tail > 0) PH_CUDA_OK(cudaMemsetAsync(p.tail_counter, 0, (size_t)n_tail * sizeof(int), st));
-    if (a_in_smem) {
+    if (a_in_smem && !sym) {
       kern<<<grid, THREADS, smem, st>>>(p);
     } else {
       PH_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(THREADS), smem, st, p));

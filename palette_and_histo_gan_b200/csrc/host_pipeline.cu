@@ -174,6 +174,13 @@ static int host_hist_begin_impl(ph_host_ctx* ctx, const void* real_host, bool re
   PH_CHECK_ARG(bins >= 1 && bins <= 1024, "bins must be in [1,1024]");
   PH_CUDA_OK(cudaSetDevice(ctx->device));
   ctx->job_valid = false;
+  // the bin centres are host data here, so the library checks the contract of PH_IMPL_MIRROR itself: antisymmetric
+  // centres (tf.linspace(-3, 3, 64), histogram.py:55) let the fake images' forward share the weight vectors of +x and -x
+  {
+    float asym = 0.f;
+    for (int j = 0; j < bins; ++j) asym = fmaxf(asym, fabsf(bin_centers_host[j] + bin_centers_host[bins - 1 - j]));
+    if (asym <= 2e-5f * sqrtf(sigma_sqr)) impl |= PH_IMPL_MIRROR; else impl &= ~PH_IMPL_MIRROR;
+  }
 
   // chunking: at least two images per SM per chunk (each chunk then takes the whole-image kernel path) and at
   // least 8 MiB per copy.  (Measured at cfgC: uniform 296-image chunks 520 k pairs/s; 148: 441 k; 592: 478 k; a

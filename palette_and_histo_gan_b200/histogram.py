@@ -50,6 +50,18 @@ def histogram_domain(size: int, device) -> torch.Tensor:
     return dom
 
 
+MIRROR_FLAG = 16  # PH_IMPL_MIRROR
+
+
+def _mirror_flag(size: int, sigma, mirror: bool) -> int:
+    """PH_IMPL_MIRROR when the bin centres are antisymmetric to within 2e-5 sigma (palhist.h) — `tf.linspace(-3, 3,
+    64)` is, to 3.6e-7 — so that dense 64-bin batches run the mirrored-tile forward."""
+    if not mirror:
+        return 0
+    dom = tf_linspace(-3.0, 3.0, int(size)).astype(np.float64)
+    return MIRROR_FLAG if float(np.abs(dom + dom[::-1]).max()) <= 2e-5 * float(np.float32(sigma)) else 0
+
+
 def _method_id(method) -> int:
     try:
         return _lib.METHODS[method]
@@ -249,16 +261,19 @@ def _range_checked(run, impl, device, range_check):
 
 
 def calculate_rgbuv_histogram(image_batch, size=64, method="inverse-quadratic", sigma=0.02, *, impl="auto",
-                              dedup=False, range_check="async"):
+                              dedup=False, range_check="async", mirror=True):
     """histogram.py:36-81.  image_batch (B,H,W,3|4) float32 in [-1,1] -> (B,size,size,3), sums to 1 per image.
     `dedup=True`: contract each image's unique colours with their multiplicities (exact; pays off for
     palette images such as dataset sprites, falls back to the dense contraction per image otherwise).
-    `range_check`: see `_range_checked` (images outside [-1, 1] on the tensor-core engine)."""
+    `range_check`: see `_range_checked` (images outside [-1, 1] on the tensor-core engine).
+    `mirror`: dense 64-bin batches share the weight vectors of +x and -x (`_mirror_flag`); False = six vectors per
+    pixel around the exact centres."""
     image = require_cuda(from_any(image_batch, name="image_batch"), torch.float32, name="image_batch")
     dom = histogram_domain(size, image.device)
     mid, s2 = _method_id(method), _sigma_sqr(sigma)
+    mflag = _mirror_flag(size, sigma, mirror)
     out = _range_checked(lambda eng: _RgbuvHistogramFn.apply(image, dom, mid, s2,
-                                                             _lib.IMPLS[eng] | (DEDUP_FLAG if dedup else 0)),
+                                                             _lib.IMPLS[eng] | (DEDUP_FLAG if dedup else 0) | mflag),
                          impl, image.device, range_check)
     return to_caller_framework(out, image_batch)
 
@@ -316,11 +331,12 @@ def l2_loss(y_true, y_pred):
 
 
 def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", sigma=0.02, *, group=None,
-                   global_batch=None, impl="auto", dedup_real=True, range_check="async"):
+                   global_batch=None, impl="auto", dedup_real=True, range_check="async", mirror=True):
     """`hellinger_loss(calculate_rgbuv_histogram(real), calculate_rgbuv_histogram(fake))` as one call
     (pix2pix_model.py:243-245); differentiable with respect to `fake_image`.  `dedup_real`: the real images
     come from the dataset and are palette sprites, so their histogram is contracted over unique colours
-    (images that are not palette-like are detected on the device and contracted densely)."""
+    (images that are not palette-like are detected on the device and contracted densely).  `mirror`: the fake
+    images' forward shares the weight vectors of +x and -x (`calculate_rgbuv_histogram`)."""
     real = require_cuda(from_any(real_image, name="real_image"), torch.float32, name="real_image")
     fake = require_cuda(from_any(fake_image, name="fake_image"), torch.float32, name="fake_image")
     if real.shape != fake.shape:
@@ -330,7 +346,8 @@ def histogram_loss(real_image, fake_image, size=64, method="inverse-quadratic", 
                          "`_lib.async_status()` after the step instead")
     dom = histogram_domain(size, fake.device)
     mid, s2 = _method_id(method), _sigma_sqr(sigma)
-    out = _range_checked(lambda eng: _HistogramLossFn.apply(real, fake, dom, mid, s2, _lib.IMPLS[eng], group,
+    mflag = _mirror_flag(size, sigma, mirror)
+    out = _range_checked(lambda eng: _HistogramLossFn.apply(real, fake, dom, mid, s2, _lib.IMPLS[eng] | mflag, group,
                                                             global_batch, bool(dedup_real)),
                          impl, fake.device, range_check)
     return to_caller_framework(out, fake_image)
