@@ -292,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- per-phase breakdown (same kernels, CUDA events between phases on the launching stream) ----
     dom = H.histogram_domain(BINS, dev)
-    mid, s2, impl_id = 0, H._sigma_sqr(0.02), _lib.IMPLS[impl]
+    mid, s2, impl_id = 0, H._sigma_sqr(0.02), _lib.IMPLS[impl] | H._mirror_flag(BINS, 0.02, True)  # as histogram_loss
     fake_d = fake.detach()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     barrier()
@@ -488,7 +488,7 @@ def bench_scale_sweep(torch, dev, world, rank, distributed, barrier, peaks):
     tflops = 24.0 * bins * bins * side * side * gb / (float(ms) * 1e-3) / 1e12
     # per-phase breakdown of one step on this rank (CUDA events between the phases, as for cfgC)
     dom = H.histogram_domain(bins, dev)
-    s2, impl_id = H._sigma_sqr(0.02), 0
+    s2, impl_id = H._sigma_sqr(0.02), H._mirror_flag(bins, 0.02, True)
     fake_d = fake.detach()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     barrier()

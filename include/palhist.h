@@ -74,7 +74,7 @@ enum ph_impl {
   PH_IMPL_DEDUP = 8,
   /* flag, OR-ed into impl for ph_hist_forward / ph_hist_forward_ssum: the caller asserts that the bin centres are
    * antisymmetric, |c[j] + c[bins-1-j]| <= 2e-5 sigma for every j (tf.linspace(-3, 3, 64), histogram.py:55, is: 3.6e-7).
-   * Dense 64-bin batches on the tensor-core engine then run the mirrored-tile forward: the weight vectors of +x and -x
+   * Dense 64-bin batches of images with >= 1024 pixels on the tensor-core engine then run the mirrored-tile forward: the weight vectors of +x and -x
    * are bin-reversed copies of each other around the midpoint centres (c[j] - c[63-j]) / 2, three vectors per pixel
    * instead of six (adds <= 2e-6 to the histogram error at 64 x 64 pixels).  Ignored for every other
    * configuration (other bin counts, PH_IMPL_DEDUP, the CUDA-core engine, the backward).  A launch whose centres break

@@ -17,6 +17,7 @@ METHODS = {"inverse-quadratic": 0, "RBF": 1}
 ORDERINGS = {"top2bottom": 0, "bottom2top": 1, "grayness": 2, "shuffled": 3}
 MAP_OPS = {"blacken": 0, "normalize": 1, "denormalize": 2}
 ASYNC_RANGE = 1
+ASYNC_MIRROR = 2  # a forward launched with PH_IMPL_MIRROR found bin centres that are not antisymmetric
 ABI_VERSION = 3
 COMM_HANDLE_BYTES = 64
 INDEX_MODES = {"exact": 0, "nearest": 1}

@@ -757,8 +757,8 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tca_kernel(Params p) {
 // vector of x.  TensorFlow's `linspace(-3, 3, 64)` is antisymmetric only to 3.6e-7 (start + i * delta in float32), so
 // the vectors are generated once around the MIDPOINT centres t_j = (c_j - c_{63-j}) / 2 and used for both signs: every
 // use is off by at most half the asymmetry, 1.8e-7 — the size of the float32 rounding of the coordinate itself.
-// Measured cost (CPU model oracle/…, tests): histogram 1.8-2.1e-6 from the float64 oracle at 64 x 64 pixels (kernel
-// above: 0.8-1.2e-6), 4.9e-6 for an 8 x 8 image (2.8e-6); gradients move by 0.4-1.9e-6 through G^.  The backward keeps the
+// Measured cost (tools/tc_check_sym.py, tests): histogram 1.9-2.1e-6 from the float64 reference at 64 x 64 pixels (kernel
+// above: 0.9-1.2e-6), 5.3e-6 for an 8 x 8 image (2.7e-6); gradients move by 0.4-1.9e-6 through G^.  The backward keeps the
 // exact centres (dK/du is ten times as sensitive).
 // With alpha = sqrt(Iy) k(a), beta = sqrt(Iy) k(b), gamma = sqrt(Iy) k(c)  (64 bins each, centres t):
 //     H_R[i, j] = (alpha beta^T)[i, j]     H_G[i, j] = (alpha gamma^T)[63-i, j]     H_B[i, j] = (beta gamma^T)[63-i, 63-j]
@@ -773,12 +773,13 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tca_kernel(Params p) {
 // alpha or beta x 16 pixels: one tcgen05.st.x16 per thread; the beta warps also store their rows to the B tile) and
 // one gamma task (32 bins x 8 pixels -> B tile).
 // =============================================================================================
-constexpr int SKB = 64;                  // pixels per stage
-constexpr int SNS = 3;                   // stages in flight: B tiles in shared memory, A slots in tensor memory
-constexpr int S_CHAIN = 16;              // stages per accumulation chain (1024 pixels, as above)
-constexpr int SPR = 4;                   // pixel ring slots
+constexpr int NSUB = 2;                  // 64-pixel sub-stages per stage: one barrier round trip per NSUB x 64 pixels
+constexpr int SKB = 64 * NSUB;           // pixels per stage
+constexpr int SNS = 4 / NSUB;            // stages in flight: B tiles in shared memory, A slots in tensor memory
+constexpr int S_CHAIN = 16 / NSUB;       // stages per accumulation chain (1024 pixels, as above)
+constexpr int SPR = NSUB == 1 ? 6 : 3;   // pixel ring slots
 constexpr int S_A_COL0 = 256;            // D = columns 0-255, A slots behind it
-constexpr int S_A_SLOT_COLS = 64;        // four K steps x [hi 8 | lo 8] columns
+constexpr int S_A_SLOT_COLS = SKB;       // SKB / 16 K steps x [hi 8 | lo 8] columns
 constexpr int SB_KB_BYTES = 32 * 128;    // 4096: one core-matrix column (8 pixels) of all 256 rows
 constexpr int SB_STAGE_BYTES = (SKB / 8) * SB_KB_BYTES;  // 32768
 constexpr int ROW_G_HI = 0, ROW_B_HI = 64, ROW_G_LO = 128, ROW_B_LO = 192;  // B tile rows / D columns
@@ -789,7 +790,7 @@ struct PxSlotS {
 };
 
 struct SmemS {
-  alignas(128) unsigned char bt[SNS][SB_STAGE_BYTES];  // 96 KB
+  alignas(128) unsigned char bt[SNS][SB_STAGE_BYTES];  // 128 KB
   float acc[3][BINS][BINS + 1];
   PxSlotS px[SPR];
   float ctr[BINS];  // scaled midpoint centres
@@ -840,9 +841,10 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_sym_kernel(Params p) {
       for (uint32_t base = px0; base < px1; base += SKB, ++it) {
         if ((int)(it % PXW) != me) continue;
         const int slot = it % SPR;
-        float va[2], vb[2], vc[2], vs[2];
+        constexpr int PPL = SKB / 32;  // pixels per lane
+        float va[PPL], vb[PPL], vc[PPL], vs[PPL];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < PPL; ++k) {
           const uint32_t px = base + k * 32 + lane;
           const bool valid = px < px1;
           float r = 0.f, g = 0.f, bl = 0.f;
@@ -870,7 +872,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_sym_kernel(Params p) {
         mbar_wait_relaxed(&S.px_empty[slot], ((it / SPR) & 1) ^ 1, 400);
         PxSlotS& o = S.px[slot];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < PPL; ++k) {
           o.a[k * 32 + lane] = va[k]; o.b[k * 32 + lane] = vb[k]; o.c[k * 32 + lane] = vc[k];
           o.siy[k * 32 + lane] = vs[k];
         }
@@ -888,71 +890,92 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_sym_kernel(Params p) {
     const f32x2 negc = pack2(-c_bin, -c_bin);
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t row16 = (uint32_t)((bin >> 3) * 128 + (bin & 7) * 16);  // byte offset of row `bin` in a core-matrix column
-    uint32_t it = 0, chain = 0;
+    // Wrap-around counters (no % or /).  The stores of a stage are PUBLISHED one stage late: fence, tcgen05.wait::st and
+    // the arrival on ab_full follow the next stage's arithmetic, so their latency (all 16 warps reach them together)
+    // is hidden behind it; a chain's last stage is published at once.
+    uint32_t slot = 0, slot_par = 0, stage = 0, stage_par = 0, chain = 0;
+    int pend = -1;  // stage stored but not yet published (warp-uniform)
     for (int64_t w = first; w < p.items; w += step) {
       const ItemRange ir = item_range(p, w);
       const uint32_t nkb = (ir.px1 - ir.px0 + SKB - 1) / SKB;
-      for (uint32_t kb = 0; kb < nkb; ++kb, ++it) {
-        const int slot = it % SPR, stage = it % SNS;
-        mbar_wait(&S.px_full[slot], (it / SPR) & 1);
+      for (uint32_t kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&S.px_full[slot], slot_par);
         const PxSlotS& in = S.px[slot];
-        ulonglong2 xx[4], iw[4], xc[2], ic[2];
-        {
-          const float* src = (quad < 2 ? in.a : in.b) + r16 * 16;
+        unsigned char* tile = &S.bt[stage][0];
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+          ulonglong2 xx[4], iw[4], xc[2], ic[2];
+          {
+            const float* src = (quad < 2 ? in.a : in.b) + sub * 64 + r16 * 16;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              xx[q4] = *reinterpret_cast<const ulonglong2*>(src + q4 * 4);
+              iw[q4] = *reinterpret_cast<const ulonglong2*>(&in.siy[sub * 64 + r16 * 16 + q4 * 4]);
+            }
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+              xc[q2] = *reinterpret_cast<const ulonglong2*>(&in.c[sub * 64 + g8 * 8 + q2 * 4]);
+              ic[q2] = *reinterpret_cast<const ulonglong2*>(&in.siy[sub * 64 + g8 * 8 + q2 * 4]);
+            }
+          }
+          if (sub == NSUB - 1) {
+            mbar_arrive_warp(&S.px_empty[slot]);
+            if (++slot == SPR) { slot = 0; slot_par ^= 1; }
+          }
+          uint32_t rr[16];  // this thread's row: [hi: pixel pairs 0..7 | lo: pixel pairs 0..7]
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            xx[q4] = *reinterpret_cast<const ulonglong2*>(src + q4 * 4);
-            iw[q4] = *reinterpret_cast<const ulonglong2*>(&in.siy[r16 * 16 + q4 * 4]);
+            f32x2 w0, w1;
+            weight4<METHOD>(xx[q4].x, xx[q4].y, negc, wa2, wb2, w0, w1);
+            w0 = mul2(w0, iw[q4].x);
+            w1 = mul2(w1, iw[q4].y);
+            split_f16x2(w0, mone2, rr[2 * q4], rr[8 + 2 * q4]);
+            split_f16x2(w1, mone2, rr[2 * q4 + 1], rr[8 + 2 * q4 + 1]);
           }
-#pragma unroll
-          for (int q2 = 0; q2 < 2; ++q2) {
-            xc[q2] = *reinterpret_cast<const ulonglong2*>(&in.c[g8 * 8 + q2 * 4]);
-            ic[q2] = *reinterpret_cast<const ulonglong2*>(&in.siy[g8 * 8 + q2 * 4]);
+          uint4 ghi, glo;
+          {
+            f32x2 w0, w1, w2, w3;
+            weight4<METHOD>(xc[0].x, xc[0].y, negc, wa2, wb2, w0, w1);
+            weight4<METHOD>(xc[1].x, xc[1].y, negc, wa2, wb2, w2, w3);
+            w0 = mul2(w0, ic[0].x); w1 = mul2(w1, ic[0].y); w2 = mul2(w2, ic[1].x); w3 = mul2(w3, ic[1].y);
+            split_f16x2(w0, mone2, ghi.x, glo.x);
+            split_f16x2(w1, mone2, ghi.y, glo.y);
+            split_f16x2(w2, mone2, ghi.z, glo.z);
+            split_f16x2(w3, mone2, ghi.w, glo.w);
           }
+          if (sub == 0) {
+            if (pend >= 0) {  // publish the previous stage
+              fence_proxy_async_smem();
+              tmem_st_wait();
+              tc_fence_before_sync();
+              mbar_arrive_warp(&S.ab_full[pend]);
+            }
+            // the MMAs that read this stage's A slot and B tile (SNS stages ago) are done
+            mbar_wait(&S.ab_empty[stage], stage_par ^ 1);
+            tc_fence_after_sync();
+          }
+          // K step 4 sub + r16 of the stage; core-matrix columns 8 sub + 2 r16 (+ 1) for beta, 8 sub + g8 for gamma
+          tmem_st16(tmem + lane_addr + S_A_COL0 + stage * S_A_SLOT_COLS + (sub * 4 + r16) * 16, rr);
+          if (quad >= 2) {  // beta is also the B operand of alpha . beta^T: rows 64 + bin (hi), 192 + bin (lo)
+            unsigned char* col = tile + (sub * 8 + 2 * r16) * SB_KB_BYTES + row16;
+            *reinterpret_cast<uint4*>(col + ROW_B_HI * 16) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+            *reinterpret_cast<uint4*>(col + ROW_B_HI * 16 + SB_KB_BYTES) = make_uint4(rr[4], rr[5], rr[6], rr[7]);
+            *reinterpret_cast<uint4*>(col + ROW_B_LO * 16) = make_uint4(rr[8], rr[9], rr[10], rr[11]);
+            *reinterpret_cast<uint4*>(col + ROW_B_LO * 16 + SB_KB_BYTES) = make_uint4(rr[12], rr[13], rr[14], rr[15]);
+          }
+          *reinterpret_cast<uint4*>(tile + (sub * 8 + g8) * SB_KB_BYTES + row16 + ROW_G_HI * 16) = ghi;
+          *reinterpret_cast<uint4*>(tile + (sub * 8 + g8) * SB_KB_BYTES + row16 + ROW_G_LO * 16) = glo;
         }
-        mbar_arrive_warp(&S.px_empty[slot]);
-        uint32_t rr[16];  // this thread's row: [hi: pixel pairs 0..7 | lo: pixel pairs 0..7]
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          f32x2 w0, w1;
-          weight4<METHOD>(xx[q4].x, xx[q4].y, negc, wa2, wb2, w0, w1);
-          w0 = mul2(w0, iw[q4].x);
-          w1 = mul2(w1, iw[q4].y);
-          split_f16x2(w0, mone2, rr[2 * q4], rr[8 + 2 * q4]);
-          split_f16x2(w1, mone2, rr[2 * q4 + 1], rr[8 + 2 * q4 + 1]);
-        }
-        uint4 ghi, glo;
-        {
-          f32x2 w0, w1, w2, w3;
-          weight4<METHOD>(xc[0].x, xc[0].y, negc, wa2, wb2, w0, w1);
-          weight4<METHOD>(xc[1].x, xc[1].y, negc, wa2, wb2, w2, w3);
-          w0 = mul2(w0, ic[0].x); w1 = mul2(w1, ic[0].y); w2 = mul2(w2, ic[1].x); w3 = mul2(w3, ic[1].y);
-          split_f16x2(w0, mone2, ghi.x, glo.x);
-          split_f16x2(w1, mone2, ghi.y, glo.y);
-          split_f16x2(w2, mone2, ghi.z, glo.z);
-          split_f16x2(w3, mone2, ghi.w, glo.w);
-        }
-        // the MMAs that read this stage's A slot and B tile (SNS stages ago) are done
-        mbar_wait(&S.ab_empty[stage], ((it / SNS) & 1) ^ 1);
-        tc_fence_after_sync();
-        tmem_st16(tmem + lane_addr + S_A_COL0 + stage * S_A_SLOT_COLS + r16 * 16, rr);
-        unsigned char* tile = &S.bt[stage][0];
-        if (quad >= 2) {  // beta is also the B operand of alpha . beta^T: rows 64 + bin (hi), 192 + bin (lo)
-          unsigned char* col = tile + (2 * r16) * SB_KB_BYTES + row16;
-          *reinterpret_cast<uint4*>(col + ROW_B_HI * 16) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
-          *reinterpret_cast<uint4*>(col + ROW_B_HI * 16 + SB_KB_BYTES) = make_uint4(rr[4], rr[5], rr[6], rr[7]);
-          *reinterpret_cast<uint4*>(col + ROW_B_LO * 16) = make_uint4(rr[8], rr[9], rr[10], rr[11]);
-          *reinterpret_cast<uint4*>(col + ROW_B_LO * 16 + SB_KB_BYTES) = make_uint4(rr[12], rr[13], rr[14], rr[15]);
-        }
-        *reinterpret_cast<uint4*>(tile + g8 * SB_KB_BYTES + row16 + ROW_G_HI * 16) = ghi;
-        *reinterpret_cast<uint4*>(tile + g8 * SB_KB_BYTES + row16 + ROW_G_LO * 16) = glo;
-        fence_proxy_async_smem();
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive_warp(&S.ab_full[stage]);
+        pend = (int)stage;
+        if (++stage == SNS) { stage = 0; stage_par ^= 1; }
 
         const bool chain_end = ((kb + 1) % S_CHAIN == 0) || (kb + 1 == nkb);
         if (!chain_end) continue;
+        fence_proxy_async_smem();
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&S.ab_full[pend]);
+        pend = -1;
         // ---- chain epilogue: D (128 rows x [. gamma_hi | . beta_hi | . gamma_lo | . beta_lo]) += into the fp32 accumulator.
         //      Warp (quad, r16): rows 32 quad .., columns 32 r16 .. + 31 of the hi half and of the lo half. ----
         mbar_wait(&S.d_full, chain & 1);
@@ -1270,10 +1293,15 @@ int tc_hist_forward(const float* image, int64_t batch, int64_t npix, int channel
   const FwdPlan pl = tc_fwd_plan(batch, npix, dedup);
   // mirrored-tile kernel: dense 64-bin batches whose centres the caller declared antisymmetric (PH_IMPL_MIRROR)
   static const bool sym_off = getenv("PH_FWD_SYM") && atoi(getenv("PH_FWD_SYM")) == 0;  // tuning knob
-  const bool sym = mirror && !dedup && nb == 1 && !sym_off;
+  // images of fewer than 1024 pixels keep the exact centres: the centre mismatch averages out over the pixels (3.5e-6 at
+  // 32 x 32, 2.1e-6 at 64 x 64 against 5e-6 with a 1e-5 peak error for 8 x 8 or 20 x 12 images), and they cost nothing
+  const bool sym = mirror && !dedup && nb == 1 && npix >= 1024 && !sym_off;
   p.n_whole = pl.n_whole;
   p.splits = pl.splits;
   p.px_per_split = ceil_div(ceil_div(npix, p.splits), sym ? SKB : KB) * (sym ? SKB : KB);
+  // rounding the slice length up to whole stages can leave the last slices without pixels (4096 pixels in 10 slices of
+  // 512): an item must own at least one stage, so the slice count follows the rounded length
+  p.splits = (int)ceil_div(npix, p.px_per_split);
   p.items = p.n_whole + (batch - p.n_whole) * p.splits;
   p.eps = eps;
   const tcgen::WeightScales wsc = tcgen::weight_scales(method, sigma_sqr);

@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg._lib.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in palhist.h but not exported"
-    assert lib.ph_abi_version() == pkg._lib.ABI_VERSION == 2
+    assert lib.ph_abi_version() == pkg._lib.ABI_VERSION == 3
 
 
 def test_ctypes_prototypes_match_header(pkg):

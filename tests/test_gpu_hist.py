@@ -226,7 +226,9 @@ def test_dedup_forward_matches_dense(H, cuda, sprites):
     batch = np.concatenate([spr[:100], dense[:12], few, spr[100:], dense[12:]]).astype(np.float32)
     x = torch.from_numpy(batch).to(cuda)
     a = H.calculate_rgbuv_histogram(x, impl="tc", dedup=True).cpu().numpy()
-    b = H.calculate_rgbuv_histogram(x, impl="tc", dedup=False).cpu().numpy()
+    # the regrouping is what is under test: both sides on the exact centres (the mirrored-tile kernel, the default
+    # for dense batches, has its own tests below)
+    b = H.calculate_rgbuv_histogram(x, impl="tc", dedup=False, mirror=False).cpu().numpy()
     assert ho.rel_l2(a, b) < 3e-6
     pick = [0, 57, 100, 105, 112, 113, 150, 225]
     ref, _ = ho.rgbuv_histogram_f64(batch[pick])
@@ -236,7 +238,7 @@ def test_dedup_forward_matches_dense(H, cuda, sprites):
     f1 = fake.clone().requires_grad_(True)
     f2 = fake.clone().requires_grad_(True)
     l1 = H.histogram_loss(x, f1, dedup_real=True); l1.backward()
-    l2 = H.histogram_loss(x, f2, dedup_real=False); l2.backward()
+    l2 = H.histogram_loss(x, f2, dedup_real=False, mirror=False); l2.backward()  # everything dense on the exact centres
     assert abs(float(l1.detach()) - float(l2.detach())) / float(l2.detach()) < 1e-6
     assert ho.rel_l2(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < 1e-5
 
@@ -419,7 +421,7 @@ def test_dense_images_in_a_deduplicated_batch_are_bit_identical(H, cuda, sprites
     assert batch.shape[0] == 296
     x = torch.from_numpy(batch).to(cuda)
     a = H.calculate_rgbuv_histogram(x, impl="tc", dedup=True)
-    b = H.calculate_rgbuv_histogram(x, impl="tc", dedup=False)
+    b = H.calculate_rgbuv_histogram(x, impl="tc", dedup=False, mirror=False)  # the same kernel without de-duplication
     dense_idx = list(range(90, 100)) + list(range(286, 296))
     assert torch.equal(a[dense_idx], b[dense_idx])
     ref, _ = ho.rgbuv_histogram_f64(batch[[95, 290]])
@@ -715,3 +717,92 @@ def test_cfgA_batch_32_sprites_against_oracle(H, cuda, sprites, impl):
     assert ho.rel_l2(hf, ref["hist_fake"]) < HIST_TOL and ho.rel_l2(hr, ref["hist_real"]) < HIST_TOL
     assert abs(float(loss.detach()) - ref["loss"]) / ref["loss"] < LOSS_TOL
     assert ho.rel_l2(f.grad.cpu().numpy(), ref["grad"]) < GRAD_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# mirrored-tile forward (PH_IMPL_MIRROR, the default for dense 64-bin batches)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(3, 64, 64, 4), (2, 32, 32, 4), (3, 20, 12, 4), (2, 16, 16, 3), (4, 8, 8, 4),
+                                   (1, 96, 96, 4)])
+def test_mirrored_forward_against_oracle(H, cuda, shape):
+    """Three weight vectors per pixel around the midpoint centres instead of six around the exact ones: within the 1e-5
+    bar of the float64 oracle (measured 2.1e-6 at 64 x 64, 3.5e-6 at 32 x 32), within 6e-6 of the exact-centre
+    kernel, every channel alike (the bin reversals of the G and B histograms), rows summing to one."""
+    rng = np.random.default_rng(61)
+    img = np.tanh(rng.standard_normal(shape)).astype(np.float32)
+    x = torch.from_numpy(img).to(cuda)
+    s = H.calculate_rgbuv_histogram(x, impl="tc", mirror=True)
+    e = H.calculate_rgbuv_histogram(x, impl="tc", mirror=False)
+    # images of fewer than 1024 pixels keep the exact-centre kernel (the mismatch does not average out over so few
+    # pixels: measured 5e-6 with a 1e-5 peak error at 8 x 8 / 20 x 12); from 32 x 32 on the mirrored kernel runs
+    assert torch.equal(s, e) == (shape[1] * shape[2] < 1024)
+    sn = s.cpu().numpy()
+    ref, _ = ho.rgbuv_histogram_f64(img)
+    assert ho.rel_l2(sn, ref) < HIST_TOL and ho.rel_max(sn, ref) < HIST_TOL
+    for c in range(3):
+        assert ho.rel_l2(sn[..., c], ref[..., c]) < HIST_TOL, c
+    assert ho.rel_l2(sn, e.cpu().numpy()) < 6e-6
+    assert float((s.sum((1, 2, 3)) - 1).abs().max()) < 3e-6
+
+
+def test_mirrored_forward_plans_rbf_and_determinism(H, cuda):
+    """Whole-image items, the sliced tail of a partial wave and a batch sliced entirely; RBF; bit-reproducible."""
+    rng = np.random.default_rng(62)
+    img = np.tanh(rng.standard_normal((160, 64, 64, 4))).astype(np.float32)  # 148 whole images + 12 sliced
+    x = torch.from_numpy(img).to(cuda)
+    s = H.calculate_rgbuv_histogram(x, impl="tc")
+    pick = [0, 77, 147, 148, 153, 159]
+    ref, _ = ho.rgbuv_histogram_f64(img[pick])
+    assert ho.rel_l2(s[pick].cpu().numpy(), ref) < HIST_TOL
+    assert torch.equal(s, H.calculate_rgbuv_histogram(x, impl="tc"))
+    few = H.calculate_rgbuv_histogram(x[:5], impl="tc")  # batch < SM count: every image in pixel slices
+    assert ho.rel_l2(few.cpu().numpy(), s[:5].cpu().numpy()) < 2e-6
+    r = H.calculate_rgbuv_histogram(x[:4], method="RBF", sigma=0.5, impl="tc").cpu().numpy()
+    ref_r, _ = ho.rgbuv_histogram_f64(img[:4], method="RBF", sigma=0.5)
+    assert ho.rel_l2(r, ref_r) < HIST_TOL
+
+
+def test_mirrored_loss_and_gradient_at_the_bench_shape(H, cuda, sprites):
+    """The default `histogram_loss` (de-duplicated real sprites, mirrored-tile forward of the fake images, exact-centre
+    backward) at one full wave + tail: loss and the gradient of picked images against the float64 oracle."""
+    rng = np.random.default_rng(63)
+    n = 300
+    spr = normalize(np.concatenate([sprites["front"], sprites["right"], sprites["front"]])[:n].astype(np.float32))
+    fake_np = np.tanh(rng.standard_normal((n, 64, 64, 4))).astype(np.float32)
+    real = torch.from_numpy(spr).to(cuda)
+    fake = torch.from_numpy(fake_np).to(cuda).requires_grad_(True)
+    loss = H.histogram_loss(real, fake)
+    loss.backward()
+    ht, _ = ho.rgbuv_histogram_f64(spr)
+    hp, _ = ho.rgbuv_histogram_f64(fake_np)
+    ssum = float(((np.sqrt(hp) - np.sqrt(ht)) ** 2).sum())
+    ref_loss = np.sqrt(ssum) / np.sqrt(2.0) / n
+    assert abs(float(loss.detach()) - ref_loss) / ref_loss < LOSS_TOL
+    pick = [0, 147, 148, 299]
+    ref = ho.hist_loss_and_grad_f64(spr[pick], fake_np[pick], global_batch=n, global_ssum=ssum)
+    g = fake.grad[pick].cpu().numpy()
+    for k in range(len(pick)):
+        assert ho.rel_l2(g[k], ref["grad"][k]) < GRAD_TOL, pick[k]
+
+
+def test_mirror_flag_on_asymmetric_centres_is_flagged_not_silent(H, cuda):
+    """PH_IMPL_MIRROR is the caller's assertion that the centres are antisymmetric; a launch whose centres are not sets
+    PH_ASYNC_MIRROR and the next ph_hist_* call fails (the Python host only sets the flag after checking the values)."""
+    from palette_and_histo_gan_b200 import _lib
+
+    assert H._mirror_flag(64, 0.02, True) == H.MIRROR_FLAG and H._mirror_flag(64, 0.02, False) == 0
+    assert H._mirror_flag(64, 0.002, True) == 0  # asymmetry of tf.linspace / sigma too large: exact-centre kernel
+    x = torch.tanh(torch.randn(2, 32, 32, 4, device=cuda))
+    dom = H.histogram_domain(64, cuda).clone()
+    dom[5] += 1e-3
+    _lib.async_status(clear=True)
+    H._forward(x, dom, 0, H._sigma_sqr(0.02), _lib.IMPLS["tc"] | H.MIRROR_FLAG)
+    torch.cuda.synchronize()
+    assert _lib.async_status() & _lib.ASYNC_MIRROR
+    with pytest.raises(_lib.PalHistError, match="antisymmetric"):
+        H.calculate_rgbuv_histogram(x, impl="tc")
+    assert _lib.async_status() == 0
+    # without the flag the same centres run on the exact-centre kernel
+    h, _ = H._forward(x, dom, 0, H._sigma_sqr(0.02), _lib.IMPLS["tc"])
+    ref, _ = ho.rgbuv_histogram_f64(x.cpu().numpy(), dom=dom.cpu().numpy())
+    assert ho.rel_l2(h.cpu().numpy(), ref) < HIST_TOL
