@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpalhist.so")
+# PALHIST_LIB: another build of the same library (kernel experiments: tools/gpu_r2_variants.sh times several
+# builds on one box); it must export the same ABI, which _load() checks
+LIB_PATH = os.environ.get("PALHIST_LIB") or os.path.join(_HERE, "libpalhist.so")
 
 PH_OK = 0
 PH_ERR_INVALID, PH_ERR_CUDA, PH_ERR_UNSUPPORTED = -1, -2, -3
