@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(FWD_THREADS) hist_fwd_simt_kernel(FwdParams p)
       if (px < px_end) {
         if (p.comp != nullptr) {
           const int64_t o = b * p.npix + px;
-          const double lc = log((double)p.comp[o] + (double)p.eps);
-          split_double(lc - log((double)p.proj1[o] + (double)p.eps), u_l, ul_l);
-          split_double(lc - log((double)p.proj2[o] + (double)p.eps), v_l, vl_l);
+          const double lc = log_pos((double)p.comp[o] + (double)p.eps);
+          split_double(lc - log_pos((double)p.proj1[o] + (double)p.eps), u_l, ul_l);
+          split_double(lc - log_pos((double)p.proj2[o] + (double)p.eps), v_l, vl_l);
           iy_l = p.inten[o];
         } else {
           const float* src = p.image + (b * p.npix + px) * p.channels;

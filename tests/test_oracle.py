@@ -355,3 +355,23 @@ def test_reference_augment_fixture_is_reproducible(tmp_path, monkeypatch, refere
     assert set(fresh) == set(reference_augment)
     for k in fresh:
         assert np.array_equal(fresh[k], reference_augment[k]), k
+
+
+def test_log_table():
+    """The float64 log of the kernels' pixel terms (common.cuh: log_pos): the table in the source is the generator's, and
+    the formula stays within 3e-15 of long-double logs over the range of x + eps (histogram.py:58-66)."""
+    import re
+    from oracle import make_log_table as mt
+    rows = mt.table()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "palette_and_histo_gan_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("PH_LOG_TABLE[128] = {"):]
+    body = body[:body.index("};")]
+    vals = [float.fromhex(v) for v in re.findall(r"-?0x[0-9a-f.]+p[-+]?\d+", body)]
+    assert len(vals) == 256
+    assert vals == [v for row in rows for v in row]
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(1e-6, 1.000001, 100000), 10.0 ** rng.uniform(-6, 0, 100000),
+                        rng.uniform(0.99, 1.000001, 20000), np.array([1e-6, 1.0, 1.000001, 0.5, 0.25 + 1e-6])])
+    err = np.abs(mt.log_pos_numpy(x, rows).astype(np.longdouble) - np.log(x.astype(np.longdouble)))
+    assert float(err.max()) < 3e-15, float(err.max())
