@@ -773,6 +773,110 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_tca_kernel(Params p) {
 // alpha or beta x 16 pixels: one tcgen05.st.x16 per thread; the beta warps also store their rows to the B tile) and
 // one gamma task (32 bins x 8 pixels -> B tile).
 // =============================================================================================
+// ---- float32 difference of two logarithms for the pixel pass below -------------------------------------------------
+// The three pixel-pass warps are this kernel's critical path (3 warps x one 128-pixel stage each: a slower pixel pass
+// slows the kernel one for one, profiles/r2d_fwd_timing_experiments.txt), and logf(e0 / e1) costs an IEEE division + a
+// libdevice log per coordinate.  Instead: log x = k ln2 + L_i + log1p(r) with x = 2^k m, the mantissa's top 7 bits
+// picking one of 128 intervals with centre c_i, r = fma(m, RN(1 / c_i), -1), |r| < 2^-8 (three series terms).
+// L_i = -log(RN(1 / c_i)) is tabulated as L_hi (a multiple of 2^-23: differences of two L_hi are exact) + L_lo, ln 2 is
+// split as LN2_HI (a multiple of 2^-18: k LN2_HI is exact) + LN2_LO, so the large part of a DIFFERENCE of two logs,
+// dk LN2_HI + dL_hi, costs one FMA whose rounding error is recovered exactly, and everything else is < 0.01.  The result
+// is the correctly rounded float32 difference in all but ~1e-9 of absolute error (mean 0.25 ulp against 1.3 ulp for
+// logf of the rounded ratio; the generator script make_log_table.py beside the test oracles replays it on the CPU).
+__device__ const float4 PH_LOGF_TABLE[128] = {
+    {0x1.fe01fe0000000p-1f, 0x1.ff00000000000p-9f, 0x1.5856220000000p-26f, 0.0f},     {0x1.fa11ca0000000p-1f, 0x1.7dc5000000000p-7f, -0x1.861fbe0000000p-25f, 0.0f},
+    {0x1.f6310a0000000p-1f, 0x1.3cea800000000p-6f, -0x1.105cae0000000p-25f, 0.0f},     {0x1.f25f640000000p-1f, 0x1.b9fc000000000p-6f, 0x1.5f5f240000000p-27f, 0.0f},
+    {0x1.ee9c800000000p-1f, 0x1.1b0d800000000p-5f, 0x1.0923da0000000p-25f, 0.0f},     {0x1.eae8080000000p-1f, 0x1.58a5c00000000p-5f, -0x1.506e360000000p-26f, 0.0f},
+    {0x1.e741aa0000000p-1f, 0x1.95c8400000000p-5f, -0x1.266e380000000p-26f, 0.0f},     {0x1.e3a9180000000p-1f, 0x1.d276c00000000p-5f, -0x1.ba49ea0000000p-26f, 0.0f},
+    {0x1.e01e020000000p-1f, 0x1.0759800000000p-4f, 0x1.24c7240000000p-27f, 0.0f},     {0x1.dca01e0000000p-1f, 0x1.253f600000000p-4f, 0x1.20a1420000000p-28f, 0.0f},
+    {0x1.d92f220000000p-1f, 0x1.42edc00000000p-4f, 0x1.b34c8e0000000p-25f, 0.0f},     {0x1.d5cac80000000p-1f, 0x1.6065800000000p-4f, 0x1.5a6ea20000000p-25f, 0.0f},
+    {0x1.d272ca0000000p-1f, 0x1.7da7600000000p-4f, 0x1.20f6260000000p-25f, 0.0f},     {0x1.cf26e60000000p-1f, 0x1.9ab4200000000p-4f, 0x1.29019e0000000p-27f, 0.0f},
+    {0x1.cbe6da0000000p-1f, 0x1.b78c800000000p-4f, -0x1.6a78920000000p-27f, 0.0f},     {0x1.c8b2660000000p-1f, 0x1.d431400000000p-4f, -0x1.5a4d320000000p-26f, 0.0f},
+    {0x1.c5894e0000000p-1f, 0x1.f0a3000000000p-4f, 0x1.c88b160000000p-27f, 0.0f},     {0x1.c26b540000000p-1f, 0x1.0671500000000p-3f, -0x1.86b4d20000000p-28f, 0.0f},
+    {0x1.bf583e0000000p-1f, 0x1.1478600000000p-3f, -0x1.c8c5ea0000000p-26f, 0.0f},     {0x1.bc4fd60000000p-1f, 0x1.2266f00000000p-3f, 0x1.9452d60000000p-26f, 0.0f},
+    {0x1.b951e20000000p-1f, 0x1.303d700000000p-3f, 0x1.3192000000000p-25f, 0.0f},     {0x1.b65e2e0000000p-1f, 0x1.3dfc300000000p-3f, -0x1.ec99ce0000000p-26f, 0.0f},
+    {0x1.b374840000000p-1f, 0x1.4ba3700000000p-3f, 0x1.34d2b00000000p-26f, 0.0f},     {0x1.b094b40000000p-1f, 0x1.5933900000000p-3f, -0x1.a59f7e0000000p-25f, 0.0f},
+    {0x1.adbe880000000p-1f, 0x1.66acd00000000p-3f, 0x1.01cab60000000p-25f, 0.0f},     {0x1.aaf1d20000000p-1f, 0x1.740f900000000p-3f, 0x1.fe01be0000000p-26f, 0.0f},
+    {0x1.a82e660000000p-1f, 0x1.815c000000000p-3f, 0x1.670d600000000p-25f, 0.0f},     {0x1.a574100000000p-1f, 0x1.8e92900000000p-3f, 0x1.4436a20000000p-30f, 0.0f},
+    {0x1.a2c2a80000000p-1f, 0x1.9bb3600000000p-3f, 0x1.51f7ee0000000p-25f, 0.0f},     {0x1.a01a020000000p-1f, 0x1.a8bed00000000p-3f, -0x1.07be880000000p-26f, 0.0f},
+    {0x1.9d79f20000000p-1f, 0x1.b5b5100000000p-3f, 0x1.d03ed60000000p-25f, 0.0f},     {0x1.9ae24e0000000p-1f, 0x1.c296900000000p-3f, -0x1.dbcf9c0000000p-25f, 0.0f},
+    {0x1.9852f00000000p-1f, 0x1.cf63600000000p-3f, -0x1.b7d8e80000000p-25f, 0.0f},     {0x1.95cbb00000000p-1f, 0x1.dc1bd00000000p-3f, -0x1.1aa09c0000000p-26f, 0.0f},
+    {0x1.934c680000000p-1f, 0x1.e8c0200000000p-3f, 0x1.42a96a0000000p-25f, 0.0f},     {0x1.90d4f20000000p-1f, 0x1.f550a00000000p-3f, 0x1.d96f6a0000000p-28f, 0.0f},
+    {0x1.8e65280000000p-1f, 0x1.00e6c00000000p-2f, 0x1.c56a800000000p-25f, 0.0f},     {0x1.8bfce80000000p-1f, 0x1.071b880000000p-2f, -0x1.f32a700000000p-26f, 0.0f},
+    {0x1.899c100000000p-1f, 0x1.0d46b00000000p-2f, 0x1.ecd5ba0000000p-25f, 0.0f},     {0x1.87427c0000000p-1f, 0x1.1368700000000p-2f, -0x1.7b15d40000000p-28f, 0.0f},
+    {0x1.84f00c0000000p-1f, 0x1.1980d00000000p-2f, 0x1.a2a11c0000000p-25f, 0.0f},     {0x1.82a4a00000000p-1f, 0x1.1f8ff80000000p-2f, 0x1.1245180000000p-25f, 0.0f},
+    {0x1.8060180000000p-1f, 0x1.2596000000000p-2f, 0x1.1df7640000000p-26f, 0.0f},     {0x1.7e22560000000p-1f, 0x1.2b93000000000p-2f, 0x1.3789d40000000p-26f, 0.0f},
+    {0x1.7beb3a0000000p-1f, 0x1.3187180000000p-2f, 0x1.20a20c0000000p-25f, 0.0f},     {0x1.79baa60000000p-1f, 0x1.3772680000000p-2f, 0x1.3fec320000000p-29f, 0.0f},
+    {0x1.7790820000000p-1f, 0x1.3d54f80000000p-2f, -0x1.7e08e40000000p-30f, 0.0f},     {0x1.756cac0000000p-1f, 0x1.432ef00000000p-2f, 0x1.7c27400000000p-25f, 0.0f},
+    {0x1.734f0c0000000p-1f, 0x1.4900680000000p-2f, 0x1.d8013a0000000p-27f, 0.0f},     {0x1.7137860000000p-1f, 0x1.4ec9780000000p-2f, -0x1.3effec0000000p-25f, 0.0f},
+    {0x1.6f26020000000p-1f, 0x1.548a280000000p-2f, 0x1.536e940000000p-25f, 0.0f},     {0x1.6d1a620000000p-1f, 0x1.5a42b00000000p-2f, -0x1.e659800000000p-25f, 0.0f},
+    {0x1.6b14900000000p-1f, 0x1.5ff3080000000p-2f, 0x1.d4f27c0000000p-27f, 0.0f},     {0x1.6914740000000p-1f, 0x1.659b580000000p-2f, -0x1.c7c1e00000000p-26f, 0.0f},
+    {0x1.6719f40000000p-1f, 0x1.6b3bb00000000p-2f, 0x1.6d65100000000p-28f, 0.0f},     {0x1.6524f80000000p-1f, 0x1.70d4300000000p-2f, -0x1.d0edba0000000p-27f, 0.0f},
+    {0x1.63356c0000000p-1f, 0x1.7664e00000000p-2f, -0x1.a312160000000p-29f, 0.0f},     {0x1.614b360000000p-1f, 0x1.7bede00000000p-2f, 0x1.0fbd7e0000000p-25f, 0.0f},
+    {0x1.5f66440000000p-1f, 0x1.816f400000000p-2f, -0x1.37cad80000000p-28f, 0.0f},     {0x1.5d867c0000000p-1f, 0x1.86e9180000000p-2f, 0x1.2d985e0000000p-25f, 0.0f},
+    {0x1.5babcc0000000p-1f, 0x1.8c5b800000000p-2f, -0x1.293a5c0000000p-25f, 0.0f},     {0x1.59d6200000000p-1f, 0x1.91c6780000000p-2f, 0x1.fa2d420000000p-25f, 0.0f},
+    {0x1.5805600000000p-1f, 0x1.972a380000000p-2f, -0x1.d765760000000p-25f, 0.0f},     {0x1.56397c0000000p-1f, 0x1.9c86b00000000p-2f, -0x1.b47ef40000000p-27f, 0.0f},
+    {0x1.54725e0000000p-1f, 0x1.a1dc080000000p-2f, -0x1.ba919a0000000p-28f, 0.0f},     {0x1.52aff60000000p-1f, 0x1.a72a480000000p-2f, -0x1.7509840000000p-28f, 0.0f},
+    {0x1.50f22e0000000p-1f, 0x1.ac71900000000p-2f, -0x1.d33a780000000p-25f, 0.0f},     {0x1.4f38f60000000p-1f, 0x1.b1b1e00000000p-2f, 0x1.77dfc60000000p-26f, 0.0f},
+    {0x1.4d843c0000000p-1f, 0x1.b6eb580000000p-2f, 0x1.9bcf360000000p-26f, 0.0f},     {0x1.4bd3ee0000000p-1f, 0x1.bc1e080000000p-2f, 0x1.e6d6860000000p-29f, 0.0f},
+    {0x1.4a27fa0000000p-1f, 0x1.c14a000000000p-2f, 0x1.ad5f040000000p-26f, 0.0f},     {0x1.4880520000000p-1f, 0x1.c66f500000000p-2f, -0x1.5c09000000000p-26f, 0.0f},
+    {0x1.46dce40000000p-1f, 0x1.cb8e080000000p-2f, -0x1.81942a0000000p-25f, 0.0f},     {0x1.453d9e0000000p-1f, 0x1.d0a6380000000p-2f, 0x1.b990f40000000p-25f, 0.0f},
+    {0x1.43a2740000000p-1f, 0x1.d5b7f80000000p-2f, -0x1.59d3960000000p-26f, 0.0f},     {0x1.420b520000000p-1f, 0x1.dac3580000000p-2f, -0x1.6c9d360000000p-25f, 0.0f},
+    {0x1.40782e0000000p-1f, 0x1.dfc8580000000p-2f, -0x1.6b92a40000000p-26f, 0.0f},     {0x1.3ee8f40000000p-1f, 0x1.e4c7180000000p-2f, 0x1.8743b80000000p-25f, 0.0f},
+    {0x1.3d5d9a0000000p-1f, 0x1.e9bfa00000000p-2f, 0x1.bac3100000000p-25f, 0.0f},     {0x1.3bd60e0000000p-1f, 0x1.eeb2080000000p-2f, 0x1.8006f00000000p-25f, 0.0f},
+    {0x1.3a52440000000p-1f, 0x1.f39e580000000p-2f, 0x1.2008f40000000p-25f, 0.0f},     {0x1.38d22e0000000p-1f, 0x1.f884a00000000p-2f, 0x1.b7d3da0000000p-27f, 0.0f},
+    {0x1.3755be0000000p-1f, 0x1.fd64f00000000p-2f, -0x1.b93d500000000p-27f, 0.0f},     {0x1.35dce60000000p-1f, 0x1.011fac0000000p-1f, -0x1.ef400e0000000p-26f, 0.0f},
+    {0x1.34679a0000000p-1f, 0x1.0389f00000000p-1f, 0x1.4b98d00000000p-27f, 0.0f},     {0x1.32f5ce0000000p-1f, 0x1.05f14c0000000p-1f, 0x1.38645a0000000p-25f, 0.0f},
+    {0x1.3187760000000p-1f, 0x1.0855c80000000p-1f, -0x1.ca5d780000000p-28f, 0.0f},     {0x1.301c820000000p-1f, 0x1.0ab76c0000000p-1f, 0x1.0ee14e0000000p-25f, 0.0f},
+    {0x1.2eb4ea0000000p-1f, 0x1.0d163c0000000p-1f, 0x1.019d6c0000000p-25f, 0.0f},     {0x1.2d50a00000000p-1f, 0x1.0f72400000000p-1f, 0x1.e9b4980000000p-25f, 0.0f},
+    {0x1.2bef980000000p-1f, 0x1.11cb840000000p-1f, -0x1.ff06600000000p-26f, 0.0f},     {0x1.2a91ca0000000p-1f, 0x1.1422000000000p-1f, 0x1.d887aa0000000p-26f, 0.0f},
+    {0x1.2937260000000p-1f, 0x1.1675cc0000000p-1f, -0x1.bb45a00000000p-25f, 0.0f},     {0x1.27dfa40000000p-1f, 0x1.18c6e00000000p-1f, 0x1.9ae7840000000p-28f, 0.0f},
+    {0x1.268b380000000p-1f, 0x1.1b154c0000000p-1f, -0x1.0025d60000000p-25f, 0.0f},     {0x1.2539d80000000p-1f, 0x1.1d61100000000p-1f, -0x1.0624000000000p-27f, 0.0f},
+    {0x1.23eb7a0000000p-1f, 0x1.1faa340000000p-1f, -0x1.063dac0000000p-27f, 0.0f},     {0x1.22a0120000000p-1f, 0x1.21f0c00000000p-1f, 0x1.05beec0000000p-29f, 0.0f},
+    {0x1.2157980000000p-1f, 0x1.2434b80000000p-1f, -0x1.037c6c0000000p-25f, 0.0f},     {0x1.2012020000000p-1f, 0x1.2676200000000p-1f, -0x1.7abcf20000000p-25f, 0.0f},
+    {0x1.1ecf440000000p-1f, 0x1.28b5000000000p-1f, 0x1.ed81e00000000p-27f, 0.0f},     {0x1.1d8f560000000p-1f, 0x1.2af1600000000p-1f, -0x1.7cdfa80000000p-28f, 0.0f},
+    {0x1.1c52300000000p-1f, 0x1.2d2b400000000p-1f, -0x1.7448d80000000p-27f, 0.0f},     {0x1.1b17c60000000p-1f, 0x1.2f62ac0000000p-1f, -0x1.84f6ac0000000p-25f, 0.0f},
+    {0x1.19e0120000000p-1f, 0x1.3197a00000000p-1f, 0x1.21ff9c0000000p-27f, 0.0f},     {0x1.18ab080000000p-1f, 0x1.33ca2c0000000p-1f, 0x1.65132a0000000p-30f, 0.0f},
+    {0x1.1778a20000000p-1f, 0x1.35fa500000000p-1f, -0x1.ecc9160000000p-25f, 0.0f},     {0x1.1648d60000000p-1f, 0x1.3828100000000p-1f, -0x1.d478680000000p-25f, 0.0f},
+    {0x1.151b9a0000000p-1f, 0x1.3a53740000000p-1f, 0x1.77af7e0000000p-27f, 0.0f},     {0x1.13f0e80000000p-1f, 0x1.3c7c800000000p-1f, 0x1.8773200000000p-25f, 0.0f},
+    {0x1.12c8b80000000p-1f, 0x1.3ea33c0000000p-1f, -0x1.a14d0a0000000p-25f, 0.0f},     {0x1.11a3020000000p-1f, 0x1.40c7a40000000p-1f, -0x1.af918a0000000p-28f, 0.0f},
+    {0x1.107fbc0000000p-1f, 0x1.42e9c80000000p-1f, -0x1.5e07f40000000p-25f, 0.0f},     {0x1.0f5ee00000000p-1f, 0x1.4509a40000000p-1f, 0x1.cceec20000000p-27f, 0.0f},
+    {0x1.0e40660000000p-1f, 0x1.4727440000000p-1f, -0x1.4ac5540000000p-25f, 0.0f},     {0x1.0d24460000000p-1f, 0x1.4942a80000000p-1f, -0x1.dfa07e0000000p-26f, 0.0f},
+    {0x1.0c0a780000000p-1f, 0x1.4b5bd80000000p-1f, -0x1.4523b20000000p-26f, 0.0f},     {0x1.0af2f80000000p-1f, 0x1.4d72d00000000p-1f, 0x1.fb9fd00000000p-25f, 0.0f},
+    {0x1.09ddba0000000p-1f, 0x1.4f87a40000000p-1f, 0x1.8604de0000000p-26f, 0.0f},     {0x1.08cabc0000000p-1f, 0x1.519a4c0000000p-1f, -0x1.785cbc0000000p-25f, 0.0f},
+    {0x1.07b9f20000000p-1f, 0x1.53aad00000000p-1f, 0x1.8999b80000000p-25f, 0.0f},     {0x1.06ab5a0000000p-1f, 0x1.55b9340000000p-1f, 0x1.ba817a0000000p-26f, 0.0f},
+    {0x1.059eea0000000p-1f, 0x1.57c5800000000p-1f, -0x1.7d21ce0000000p-26f, 0.0f},     {0x1.04949c0000000p-1f, 0x1.59cfb40000000p-1f, -0x1.228bbc0000000p-28f, 0.0f},
+    {0x1.038c6c0000000p-1f, 0x1.5bd7d40000000p-1f, -0x1.fd8e380000000p-25f, 0.0f},     {0x1.0286500000000p-1f, 0x1.5ddde40000000p-1f, 0x1.0149920000000p-25f, 0.0f},
+    {0x1.0182440000000p-1f, 0x1.5fe1ec0000000p-1f, 0x1.e462480000000p-27f, 0.0f},     {0x1.0080400000000p-1f, 0x1.61e3f00000000p-1f, 0x1.a464660000000p-29f, 0.0f},
+};
+constexpr float LN2_HI = 0x1.62e4p-1f, LN2_LO = 1.428606765330187e-06f;
+struct LogParts { float k, hi, sm; };
+__device__ __forceinline__ bool normal_positive(float x) {
+  return (uint32_t)(__float_as_int(x) - 0x00800000) < (uint32_t)(0x7f800000 - 0x00800000);
+}
+__device__ __forceinline__ LogParts log_parts(float x, const float4* tab) {
+  const int bits = __float_as_int(x);
+  const float4 t = tab[(bits >> 16) & 127];
+  const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+  const float r = fmaf(m, t.x, -1.0f);
+  float q = fmaf(r, -0.25f, 1.0f / 3.0f);
+  q = fmaf(r, q, -0.5f);
+  LogParts o;
+  o.k = (float)((bits >> 23) - 127);
+  o.hi = t.y;
+  o.sm = (t.z + r) + (r * r) * q;
+  return o;
+}
+static __device__ __noinline__ void log_diffs_rare(float e0, float e1, float e2, float& da, float& db, float& dc) {
+  da = logf(e0 / e1); db = logf(e0 / e2); dc = logf(e1 / e2);  // out of line: keeps the pixel pass short
+}
+__device__ __forceinline__ float log_diff(const LogParts& a, const LogParts& b) {
+  const float dk = a.k - b.k, dh = a.hi - b.hi;
+  const float big = fmaf(dk, LN2_HI, dh);
+  const float err = fmaf(dk, LN2_HI, -big) + dh;  // exact: dk LN2_HI and dh are multiples of 2^-23 below 16
+  return big + (err + ((a.sm - b.sm) + dk * LN2_LO));
+}
+
 constexpr int NSUB = 2;                  // 64-pixel sub-stages per stage: one barrier round trip per NSUB x 64 pixels
 constexpr int SKB = 64 * NSUB;           // pixels per stage
 constexpr int SNS = 4 / NSUB;            // stages in flight: B tiles in shared memory, A slots in tensor memory
@@ -794,6 +898,7 @@ struct SmemS {
   float acc[3][BINS][BINS + 1];
   PxSlotS px[SPR];
   float ctr[BINS];  // scaled midpoint centres
+  alignas(16) float4 ltab[128];  // PH_LOGF_TABLE
   float red[PROD_WARPS];
   double red2[PROD_WARPS];
   int last_flag;
@@ -820,6 +925,7 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_sym_kernel(Params p) {
     // the caller asserted antisymmetric centres (PH_IMPL_MIRROR): never silently wrong if they are not
     if (!(fabsf(cj + cm) <= p.mirror_tol)) *reinterpret_cast<volatile int*>(p.status) = PH_ASYNC_MIRROR;
   }
+  if (tid >= 128 && tid < 256) S.ltab[tid - 128] = PH_LOGF_TABLE[tid - 128];
   if (warp == MMA_WARP) tmem_alloc(&S.tmem_base, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
@@ -861,9 +967,16 @@ __global__ void __launch_bounds__(THREADS, 1) hist_fwd_sym_kernel(Params p) {
           const float x0 = fmaf(r, 0.5f, 0.5f), x1 = fmaf(g, 0.5f, 0.5f), x2 = fmaf(bl, 0.5f, 0.5f);
           const float iy = sqrtf(x0 * x0 + x1 * x1 + x2 * x2 + p.eps);
           const float e0 = x0 + p.eps, e1 = x1 + p.eps, e2 = x2 + p.eps;
-          va[k] = logf(e0 / e1) * p.coord_scale;
-          vb[k] = logf(e0 / e2) * p.coord_scale;
-          vc[k] = logf(e1 / e2) * p.coord_scale;
+          float da, db, dc;
+          if (normal_positive(e0) && normal_positive(e1) && normal_positive(e2)) {
+            const LogParts l0 = log_parts(e0, S.ltab), l1 = log_parts(e1, S.ltab), l2 = log_parts(e2, S.ltab);
+            da = log_diff(l0, l1); db = log_diff(l0, l2); dc = log_diff(l1, l2);
+          } else {  // images outside [-1, 1]: whatever logf of the ratio gives (NaN, inf), as in the exact-centre kernel
+            log_diffs_rare(e0, e1, e2, da, db, dc);
+          }
+          va[k] = da * p.coord_scale;
+          vb[k] = db * p.coord_scale;
+          vc[k] = dc * p.coord_scale;
           // every product of two operands carries the intensity once; masked pixels contribute nothing
           vs[k] = valid ? sqrtf(iy) : 0.f;
           // operand = sqrt(Iy) x (scaled weight <= 2^14) must stay below fp16's 65504 — flagged, never silent
