@@ -375,3 +375,31 @@ def test_log_table():
                         rng.uniform(0.99, 1.000001, 20000), np.array([1e-6, 1.0, 1.000001, 0.5, 0.25 + 1e-6])])
     err = np.abs(mt.log_pos_numpy(x, rows).astype(np.longdouble) - np.log(x.astype(np.longdouble)))
     assert float(err.max()) < 3e-15, float(err.max())
+
+
+def test_logf_difference_table():
+    """The float32 log differences of the mirrored forward's pixel pass (hist_tc.cu: log_parts / log_diff): the table in
+    the source is the generator's; the formula replayed in numpy float32 is within 1e-9 + half an ulp of the long-double
+    difference (histogram.py:72-74 takes log(x_a + eps) - log(x_b + eps))."""
+    import re
+    from oracle import make_log_table as mt
+    rows = mt.table_f32()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "palette_and_histo_gan_b200", "csrc", "hist_tc.cu")).read()
+    body = src[src.index("PH_LOGF_TABLE[128] = {"):]
+    body = body[:body.index("};")]
+    vals = [float.fromhex(v) for v in re.findall(r"(-?0x[0-9a-f.]+p[-+]?\d+)f", body)]
+    assert len(vals) == 384
+    assert vals == [v for row in rows for v in row]
+    assert "LN2_HI = 0x1.62e4p-1f, LN2_LO = %rf" % mt.LN2_LO in src
+    assert mt.LN2_HI == float.fromhex("0x1.62e4p-1")
+    rng = np.random.default_rng(1)
+    n = 100000
+    x0 = np.concatenate([rng.uniform(1e-6, 1.000001, n), 10.0 ** rng.uniform(-6, 0, n)]).astype(np.float32)
+    x1 = rng.permutation(x0)
+    d = mt.logdiff_f32_numpy(x0, x1, rows)
+    LD = np.longdouble
+    ref = np.log(x0.astype(LD)) - np.log(x1.astype(LD))
+    err = np.abs(d.astype(LD) - ref)
+    ulp = np.spacing(np.abs(ref.astype(np.float32))).astype(LD)
+    assert float((err - 0.5 * ulp).max()) < 1e-9, float((err - 0.5 * ulp).max())
