@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 
 METRIC = "histogram-loss fwd+bwd images/s at 64x64"
 # share of hist_bwd_tc_kernel + its prologue in the step's launch list under ncu (profiles/README.md, this round's capture)
-NCU_BWD_SHARE = 0.630
+NCU_BWD_SHARE = 0.623
 GLOBAL_BATCH = int(os.environ.get("PH_BENCH_BATCH", "4096"))  # cfgC (override only for tuning runs)
 HW = 64
 BINS = 64
@@ -324,14 +324,14 @@ def run_ours(args, rank, world, local_rank):
         "bound": "tensor", "kernel": "hist backward (prologue + contraction kernel)",
         "achieved": bwd_tflops, "peak": f16_peak, "unit": "TFLOP/s", "frac": bwd_tflops / f16_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of hist_bwd_tc_kernel, one `ncu --set full` capture at 4096
-        # images per launch (profiles/r2b_prof_hist_raw.csv: 470.1 MB + 239.0 MB), scaled to this rank's share
-        "traffic": 709.1e6 * local_b / 4096.0,
-        "traffic_source": "profiles/r2b_prof_hist_raw.csv (ncu, 4096 images/launch), scaled by local batch",
+        # images per launch (profiles/r2d_prof_hist_raw.csv: 470.8 MB + 240.8 MB), scaled to this rank's share
+        "traffic": 711.6e6 * local_b / 4096.0,
+        "traffic_source": "profiles/r2d_prof_hist_raw.csv (ncu, 4096 images/launch), scaled by local batch",
         "algorithmic_bytes": float(local_b) * npix * 4 * 4 * 2 + float(local_b) * 3 * BINS * BINS * 4,
         "peak_source": f"{peaks['source']}: {'bf16_tflops (burst: timed region %.2f s)' % (ms / 1e3) if burst else 'bf16_tflops_sustained'} "
                        "(kind::f16 runs at the bf16 dense rate)",
         # duration of the dominant kernel (+ its 0.1 ms prologue) per launch, CUDA events on the launching stream, and
-        # its share of the step under ncu (profiles/r2b_launches_step_summary.csv) — the two must agree
+        # its share of the step under ncu (profiles/r2d_launches_step_summary.csv) — the two must agree
         "kernel_ms": float(phase_ms[3]), "kernel_share_of_step": float(phase_ms[3] / (ms / args.steps)),
         "kernel_ncu_share": NCU_BWD_SHARE,
         # fp32-accurate results need three fp16 products per algorithmic product (hi.hi + hi.lo + lo.hi): the
@@ -344,9 +344,10 @@ def run_ours(args, rank, world, local_rank):
         "phase_ms": {"fwd_real": phase_ms[0], "fwd_fake+hellinger_sum": phase_ms[1], "allreduce+loss": phase_ms[2],
                      "bwd": phase_ms[3]},
         "engine": impl,
-        "note": "both contraction kernels are bound by the CUDA-core generation of their operands (issue slots 62-65 % busy; "
-                "tensor pipe 48 % active in the mirrored-tile forward — three weight vectors per pixel instead of six — and "
-                "36 % in the backward under ncu, profiles/README.md), not by the tensor pipe or HBM",
+        "note": "no single resource bounds either contraction kernel (ncu: issue slots 61-64 %, MUFU 26 / 53 %, tensor pipe "
+                "48 % in the mirrored-tile forward and 37 % in the backward, HBM 2-3 %): per 128-pixel round the backward "
+                "needs 1 000-1 400 cycles EACH of tensor-memory read-back (64 B per clock), MUFU, issue slots and MMAs and "
+                "takes ~2 370; removing all weight arithmetic buys 15 % (profiles/r2d_bwd_timing_experiments.txt)",
     }
 
     # ---- e2e: host buffers through the C ABI (pinned in, loss + gradient out) ----
