@@ -203,15 +203,24 @@ __device__ __forceinline__ void finish_item(SmemT& S, const Params& p, const Ite
     if (t == 0) p.denom[b] = d * dscale;
     const float inv_d = 1.0f / d;
     float* dst = p.hist + b * (int64_t)(3 * BINS * BINS);
+    // Element k of this thread is e = t + 512 k of the channel-last histogram, e = (i 64 + j) 3 + c.  512 x 3 is a
+    // multiple of 3 and of 3 x 64: elements k and k + 3 share channel and v-bin and lie 8 u-bins apart, so three base
+    // pointers serve all 24 (the divisions by 3 were a quarter of a de-duplicated item's instructions)
+    constexpr int PER_THREAD = 3 * BINS * BINS / (PROD_WARPS * 32);  // 24
+    const float* a3[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int e = t + r * (PROD_WARPS * 32), c = e % 3, ij = e / 3;
+      a3[r] = &S.acc[c][ij & 63][ij >> 6];
+    }
     if (!FUSE_SSUM) {
-      for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) {
-        const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-        dst[e] = S.acc[c][j][i] * inv_d;
-      }
+#pragma unroll
+      for (int k = 0; k < PER_THREAD; ++k) dst[t + k * (PROD_WARPS * 32)] = a3[k % 3][8 * (k / 3)] * inv_d;
     } else {
       // fused Hellinger partial: sum (sqrt(Hp) - sqrt(Ht))^2 of this image (histogram.py:88) while Hp is
       // on chip; the real image's histogram arrives in two batches of 12 independent loads per thread
-      constexpr int HALF = 3 * BINS * BINS / (PROD_WARPS * 32) / 2;  // 12
+      constexpr int HALF = PER_THREAD / 2;  // 12
+      static_assert(HALF % 3 == 0, "the three base pointers repeat every three elements");
       const float* ht = p.hist_true + b * (int64_t)(3 * BINS * BINS);
       float part = 0.f;
 #pragma unroll 1
@@ -222,8 +231,7 @@ __device__ __forceinline__ void finish_item(SmemT& S, const Params& p, const Ite
 #pragma unroll
         for (int k = 0; k < HALF; ++k) {
           const int e = t + (half * HALF + k) * (PROD_WARPS * 32);
-          const int c = e % 3, ij = e / 3, i = ij >> 6, j = ij & 63;
-          const float h = S.acc[c][j][i] * inv_d;
+          const float h = a3[k % 3][8 * (half * (HALF / 3) + k / 3)] * inv_d;  // HALF is a multiple of 3
           dst[e] = h;
           const float df = fast_sqrt(h) - fast_sqrt(htv[k]);
           part = fmaf(df, df, part);

@@ -243,6 +243,32 @@ def test_dedup_forward_matches_dense(H, cuda, sprites):
     assert ho.rel_l2(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < 1e-5
 
 
+def test_single_chain_whole_images_are_normalised_from_registers(H, cuda):
+    """Whole images of one accumulation chain (here 150 images of 20 x 12 and of 32 x 32 pixels: batch >= SM count,
+    <= 1024 pixels) leave the exact-centre forward straight from the drained registers (finish_single_chain,
+    hist_tc.cu): histogram against the float64 oracle, the normaliser through the backward (it divides by D)
+    against the CUDA-core engine, sums to one, run-to-run bit identity.  histogram.py:36-81."""
+    rng = np.random.default_rng(150)
+    for hw in ((20, 12), (32, 32)):
+        img = np.tanh(rng.standard_normal((150, hw[0], hw[1], 4))).astype(np.float32)
+        up = torch.from_numpy(rng.standard_normal((150, 64, 64, 3)).astype(np.float32)).to(cuda)
+        out = {}
+        for impl in ("tc", "simt"):
+            x = torch.from_numpy(img).to(cuda).requires_grad_(True)
+            h = H.calculate_rgbuv_histogram(x, impl=impl, mirror=False)
+            h.backward(up)
+            out[impl] = (h.detach(), x.grad.cpu().numpy())
+        h_tc = out["tc"][0]
+        pick = [0, 1, 73, 147, 148, 149]
+        ref, _ = ho.rgbuv_histogram_f64(img[pick])
+        assert ho.rel_l2(h_tc[pick].cpu().numpy(), ref) < HIST_TOL and ho.rel_max(h_tc[pick].cpu().numpy(), ref) < HIST_TOL
+        assert float((h_tc.sum((1, 2, 3)) - 1).abs().max()) < 3e-6
+        assert ho.rel_l2(h_tc.cpu().numpy(), out["simt"][0].cpu().numpy()) < 3e-6
+        assert ho.rel_l2(out["tc"][1], out["simt"][1]) < GRAD_TOL
+        again = H.calculate_rgbuv_histogram(torch.from_numpy(img).to(cuda), impl="tc", mirror=False)
+        assert torch.equal(again, h_tc)
+
+
 def test_u8_loader_prep_and_u8_host_path(cuda, sprites):
     """f2: uint8 sprites in, blacken + normalise fused on the device."""
     from palette_and_histo_gan_b200 import dataset_utils as D, hostapi
