@@ -193,7 +193,13 @@ __device__ __forceinline__ void finish_item(SmemT& S, const Params& p, const Ite
     }
   } else if (finish) {
     float s = 0.f;
-    for (int e = t; e < 3 * BINS * BINS; e += PROD_WARPS * 32) s += S.acc[e >> 12][(e >> 6) & 63][e & 63];
+    {
+      // element k of this thread in [c][i][j] order: e = t + 512 k -> c = k / 8, i = t / 64 + 8 (k % 8), j = t % 64
+      const float* a0 = &S.acc[0][t >> 6][t & 63];
+      constexpr int PLANE = BINS * (BINS + 1), ROW8 = 8 * (BINS + 1);
+#pragma unroll
+      for (int k = 0; k < 3 * BINS * BINS / (PROD_WARPS * 32); ++k) s += a0[(k >> 3) * PLANE + (k & 7) * ROW8];
+    }
     s = warp_sum(s);
     if (lane == 0) S.red[warp] = s;
     named_bar_sync(5, PROD_WARPS * 32);
