@@ -243,11 +243,11 @@ def test_dedup_forward_matches_dense(H, cuda, sprites):
     assert ho.rel_l2(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < 1e-5
 
 
-def test_single_chain_whole_images_are_normalised_from_registers(H, cuda):
-    """Whole images of one accumulation chain (here 150 images of 20 x 12 and of 32 x 32 pixels: batch >= SM count,
-    <= 1024 pixels) leave the exact-centre forward straight from the drained registers (finish_single_chain,
-    hist_tc.cu): histogram against the float64 oracle, the normaliser through the backward (it divides by D)
-    against the CUDA-core engine, sums to one, run-to-run bit identity.  histogram.py:36-81."""
+def test_small_whole_images_forward_and_normaliser(H, cuda):
+    """Whole-image work items of a single accumulation chain (150 images of 20 x 12 and of 32 x 32 pixels: batch >= SM
+    count, <= 1024 pixels, exact-centre forward): histogram against the float64 oracle, the normaliser through the
+    backward (it divides by D) against the CUDA-core engine, sums to one, run-to-run bit identity.
+    histogram.py:36-81."""
     rng = np.random.default_rng(150)
     for hw in ((20, 12), (32, 32)):
         img = np.tanh(rng.standard_normal((150, hw[0], hw[1], 4))).astype(np.float32)
