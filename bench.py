@@ -29,7 +29,7 @@ if ROOT not in sys.path:
 
 METRIC = "histogram-loss fwd+bwd images/s at 64x64"
 # share of hist_bwd_tc_kernel + its prologue in the step's launch list under ncu (profiles/README.md, this round's capture)
-NCU_BWD_SHARE = 0.629
+NCU_BWD_SHARE = 0.628
 GLOBAL_BATCH = int(os.environ.get("PH_BENCH_BATCH", "4096"))  # cfgC (override only for tuning runs)
 HW = 64
 BINS = 64
@@ -331,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
         "peak_source": f"{peaks['source']}: {'bf16_tflops (burst: timed region %.2f s)' % (ms / 1e3) if burst else 'bf16_tflops_sustained'} "
                        "(kind::f16 runs at the bf16 dense rate)",
         # duration of the dominant kernel (+ its 0.1 ms prologue) per launch, CUDA events on the launching stream, and
-        # its share of the step under ncu (profiles/r2f_launches_step_summary.csv) — the two must agree
+        # its share of the step under ncu (profiles/r2g_launches_step_summary.csv) — the two must agree
         "kernel_ms": float(phase_ms[3]), "kernel_share_of_step": float(phase_ms[3] / (ms / args.steps)),
         "kernel_ncu_share": NCU_BWD_SHARE,
         # fp32-accurate results need three fp16 products per algorithmic product (hi.hi + hi.lo + lo.hi): the
