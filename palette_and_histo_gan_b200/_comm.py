@@ -31,13 +31,30 @@ class PeerComm:
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.device = dev
         self._h = C.c_void_p()
-        _lib.call("ph_comm_create", dev.index, self.rank, self.world, C.byref(self._h))
-        mine = C.create_string_buffer(_lib.COMM_HANDLE_BYTES)
-        _lib.call("ph_comm_export", self._h, mine)
+        # Every rank takes part in the exchange of the handles whatever happened before it: a rank whose mailbox could
+        # not be created sends an empty handle instead of leaving its peers waiting in the collective.
+        failure = None
+        mine = b""
+        try:
+            _lib.call("ph_comm_create", dev.index, self.rank, self.world, C.byref(self._h))
+            buf = C.create_string_buffer(_lib.COMM_HANDLE_BYTES)
+            _lib.call("ph_comm_export", self._h, buf)
+            mine = bytes(buf.raw)
+        except _lib.PalHistError as e:
+            failure = e
         handles = [None] * self.world
         with torch.cuda.device(dev):
-            dist.all_gather_object(handles, bytes(mine.raw), group=group)
-        _lib.call("ph_comm_connect", self._h, b"".join(handles))
+            dist.all_gather_object(handles, mine, group=group)
+        if failure is None and any(len(h) != _lib.COMM_HANDLE_BYTES for h in handles):
+            failure = RuntimeError("a peer rank could not create its mailbox")
+        if failure is not None:
+            self.close()
+            raise failure
+        try:
+            _lib.call("ph_comm_connect", self._h, b"".join(handles))
+        except _lib.PalHistError:
+            self.close()
+            raise
 
     @property
     def handle(self):
@@ -74,19 +91,22 @@ def peer_comm(group, device):
     if key in _cache:
         return _cache[key]
     comm = None
-    ok = 1
-    if os.environ.get("PH_COLLECTIVE", "peer") == "nccl" or dist.get_backend(pg) != "nccl":
-        ok = 0
-    else:
+    # two joint decisions (MIN over the ranks), so that every rank takes the same path: whether to try at all, and
+    # whether every rank managed to map every mailbox
+    want = 0 if os.environ.get("PH_COLLECTIVE", "peer") == "nccl" or dist.get_backend(pg) != "nccl" else 1
+    flag = torch.tensor([want], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)
+    if int(flag) == 1:
+        ok = 1
         try:
             comm = PeerComm(pg, device)
         except (_lib.PalHistError, ValueError, RuntimeError):
             ok = 0
-    flag = torch.tensor([ok], dtype=torch.int32, device=device)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)
-    if int(flag) == 0:
-        if comm is not None:
-            comm.close()
-        comm = None
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=pg)
+        if int(flag) == 0:
+            if comm is not None:
+                comm.close()
+            comm = None
     _cache[key] = comm
     return comm
